@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py — Mrays/s of the fused per-ray render path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
+
+Workload (config 3 of BASELINE.json, the one the metric is quoted on): synthetic 1 M random
+Gaussians, SH degree 3, seed 1002, 1920x1080, vertical fov 60 deg, orbit radius 2.2, depth 16.
+A "step" = ONE full 1080p frame (ray generation + LBVH traversal + intersection + 16-nearest
+k-buffer + SH compositing + framebuffer write) of one view of the 64-view orbit (config 5); the
+step s on rank r renders view (s*N + r) mod 64, view 0 being config 3's camera.  Multi-GPU is
+view-sharded with the scene replicated on every GPU and no collective on the data path, so
+per-GPU work is fixed as N grows ("scaling": "weak").  One ray = one finished pixel.
+
+value  = whole-job Mrays/s with everything resident in HBM (device-timed, CUDA events, max over ranks)
+e2e    = the same through the public API call with HOST buffers (RayTracer.render: camera struct
+         in, image copied back to host memory inside the timed region)
+roofline = algorithmic bytes per ray (16 + kbar*(64 + 192[sh])) x rays per launch /
+         mean kernel time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+cpu_baseline = oracle/ref_cpu.cpp (reference-shaped C++/OpenMP port, float32) on a pixel subsample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "rt-gaussian-splat-renderer_b200"))
+
+N_VIEWS = 64
+DEPTH = 16
+T_CUT = 1e-4
+FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="1m_deg3_1080p")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-stride", type=int, default=0, help="pixel subsample stride of the CPU legs (0 = auto)")
+    return ap.parse_args()
+
+
+def make_views(W, H):
+    from rtgs.orbit import focal_from_fov, orbit_pose
+    from rtgs.synthetic import FOV_DEG, ORBIT_R
+    f = focal_from_fov(H, FOV_DEG)
+    return f, [orbit_pose(2 * np.pi * k / N_VIEWS, np.pi / 2, ORBIT_R) for k in range(N_VIEWS)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            tok = [t.strip() for t in line.split(",")]
+            if len(tok) < 7:
+                continue
+            try:
+                sm.append(float(tok[0]))
+                smax.append(float(tok[1]))
+            except ValueError:
+                continue
+            for name, v in zip(names, tok[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def load_traffic():
+    """dram bytes per launch of the render kernel from the committed ncu summary, if any."""
+    p = ROOT / "profiles" / "render_kernel_traffic.json"
+    if p.exists():
+        try:
+            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            return None
+    return None
+
+
+def cpu_leg(cfg_name, scene_arrays, W, H, focal, views, steps, warmup, stride):
+    """The reference-shaped CPU port (float32, all host threads) on a pixel subsample."""
+    from oracle import ref_cpu
+    from oracle import ref_numpy as O
+    ref_cpu.build()
+    t0 = time.perf_counter()
+    cs = ref_cpu.CpuScene(scene_arrays["pos"], scene_arrays["rot"], scene_arrays["scale"], scene_arrays["color"],
+                          scene_arrays["opacity"], scene_arrays["sh"])
+    build_s = time.perf_counter() - t0
+    pix = ref_cpu.all_pixels(W, H, stride)
+    times = []
+    for s in range(warmup + steps):
+        pos, rot = views[s % N_VIEWS]
+        cam = O.CameraParams(np.asarray(pos), np.asarray(rot), W, H, (focal, focal))
+        t0 = time.perf_counter()
+        cs.render(cam, DEPTH, pixels=pix, precision="float")
+        dt = time.perf_counter() - t0
+        if s >= warmup:
+            times.append(dt)
+    total = sum(times)
+    return {"mrays": pix.shape[0] * len(times) / total / 1e6, "ms_per_step": 1e3 * total / len(times),
+            "cores": ref_cpu.max_threads(), "rays_per_step": int(pix.shape[0]), "build_s": build_s,
+            "sample": f"every {stride}th column and row of each 1080p view ({pix.shape[0]} rays/step), "
+                      f"{len(times)} steps, float32, K={DEPTH} closest-hit restarts over the LBVH"}
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    from rtgs.synthetic import CONFIGS, make_scene
+    n_g, seed, sh_deg, (W, H) = CONFIGS[args.config]
+    config = {"workload": f"synthetic {n_g} random Gaussians, SH degree {sh_deg}, seed {seed}, {W}x{H}, fov 60, "
+                          f"orbit r=2.2, depth {DEPTH}, t_cut {T_CUT}; 64-view orbit, view (step*N+rank)%64",
+              "gaussians": n_g, "sh_degree": sh_deg, "resolution": [W, H], "depth": DEPTH,
+              "sharding": "camera views (scene replicated, no collective)",
+              "l2": "inputs larger than L2 (packed scene 360 MB > 126 MB) and a new view every step"}
+
+    # ------------------------------------------------------------------ reference arm (CPU port)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        arrays = make_scene(n_g, seed, sh_deg)
+        focal, views = make_views(W, H)
+        stride = args.cpu_stride or 8
+        r = cpu_leg(args.config, arrays, W, H, focal, views, args.steps, args.warmup, stride)
+        line = {"impl": "reference", "metric": "Mrays/s", "value": r["mrays"], "unit": "Mrays/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "port",
+                                 "sample": r["sample"]},
+                "e2e": {"value": r["mrays"], "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0,
+                "note": "the reference is Python+Taichi and cannot run here; this is oracle/ref_cpu.cpp, a C++/OpenMP "
+                        "port with the reference's algorithm shape, on the host cores"}
+        print(json.dumps(line))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA)
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from rtgs.camera import Camera
+    from rtgs.ray_tracer import RayTracer
+    from rtgs.scene import Scene
+
+    arrays = make_scene(n_g, seed, sh_deg)
+    focal, views = make_views(W, H)
+    t0 = time.perf_counter()
+    scene = Scene(device=local_rank).from_arrays(arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"],
+                                                 arrays["opacity"], arrays["sh"])
+    torch.cuda.synchronize()
+    build_ms = 1e3 * (time.perf_counter() - t0)
+    cam = Camera(views[0][0], views[0][1], (W, H), (focal, focal), device=local_rank)
+    rt = RayTracer((W, H), scene, cam, t_cut=T_CUT)
+    out = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
+
+    def set_view(step):
+        v = (step * world + rank) % N_VIEWS
+        cam.position, cam.rotation = views[v]
+        return v
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views
+    agg = {}
+    for s in range(args.steps):
+        set_view(s)
+        rt.render_device(DEPTH, out=out, collect_stats=True)
+        for k, v in rt.last_stats.items():
+            agg[k] = agg.get(k, 0) + v
+    kbar = agg["layers"] / agg["rays"]
+    bytes_ray = 16 + kbar * (64 + (192 if sh_deg > 0 else 0))
+
+    for s in range(args.warmup):
+        set_view(s)
+        rt.render_device(DEPTH, out=out)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    e_beg, e_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches = 0
+    barrier()
+    e_beg.record()
+    for s in range(args.steps):
+        set_view(s)
+        ev[s][0].record()
+        rt.render_device(DEPTH, out=out)
+        ev[s][1].record()
+        launches += 1
+    e_end.record()
+    barrier()
+    total_ms = e_beg.elapsed_time(e_end)
+    kern_ms = [a.elapsed_time(b) for a, b in ev]
+    clocks = sampler.stop() if rank == 0 else None
+
+    # end-to-end: public API call with host buffers (camera in, image out on the host)
+    for s in range(min(args.warmup, 2)):
+        set_view(s)
+        rt.render(DEPTH)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        set_view(s)
+        img = rt.render(DEPTH)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    if dist is not None:
+        t = torch.tensor([total_ms, e2e_s, float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms, e2e_s, kern_mean = t.tolist()
+    else:
+        kern_mean = float(np.mean(kern_ms))
+
+    if rank == 0:
+        rays_step = W * H * world
+        value = rays_step * args.steps / (total_ms * 1e-3) / 1e6
+        e2e_val = rays_step * args.steps / e2e_s / 1e6
+        peak, peak_src = load_peak()
+        achieved = W * H * bytes_ray / (kern_mean * 1e-3) / 1e9
+        line = {
+            "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 44,
+                    "d2h_bytes_per_step": W * H * 3 * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": load_traffic(), "peak_source": peak_src, "kernel": "k_render<16>",
+                         "kernel_ms": kern_mean, "bytes_per_ray": bytes_ray, "kbar": kbar},
+            "clocks": clocks,
+            "scene_stats": {"hit_fraction": agg["rays_hit"] / agg["rays"], "kbar": kbar,
+                            "child_boxes_tested_per_ray": agg["nodes_tested"] / agg["rays"],
+                            "candidates_per_tile": agg["candidates"] / max(agg["tiles"], 1),
+                            "pair_tests_per_ray": agg["pair_tests"] / agg["rays"],
+                            "f64_refinements_per_Mray": 1e6 * agg["f64_refinements"] / agg["rays"]},
+            "bvh_build_ms": build_ms,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            stride = args.cpu_stride or 8
+            r = cpu_leg(args.config, arrays, W, H, focal, views, min(args.steps, 4), 1, stride)
+            line["cpu_baseline"] = {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"]}
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,149 @@
+/*
+ * rtgs_b200.h — C-ABI of the B200-native rtgs per-ray render path.
+ *
+ * The reference (fangjunzhou/rt-gaussian-splat-renderer, Python + Taichi) has no FFI layer: its
+ * boundary is the Python object API  Scene / Camera / RayTracer.  This header is the C boundary a
+ * binding for that API calls into (the Python mirror in rt-gaussian-splat-renderer_b200/rtgs/ does
+ * so through ctypes; INTEGRATION.md shows the stub).  Each entry point cites the reference
+ * interface (file:line under /root/reference) that it replaces.
+ *
+ * Conventions
+ *  - every function returns RTGS_OK (0) or a negative rtgs_status; nothing throws or aborts across
+ *    the ABI; rtgs_last_error() returns a thread-local message for the last failure.
+ *  - plain pointers and sizes only.  "host" pointers are ordinary host memory borrowed for the
+ *    duration of the call; "device" pointers are CUDA device memory on the scene's device.
+ *  - a scene handle is bound to one CUDA device; calls on one handle must not overlap; different
+ *    handles may be driven concurrently from different host threads.
+ *  - image layout is the reference's field layout: pixel (i,j) = (column from the left, row from
+ *    the BOTTOM), shape (W,H), i-major (index i*H + j)  (camera.py:33-35,67-70; ray_tracer.py:33-37).
+ *  - `stream` is a cudaStream_t passed as void* (NULL = the legacy default stream).
+ */
+#ifndef RTGS_B200_H
+#define RTGS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RTGS_ABI_VERSION 1
+#define RTGS_MAX_DEPTH 32        /* largest `depth` rtgs_render composites in one pass */
+
+typedef enum rtgs_status {
+    RTGS_OK = 0,
+    RTGS_ERR_INVALID = -1,       /* bad argument */
+    RTGS_ERR_CUDA = -2,          /* a CUDA runtime call failed (message has the CUDA error) */
+    RTGS_ERR_STATE = -3,         /* call order: e.g. render before build_bvh */
+    RTGS_ERR_NOMEM = -4
+} rtgs_status;
+
+typedef struct rtgs_scene rtgs_scene;      /* opaque; owns all device memory */
+
+/* Camera — camera.py:17-29 (position, rotation quaternion (x,y,z,w), buf_size, focal_length).
+ * `rotation` is used as given (not re-normalised), as in Camera.generate_ray (camera.py:52). */
+typedef struct rtgs_camera {
+    float position[3];
+    float rotation[4];
+    float focal[2];
+    int32_t width, height;
+} rtgs_camera;
+
+/* Per-render counters (optional; mean values are over the rays of the rendered region). */
+typedef struct rtgs_render_stats {
+    uint64_t rays;               /* pixels rendered */
+    uint64_t rays_hit;           /* rays with >= 1 composited Gaussian */
+    uint64_t layers;             /* total composited layers (sum over rays of min(hits, depth)) */
+    uint64_t nodes_tested;       /* BVH child boxes tested against tile frusta */
+    uint64_t candidates;         /* (tile, Gaussian) candidates staged */
+    uint64_t pair_tests;         /* ray-Gaussian intersection tests */
+    uint64_t f64_refinements;    /* borderline decisions re-evaluated in float64 */
+    uint64_t tiles;              /* warp tiles processed */
+} rtgs_render_stats;
+
+const char* rtgs_last_error(void);
+int rtgs_abi_version(void);
+int rtgs_device_count(int* n);
+
+/* Scene.load_file back half — scene.py:116-160 (staging fields + build_gaussian kernel).
+ * Inputs are the POST-activation parameters (scene.py:110-114): unit quaternion (x,y,z,w),
+ * linear scale, sigmoid colour and opacity; `sh` is (n,15,3) float32 in the order
+ * sh_10..sh_36 of gaussian.py:37-51, or NULL for SH degree 0.  Host pointers; copied. */
+int rtgs_scene_create(int device, int64_t n,
+                      const float* pos, const float* rot_xyzw, const float* scale,
+                      const float* color, const float* opacity, const float* sh,
+                      rtgs_scene** out);
+
+/* Scene.load_file front half on the GPU — scene.py:95-114: `vertices` is the raw binary
+ * little-endian PLY vertex block (n rows of `stride_floats` float32), `col` the 62 column
+ * offsets in the order x,y,z, f_dc_0..2, f_rest_0..44, opacity, scale_0..2, rot_0..3 (any
+ * offset < 0 = property absent -> 0).  Applies the activations of scene.py:110-114 on device.
+ * sh_layout: 0 = channel-major (sh_k[c] = f_rest_{15c+k}), 1 = "taichi as executed"
+ * (sh_k[c] = f_rest_{3k+c}); see SURVEY.md §7 hard part 7. */
+int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices,
+                                    int32_t stride_floats, const int32_t* col /*[62]*/,
+                                    float scale, int32_t sh_layout, rtgs_scene** out);
+
+/* BVH build — replaces scene.py:162-404 (binned-SAH host loop) with a GPU LBVH:
+ * per-Gaussian preprocessing (quat -> R, W = S^-1 R^T, tight sqrt(3)-sigma AABB;
+ * gaussian.py:86-138), 30-bit Morton codes, radix sort, Karras hierarchy, bottom-up refit.
+ * leaf_size is accepted for Scene(leaf_prim=...) compatibility (scene.py:78-87). */
+int rtgs_scene_build_bvh(rtgs_scene* s, int32_t leaf_size);
+
+int rtgs_scene_num_gaussians(const rtgs_scene* s, int64_t* n);
+int rtgs_scene_device(const rtgs_scene* s, int* device);
+
+/* Parity / debug read-back of the LBVH integers (host pointers, any may be NULL):
+ * morton (n) in ORIGINAL order, sorted_idx (n), child ((n-1)*2, unified ids: leaf k -> n-1+k),
+ * parent (2n-1, root -1), aabb ((2n-1)*6: min xyz, max xyz). */
+int rtgs_scene_read_lbvh(rtgs_scene* s, uint32_t* morton, uint32_t* sorted_idx,
+                         int32_t* child, int32_t* parent, float* aabb);
+
+/* Read back stored Gaussian parameters in original order (Scene.gaussian_field, scene.py:131):
+ * host pointers, any may be NULL.  sh is (n,15,3). */
+int rtgs_scene_read_gaussians(rtgs_scene* s, float* pos, float* rot_xyzw, float* scale,
+                              float* color, float* opacity, float* sh);
+
+/* RayTracer.sample for a whole sample — ray_tracer.py:39-104 (clear_attenuation +
+ * generate_ray_field + depth x sample_step) fused into one pass: camera ray generation
+ * (camera.py:31-71), traversal (scene.py:406-450), intersection (gaussian.py:203-230),
+ * evaluation (gaussian.py:140-201) and front-to-back compositing (ray_tracer.py:96-98) of the
+ * `depth` nearest entries per pixel.
+ * Region: pixels i in [x0,x0+w), j in [y0,y0+h) of the camera's (W,H) image.
+ * out_rgb: device, (w,h,3) float32 i-major region buffer, or the full (W,H,3) image when
+ *          `full_image_pitch` != 0 (then pixel (i,j) is written at its full-image index).
+ * out_T:   device, final transmittance per pixel (attenuation_buf, ray_tracer.py:35), same
+ *          indexing as out_rgb; may be NULL.
+ * accumulate != 0: out_rgb += colour (sample_buf semantics, ray_tracer.py:96); else out_rgb = colour.
+ * t_cut: transmittance early-termination threshold (0 disables; reference has none).
+ * stats: optional host struct, filled after the stream is synchronised (forces a sync). */
+int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
+                int32_t x0, int32_t y0, int32_t w, int32_t h,
+                int32_t depth, float t_cut, int32_t accumulate, int32_t full_image_pitch,
+                float* out_rgb, float* out_T, void* stream, rtgs_render_stats* stats);
+
+/* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
+ * RayTracer makes: camera in, image out).  Renders the region into a library-owned device
+ * buffer and copies it to `host_rgb` ((w,h,3) float32) and optionally `host_T` ((w,h));
+ * synchronous. */
+int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam,
+                     int32_t x0, int32_t y0, int32_t w, int32_t h,
+                     int32_t depth, float t_cut, float* host_rgb, float* host_T);
+
+/* Camera.generate_ray_field — camera.py:57-71.  rays: device, (W,H,8) float32
+ * = origin xyz, direction xyz, start, end (ray.py:4-18). */
+int rtgs_generate_rays(const rtgs_camera* cam, int device, float* rays, void* stream);
+
+/* Scene.hit for a batch of rays — scene.py:406-450: per ray the Gaussian with the smallest
+ * entry distance t1 in (start, end).  rays: device (n,8) as above.  idx: device int32 (n)
+ * = ORIGINAL Gaussian index or -1; t12: device (n,2) float32 (+inf on a miss). */
+int rtgs_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays,
+                       int32_t* idx, float* t12, void* stream);
+
+int rtgs_scene_destroy(rtgs_scene* s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RTGS_B200_H */

@@ -1,0 +1,354 @@
+// abi.cu — extern "C" boundary (include/rtgs_b200.h): scene lifetime, build, render, read-back.
+#include <stdarg.h>
+#include <string.h>
+
+#include <new>
+
+#include "common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void rtgs_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+template <typename T>
+int dev_alloc(T** p, size_t count) {
+    *p = nullptr;
+    if (count == 0) count = 1;
+    cudaError_t e = cudaMalloc((void**)p, count * sizeof(T));
+    if (e != cudaSuccess) {
+        rtgs_set_error("cudaMalloc(%zu bytes) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+        return e == cudaErrorMemoryAllocation ? RTGS_ERR_NOMEM : RTGS_ERR_CUDA;
+    }
+    return RTGS_OK;
+}
+
+void free_scene(rtgs_scene* s) {
+    if (!s) return;
+    DeviceGuard g(s->device);
+    cudaFree(s->pos); cudaFree(s->rot); cudaFree(s->scale); cudaFree(s->color); cudaFree(s->opacity);
+    cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
+    cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes);
+    cudaFree(s->tile_counter); cudaFree(s->stats_dev); cudaFree(s->stage_rgb); cudaFree(s->stage_T);
+    if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
+    if (s->pinned_T) cudaFreeHost(s->pinned_T);
+    if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    delete s;
+}
+
+#define TRY(expr)                      \
+    do {                               \
+        int _r = (expr);               \
+        if (_r != RTGS_OK) return _r;  \
+    } while (0)
+
+int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
+    rtgs_scene* s = new (std::nothrow) rtgs_scene();
+    if (!s) {
+        rtgs_set_error("out of host memory");
+        return RTGS_ERR_NOMEM;
+    }
+    s->device = device;
+    s->n = n;
+    s->has_sh = has_sh;
+    s->num_nodes = n > 1 ? n - 1 : 1;
+    *out = s;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    s->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    TRY(dev_alloc(&s->pos, n * 3));
+    TRY(dev_alloc(&s->rot, n * 4));
+    TRY(dev_alloc(&s->scale, n * 3));
+    TRY(dev_alloc(&s->color, n * 3));
+    TRY(dev_alloc(&s->opacity, n));
+    if (has_sh) TRY(dev_alloc(&s->sh, n * 45));
+    TRY(dev_alloc(&s->morton, n));
+    TRY(dev_alloc(&s->sorted_idx, n));
+    TRY(dev_alloc(&s->child, (n > 1 ? n - 1 : 1) * 2));
+    TRY(dev_alloc(&s->parent, 2 * n - 1));
+    TRY(dev_alloc(&s->aabb, (2 * n - 1) * 6));
+    TRY(dev_alloc(&s->geo, n * 4));
+    if (has_sh) TRY(dev_alloc(&s->shp, n * 12));
+    TRY(dev_alloc(&s->raw, n * 3));
+    TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
+    TRY(dev_alloc(&s->tile_counter, 1));
+    TRY(dev_alloc(&s->stats_dev, 8));
+    return RTGS_OK;
+}
+
+int ensure_stage(rtgs_scene* s, size_t pixels) {
+    if (s->stage_pixels < pixels) {
+        cudaFree(s->stage_rgb);
+        cudaFree(s->stage_T);
+        s->stage_rgb = s->stage_T = nullptr;
+        s->stage_pixels = 0;
+        TRY(dev_alloc(&s->stage_rgb, pixels * 3));
+        TRY(dev_alloc(&s->stage_T, pixels));
+        s->stage_pixels = pixels;
+    }
+    if (s->pinned_pixels < pixels) {
+        if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
+        if (s->pinned_T) cudaFreeHost(s->pinned_T);
+        s->pinned_rgb = s->pinned_T = nullptr;
+        s->pinned_pixels = 0;
+        CUDA_TRY(cudaMallocHost((void**)&s->pinned_rgb, pixels * 3 * sizeof(float)));
+        CUDA_TRY(cudaMallocHost((void**)&s->pinned_T, pixels * sizeof(float)));
+        s->pinned_pixels = pixels;
+    }
+    return RTGS_OK;
+}
+
+int check_camera(const rtgs_camera* cam) {
+    RTGS_CHECK_ARG(cam != nullptr);
+    RTGS_CHECK_ARG(cam->width > 0 && cam->height > 0);
+    RTGS_CHECK_ARG(cam->focal[0] != 0.0f && cam->focal[1] != 0.0f);
+    return RTGS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rtgs_last_error(void) { return g_err; }
+int rtgs_abi_version(void) { return RTGS_ABI_VERSION; }
+
+int rtgs_device_count(int* n) {
+    RTGS_CHECK_ARG(n != nullptr);
+    CUDA_TRY(cudaGetDeviceCount(n));
+    return RTGS_OK;
+}
+
+int rtgs_scene_create(int device, int64_t n, const float* pos, const float* rot_xyzw, const float* scale,
+                      const float* color, const float* opacity, const float* sh, rtgs_scene** out) {
+    RTGS_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    RTGS_CHECK_ARG(n >= 1 && n < (1ll << 30));
+    RTGS_CHECK_ARG(pos && rot_xyzw && scale && color && opacity);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    rtgs_scene* s = nullptr;
+    int r = alloc_scene(device, n, sh != nullptr, &s);
+    if (r == RTGS_OK) {
+        auto up = [&](float* d, const float* h, size_t cnt) {
+            return cudaMemcpy(d, h, cnt * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+        };
+        bool ok = up(s->pos, pos, n * 3) && up(s->rot, rot_xyzw, n * 4) && up(s->scale, scale, n * 3) &&
+                  up(s->color, color, n * 3) && up(s->opacity, opacity, n) && (!sh || up(s->sh, sh, n * 45));
+        if (!ok) {
+            rtgs_set_error("host->device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            r = RTGS_ERR_CUDA;
+        }
+    }
+    if (r != RTGS_OK) {
+        free_scene(s);
+        return r;
+    }
+    *out = s;
+    return RTGS_OK;
+}
+
+int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices, int32_t stride_floats,
+                                    const int32_t* col, float scale, int32_t sh_layout, rtgs_scene** out) {
+    RTGS_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    RTGS_CHECK_ARG(n >= 1 && n < (1ll << 30));
+    RTGS_CHECK_ARG(vertices && col && stride_floats > 0);
+    RTGS_CHECK_ARG(sh_layout == 0 || sh_layout == 1);
+    bool has_sh = false;
+    for (int k = 6; k < 51; ++k) has_sh = has_sh || col[k] >= 0;
+    for (int k = 0; k < 62; ++k) RTGS_CHECK_ARG(col[k] < stride_floats);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    rtgs_scene* s = nullptr;
+    int r = alloc_scene(device, n, has_sh, &s);
+    float* rows = nullptr;
+    int32_t* dcol = nullptr;
+    if (r == RTGS_OK) r = dev_alloc(&rows, (size_t)n * stride_floats);
+    if (r == RTGS_OK) r = dev_alloc(&dcol, 62);
+    if (r == RTGS_OK) {
+        cudaError_t e = cudaMemcpy(rows, vertices, (size_t)n * stride_floats * sizeof(float), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dcol, col, 62 * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) {
+            rtgs_set_error("host->device upload failed: %s", cudaGetErrorString(e));
+            r = RTGS_ERR_CUDA;
+        }
+    }
+    if (r == RTGS_OK)
+        r = rtgs_launch_activate_ply(n, rows, stride_floats, dcol, scale, sh_layout, s->pos, s->rot, s->scale,
+                                     s->color, s->opacity, s->sh, s->own_stream);
+    if (r == RTGS_OK && cudaStreamSynchronize(s->own_stream) != cudaSuccess) {
+        rtgs_set_error("activation kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        r = RTGS_ERR_CUDA;
+    }
+    cudaFree(rows);
+    cudaFree(dcol);
+    if (r != RTGS_OK) {
+        free_scene(s);
+        return r;
+    }
+    *out = s;
+    return RTGS_OK;
+}
+
+int rtgs_scene_build_bvh(rtgs_scene* s, int32_t leaf_size) {
+    RTGS_CHECK_ARG(s != nullptr);
+    (void)leaf_size;  // LBVH leaves hold one Gaussian; accepted for Scene(leaf_prim=...) compatibility
+    DeviceGuard g(s->device);
+    int r = rtgs_lbvh_build(s);
+    if (r == RTGS_OK) s->built = true;
+    return r;
+}
+
+int rtgs_scene_num_gaussians(const rtgs_scene* s, int64_t* n) {
+    RTGS_CHECK_ARG(s && n);
+    *n = s->n;
+    return RTGS_OK;
+}
+
+int rtgs_scene_device(const rtgs_scene* s, int* device) {
+    RTGS_CHECK_ARG(s && device);
+    *device = s->device;
+    return RTGS_OK;
+}
+
+int rtgs_scene_read_lbvh(rtgs_scene* s, uint32_t* morton, uint32_t* sorted_idx, int32_t* child, int32_t* parent,
+                         float* aabb) {
+    RTGS_CHECK_ARG(s != nullptr);
+    if (!s->built) {
+        rtgs_set_error("rtgs_scene_read_lbvh: BVH not built");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    const int64_t n = s->n;
+    if (morton) CUDA_TRY(cudaMemcpy(morton, s->morton, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (sorted_idx) CUDA_TRY(cudaMemcpy(sorted_idx, s->sorted_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (child && n > 1) CUDA_TRY(cudaMemcpy(child, s->child, (n - 1) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (parent) CUDA_TRY(cudaMemcpy(parent, s->parent, (2 * n - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    if (aabb) CUDA_TRY(cudaMemcpy(aabb, s->aabb, (2 * n - 1) * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RTGS_OK;
+}
+
+int rtgs_scene_read_gaussians(rtgs_scene* s, float* pos, float* rot_xyzw, float* scale, float* color,
+                              float* opacity, float* sh) {
+    RTGS_CHECK_ARG(s != nullptr);
+    DeviceGuard g(s->device);
+    const int64_t n = s->n;
+    if (pos) CUDA_TRY(cudaMemcpy(pos, s->pos, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (rot_xyzw) CUDA_TRY(cudaMemcpy(rot_xyzw, s->rot, n * 4 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (scale) CUDA_TRY(cudaMemcpy(scale, s->scale, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (color) CUDA_TRY(cudaMemcpy(color, s->color, n * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (opacity) CUDA_TRY(cudaMemcpy(opacity, s->opacity, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (sh) {
+        if (s->has_sh) CUDA_TRY(cudaMemcpy(sh, s->sh, n * 45 * sizeof(float), cudaMemcpyDeviceToHost));
+        else memset(sh, 0, n * 45 * sizeof(float));
+    }
+    return RTGS_OK;
+}
+
+int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h, int32_t depth,
+                float t_cut, int32_t accumulate, int32_t full_image_pitch, float* out_rgb, float* out_T, void* stream,
+                rtgs_render_stats* stats) {
+    RTGS_CHECK_ARG(s != nullptr);
+    TRY(check_camera(cam));
+    RTGS_CHECK_ARG(out_rgb != nullptr);
+    RTGS_CHECK_ARG(w > 0 && h > 0 && x0 >= 0 && y0 >= 0 && x0 + w <= cam->width && y0 + h <= cam->height);
+    RTGS_CHECK_ARG(depth >= 1 && depth <= RTGS_MAX_DEPTH);
+    RTGS_CHECK_ARG(t_cut >= 0.0f && t_cut < 1.0f);
+    if (!s->built) {
+        rtgs_set_error("rtgs_render: call rtgs_scene_build_bvh first");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_image_pitch, out_rgb, out_T, st,
+                           stats != nullptr));
+    if (stats) {
+        unsigned long long hs[8];
+        CUDA_TRY(cudaMemcpyAsync(hs, s->stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
+        stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
+    }
+    return RTGS_OK;
+}
+
+int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                     int32_t depth, float t_cut, float* host_rgb, float* host_T) {
+    RTGS_CHECK_ARG(s != nullptr);
+    TRY(check_camera(cam));
+    RTGS_CHECK_ARG(host_rgb != nullptr);
+    RTGS_CHECK_ARG(w > 0 && h > 0 && x0 >= 0 && y0 >= 0 && x0 + w <= cam->width && y0 + h <= cam->height);
+    RTGS_CHECK_ARG(depth >= 1 && depth <= RTGS_MAX_DEPTH);
+    RTGS_CHECK_ARG(t_cut >= 0.0f && t_cut < 1.0f);
+    if (!s->built) {
+        rtgs_set_error("rtgs_render_host: call rtgs_scene_build_bvh first");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    const size_t px = (size_t)w * h;
+    TRY(ensure_stage(s, px));
+    cudaStream_t st = s->own_stream;
+    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, s->stage_rgb, host_T ? s->stage_T : nullptr, st,
+                           false));
+    CUDA_TRY(cudaMemcpyAsync(s->pinned_rgb, s->stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_T) CUDA_TRY(cudaMemcpyAsync(s->pinned_T, s->stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    memcpy(host_rgb, s->pinned_rgb, px * 3 * sizeof(float));
+    if (host_T) memcpy(host_T, s->pinned_T, px * sizeof(float));
+    return RTGS_OK;
+}
+
+int rtgs_generate_rays(const rtgs_camera* cam, int device, float* rays, void* stream) {
+    TRY(check_camera(cam));
+    RTGS_CHECK_ARG(rays != nullptr);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    return rtgs_launch_generate_rays(cam, rays, (cudaStream_t)stream);
+}
+
+int rtgs_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays, int32_t* idx, float* t12, void* stream) {
+    RTGS_CHECK_ARG(s != nullptr);
+    RTGS_CHECK_ARG(nrays >= 0);
+    RTGS_CHECK_ARG(nrays == 0 || (rays && idx && t12));
+    if (!s->built) {
+        rtgs_set_error("rtgs_trace_closest: call rtgs_scene_build_bvh first");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    return rtgs_launch_trace_closest(s, nrays, rays, idx, t12, (cudaStream_t)stream);
+}
+
+int rtgs_scene_destroy(rtgs_scene* s) {
+    free_scene(s);
+    return RTGS_OK;
+}
+
+}  // extern "C"

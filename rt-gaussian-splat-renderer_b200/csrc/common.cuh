@@ -1,0 +1,101 @@
+// common.cuh — shared declarations for the B200-native rtgs render path (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/rtgs_b200.h"
+
+#define RTGS_SM_COUNT_FALLBACK 148
+
+// ---- error plumbing (never abort across the ABI) ---------------------------------------------
+void rtgs_set_error(const char* fmt, ...);
+
+#define CUDA_TRY(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            rtgs_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,   \
+                           __LINE__);                                                          \
+            return RTGS_ERR_CUDA;                                                              \
+        }                                                                                      \
+    } while (0)
+
+#define RTGS_CHECK_ARG(cond)                                                                   \
+    do {                                                                                       \
+        if (!(cond)) {                                                                         \
+            rtgs_set_error("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__);         \
+            return RTGS_ERR_INVALID;                                                           \
+        }                                                                                      \
+    } while (0)
+
+// ---- device data layout (all records 16-byte aligned SoA of float4) ---------------------------
+// Everything below is stored in MORTON-SORTED order (sorted position s), so that neighbouring
+// BVH leaves are neighbours in memory.
+//
+// geo  [s*4 + 0] = { p.x, p.y, p.z, opacity }
+//      [s*4 + 1] = { W00, W01, W02, W10 }        W = S^-1 R^T / |q|^4  (local-frame matrix:
+//      [s*4 + 2] = { W11, W12, W20, W21 }        x' = W (x - p);  Sigma^-1 = W^T W)
+//      [s*4 + 3] = { W22, dc.r, dc.g, dc.b }     dc = post-sigmoid colour (scene.py:113)
+// shp  [s*12 .. s*12+11] = 45 SH floats (sh_10.rgb, sh_11.rgb, ... sh_36.rgb) + 3 pad
+// raw  [s*3 .. s*3+2]    = { p.xyz, q.x } { q.yzw, s.x } { s.yz, original index (int bits), 0 }
+//                          (inputs of the float64 exact-decision path)
+// node [k*4 + 0] = { lmin.x, lmin.y, lmin.z, lmax.x }
+//      [k*4 + 1] = { lmax.y, lmax.z, rmin.x, rmin.y }
+//      [k*4 + 2] = { rmin.z, rmax.x, rmax.y, rmax.z }
+//      [k*4 + 3] = { left, right (int bits), 0, 0 }   child >= 0: internal node id;
+//                                                      child <  0: leaf, sorted position = ~child
+struct rtgs_scene {
+    int device = 0;
+    int64_t n = 0;
+    bool has_sh = false;
+    bool built = false;
+    int sm_count = RTGS_SM_COUNT_FALLBACK;
+
+    // stored parameters, ORIGINAL order (Scene.gaussian_field)
+    float* pos = nullptr;      // n*3
+    float* rot = nullptr;      // n*4
+    float* scale = nullptr;    // n*3
+    float* color = nullptr;    // n*3
+    float* opacity = nullptr;  // n
+    float* sh = nullptr;       // n*45 or null
+
+    // LBVH integers (parity read-back) and boxes
+    uint32_t* morton = nullptr;      // n, original order
+    uint32_t* sorted_idx = nullptr;  // n
+    int32_t* child = nullptr;        // (n-1)*2 unified ids
+    int32_t* parent = nullptr;       // 2n-1
+    float* aabb = nullptr;           // (2n-1)*6
+    float bounds[6] = {0, 0, 0, 0, 0, 0};
+
+    // packed render records
+    float4* geo = nullptr;
+    float4* shp = nullptr;
+    float4* raw = nullptr;
+    float4* nodes = nullptr;
+    int64_t num_nodes = 0;  // max(n-1, 1)
+
+    // render scratch
+    unsigned int* tile_counter = nullptr;
+    unsigned long long* stats_dev = nullptr;  // 8 counters
+    float* stage_rgb = nullptr;               // device staging for rtgs_render_host
+    float* stage_T = nullptr;
+    size_t stage_pixels = 0;
+    float* pinned_rgb = nullptr;
+    float* pinned_T = nullptr;
+    size_t pinned_pixels = 0;
+    cudaStream_t own_stream = nullptr;
+};
+
+// ---- launchers implemented in the kernel translation units ------------------------------------
+int rtgs_lbvh_build(rtgs_scene* s);   // lbvh.cu
+int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h,
+                       int depth, float t_cut, int accumulate, int full_pitch, float* out_rgb,
+                       float* out_T, cudaStream_t stream, bool want_stats);  // render.cu
+int rtgs_launch_generate_rays(const rtgs_camera* cam, float* rays, cudaStream_t stream);
+int rtgs_launch_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays, int32_t* idx,
+                              float* t12, cudaStream_t stream);
+int rtgs_launch_activate_ply(int64_t n, const float* rows_dev, int stride, const int32_t* col,
+                             float scale, int sh_layout, float* pos, float* rot, float* sca,
+                             float* color, float* opacity, float* sh, cudaStream_t stream);

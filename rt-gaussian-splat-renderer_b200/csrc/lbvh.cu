@@ -1,0 +1,396 @@
+// lbvh.cu — GPU LBVH build for the rtgs render path (sm_100a).
+//
+// Replaces the reference's host-driven binned-SAH builder (scene.py:162-404: >= 10 kernel
+// launches + 4 device->host syncs per node, ~120 nodes/s) with a fully device-side build:
+//   scene bounds -> 30-bit Morton codes -> LSD radix sort of (code<<32 | index) ->
+//   Karras 2012 hierarchy -> per-Gaussian preprocessing + packing in sorted order ->
+//   bottom-up AABB refit -> 64-byte two-child traversal nodes.
+// The integer spec (codes, keys, hierarchy ids) is oracle/lbvh_ref.py; it must match bit for bit.
+// The split key is the Gaussian centre, as in the reference (scene.py:263-266).
+#include "common.cuh"
+#include "gsmath.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------ scene bounds (exact min/max)
+__global__ void k_bounds(const float* __restrict__ pos, int64_t n, unsigned int* __restrict__ out) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float v = pos[i * 3 + a];
+            lo[a] = fminf(lo[a], v);
+            hi[a] = fmaxf(hi[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            atomicMin(&out[a], float_to_ordered(lo[a]));
+            atomicMax(&out[3 + a], float_to_ordered(hi[a]));
+        }
+    }
+}
+
+// ------------------------------------------------------------------ Morton codes + sort keys
+__device__ __forceinline__ uint32_t expand_bits(uint32_t v) {
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+// x = (p - lo) * inv  (float32 subtract, then float32 multiply: not an FMA pattern),
+// u = uint(min(max(x*1024, 0), 1023)).  inv = 1/(hi-lo) correctly rounded, 0 when hi == lo.
+__global__ void k_morton(const float* __restrict__ pos, int64_t n, const unsigned int* __restrict__ bnd,
+                         uint32_t* __restrict__ morton, uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t u[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float lo = ordered_to_float(bnd[a]), hi = ordered_to_float(bnd[3 + a]);
+        float ext = __fsub_rn(hi, lo);
+        float inv = ext > 0.0f ? __fdiv_rn(1.0f, ext) : 0.0f;
+        float x = __fmul_rn(__fsub_rn(pos[i * 3 + a], lo), inv);
+        float q = fminf(fmaxf(__fmul_rn(x, 1024.0f), 0.0f), 1023.0f);
+        u[a] = (uint32_t)q;
+    }
+    uint32_t code = (expand_bits(u[0]) << 2) | (expand_bits(u[1]) << 1) | expand_bits(u[2]);
+    morton[i] = code;
+    keys[i] = ((uint64_t)code << 32) | (uint64_t)(uint32_t)i;
+}
+
+// ------------------------------------------------------------------ LSD radix sort (8-bit digits)
+// Keys are unique 64-bit (code<<32 | index) and arrive in ascending index order, so a STABLE sort
+// on the 30 code bits alone (bits 32..61, four 8-bit passes) yields the full-key order.
+// Per pass: (1) per-tile digit histograms, (2) exclusive scan over (digit, tile), (3) stable
+// scatter with warp-level match_any ranking.  Tile = RS_WARPS warps x 32 lanes x RS_ITEMS keys;
+// a warp owns RS_ITEMS consecutive 32-key rows of the tile so that in-tile order is preserved.
+constexpr int RS_WARPS = 8;
+constexpr int RS_ITEMS = 8;
+constexpr int RS_TILE = RS_WARPS * 32 * RS_ITEMS;  // 2048 keys per block
+constexpr int RS_BINS = 256;
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __restrict__ hist /*[bin][tile]*/,
+          int ntiles) {
+    __shared__ uint32_t sh[RS_BINS];
+    for (int b = threadIdx.x; b < RS_BINS; b += blockDim.x) sh[b] = 0;
+    __syncthreads();
+    int64_t base = (int64_t)blockIdx.x * RS_TILE;
+    for (int k = threadIdx.x; k < RS_TILE; k += blockDim.x) {
+        int64_t i = base + k;
+        if (i < n) atomicAdd(&sh[(uint32_t)(keys[i] >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    for (int b = threadIdx.x; b < RS_BINS; b += blockDim.x) hist[(int64_t)b * ntiles + blockIdx.x] = sh[b];
+}
+
+// single-block exclusive scan over `len` uint32 (len = 256 * ntiles)
+__global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ data, int64_t len) {
+    __shared__ uint32_t warp_tot[32];
+    __shared__ uint32_t carry_sh;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int64_t base = 0; base < len; base += 1024) {
+        int64_t i = base + threadIdx.x;
+        uint32_t v = i < len ? data[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = warp_tot[lane];
+            uint32_t s = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, s, o);
+                if (lane >= o) s += y;
+            }
+            warp_tot[lane] = s - w;  // exclusive warp offsets
+        }
+        __syncthreads();
+        uint32_t carry = carry_sh;
+        uint32_t incl = x + warp_tot[wid] + carry;
+        if (i < len) data[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry_sh = incl;
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(RS_WARPS * 32)
+k_rs_scatter(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_t n, int shift,
+             const uint32_t* __restrict__ hist_scanned, int ntiles) {
+    __shared__ uint32_t wcount[RS_WARPS][RS_BINS];  // per-warp digit counts -> exclusive bases
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int k = threadIdx.x; k < RS_WARPS * RS_BINS; k += blockDim.x) (&wcount[0][0])[k] = 0;
+    __syncthreads();
+
+    const int64_t wbase = (int64_t)blockIdx.x * RS_TILE + (int64_t)wid * (32 * RS_ITEMS);
+    uint64_t key[RS_ITEMS];
+    uint32_t rank[RS_ITEMS];  // rank within this warp among equal digits (stable)
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int64_t i = wbase + r * 32 + lane;
+        bool valid = i < n;
+        key[r] = valid ? in[i] : ~0ull;
+        uint32_t dig = (uint32_t)(key[r] >> shift) & 0xFFu;
+        // lanes with the same digit (invalid lanes form their own group via bit 8)
+        uint32_t peers = __match_any_sync(0xffffffffu, valid ? dig : 0x100u);
+        uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t prev = 0;
+        if (valid) prev = wcount[wid][dig];
+        __syncwarp();
+        rank[r] = prev + before;
+        if (valid && before == 0) wcount[wid][dig] = prev + __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    // exclusive scan over warps for each digit, plus the global base of (digit, tile)
+    for (int b = threadIdx.x; b < RS_BINS; b += blockDim.x) {
+        uint32_t run = hist_scanned[(int64_t)b * ntiles + blockIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) {
+            uint32_t c = wcount[w][b];
+            wcount[w][b] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r) {
+        int64_t i = wbase + r * 32 + lane;
+        if (i < n) {
+            uint32_t dig = (uint32_t)(key[r] >> shift) & 0xFFu;
+            out[wcount[wid][dig] + rank[r]] = key[r];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ Karras 2012 hierarchy
+__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int64_t n, uint64_t ki, int64_t j) {
+    if (j < 0 || j >= n) return -1;
+    return __clzll((long long)(ki ^ keys[j]));
+}
+
+__global__ void k_karras(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ child,
+                         int32_t* __restrict__ parent) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n - 1) return;
+    uint64_t ki = keys[i];
+    int d = (delta_fn(keys, n, ki, i + 1) - delta_fn(keys, n, ki, i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta_fn(keys, n, ki, i - d);
+    int64_t lmax = 2;
+    while (delta_fn(keys, n, ki, i + lmax * d) > dmin) lmax <<= 1;
+    int64_t l = 0;
+    for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
+        if (delta_fn(keys, n, ki, i + (l + t) * d) > dmin) l += t;
+    int64_t j = i + l * d;
+    int dnode = delta_fn(keys, n, ki, j);
+    int64_t s = 0, t = l;
+    do {
+        t = (t + 1) >> 1;
+        if (delta_fn(keys, n, ki, i + (s + t) * d) > dnode) s += t;
+    } while (t > 1);
+    int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
+    int64_t first = i < j ? i : j, last = i < j ? j : i;
+    int32_t left = (int32_t)(first == gamma ? (n - 1) + gamma : gamma);
+    int32_t right = (int32_t)(last == gamma + 1 ? (n - 1) + gamma + 1 : gamma + 1);
+    child[i * 2 + 0] = left;
+    child[i * 2 + 1] = right;
+    parent[left] = (int32_t)i;
+    parent[right] = (int32_t)i;
+    if (i == 0) parent[0] = -1;
+}
+
+// ------------------------------------------------------------------ preprocessing + packing
+// One thread per SORTED position: gather the stored parameters of Gaussian sorted_idx[s] and emit
+// the packed render records (layout in common.cuh) and the leaf AABB.
+//   R = as_rotation_mat3(q)         utils/quaternion.py:99-121   (float64)
+//   W = S^-1 R^T / |q|^4            Sigma^-1 = W^T W, Sigma = R S S^T R^T  (gaussian.py:86-102)
+//   AABB = p +- sqrt(3 Sigma_ii)    tight box of the sqrt(3)-sigma ellipsoid; the reference's box
+//          (gaussian.py:104-138) is a conservative superset, and the image does not depend on it.
+// Directed rounding keeps the float32 box a superset of the exact ellipsoid extent.
+__global__ void k_pack(int64_t n, const uint64_t* __restrict__ keys, const float* __restrict__ pos,
+                       const float* __restrict__ rot, const float* __restrict__ scale,
+                       const float* __restrict__ color, const float* __restrict__ opacity,
+                       const float* __restrict__ sh, uint32_t* __restrict__ sorted_idx,
+                       float4* __restrict__ geo, float4* __restrict__ shp, float4* __restrict__ raw,
+                       float* __restrict__ aabb) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    uint32_t g = (uint32_t)(keys[s] & 0xFFFFFFFFull);
+    sorted_idx[s] = g;
+    float p[3] = {pos[g * 3 + 0], pos[g * 3 + 1], pos[g * 3 + 2]};
+    float qf[4] = {rot[g * 4 + 0], rot[g * 4 + 1], rot[g * 4 + 2], rot[g * 4 + 3]};
+    float sf[3] = {scale[g * 3 + 0], scale[g * 3 + 1], scale[g * 3 + 2]};
+    double q[4] = {qf[0], qf[1], qf[2], qf[3]};
+    double sc[3] = {sf[0], sf[1], sf[2]};
+    double Wm[3][3], Rm[3][3];
+    local_frame(q, sc, Wm);
+    quat_to_mat(q, Rm);
+    geo[s * 4 + 0] = make_float4(p[0], p[1], p[2], opacity[g]);
+    geo[s * 4 + 1] = make_float4((float)Wm[0][0], (float)Wm[0][1], (float)Wm[0][2], (float)Wm[1][0]);
+    geo[s * 4 + 2] = make_float4((float)Wm[1][1], (float)Wm[1][2], (float)Wm[2][0], (float)Wm[2][1]);
+    geo[s * 4 + 3] = make_float4((float)Wm[2][2], color[g * 3 + 0], color[g * 3 + 1], color[g * 3 + 2]);
+    raw[s * 3 + 0] = make_float4(p[0], p[1], p[2], qf[0]);
+    raw[s * 3 + 1] = make_float4(qf[1], qf[2], qf[3], sf[0]);
+    raw[s * 3 + 2] = make_float4(sf[1], sf[2], __int_as_float((int)g), 0.0f);
+    if (shp != nullptr) {
+        const float* src = sh + (int64_t)g * 45;
+        float v[48];
+#pragma unroll
+        for (int k = 0; k < 45; ++k) v[k] = src[k];
+        v[45] = v[46] = v[47] = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 12; ++k)
+            shp[s * 12 + k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    }
+    // tight AABB: h_i = sqrt(3 * Sigma_ii), Sigma_ii = sum_k R_ik^2 s_k^2
+    float* bb = aabb + (int64_t)((n - 1) + s) * 6;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        double v = Rm[a][0] * Rm[a][0] * sc[0] * sc[0] + Rm[a][1] * Rm[a][1] * sc[1] * sc[1] +
+                   Rm[a][2] * Rm[a][2] * sc[2] * sc[2];
+        double h = sqrt(RTGS_BOUNDING_THRESHOLD * v) * (1.0 + 1e-6);
+        bb[a] = __double2float_rd((double)p[a] - h);
+        bb[3 + a] = __double2float_ru((double)p[a] + h);
+    }
+}
+
+// ------------------------------------------------------------------ bottom-up refit
+__global__ void k_refit(int64_t n, const int32_t* __restrict__ child, const int32_t* __restrict__ parent,
+                        float* __restrict__ aabb, unsigned int* __restrict__ visit) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    int32_t node = parent[(n - 1) + s];
+    while (node >= 0) {
+        // the first arriver stops; the second sees both children complete
+        __threadfence();
+        if (atomicAdd(&visit[node], 1u) == 0u) return;
+        __threadfence();
+        int32_t l = child[node * 2 + 0], r = child[node * 2 + 1];
+        const volatile float* bl = aabb + (int64_t)l * 6;
+        const volatile float* br = aabb + (int64_t)r * 6;
+        float* bo = aabb + (int64_t)node * 6;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            bo[a] = fminf(bl[a], br[a]);
+            bo[3 + a] = fmaxf(bl[3 + a], br[3 + a]);
+        }
+        node = parent[node];
+    }
+}
+
+// ------------------------------------------------------------------ traversal nodes (64 B)
+__global__ void k_pack_nodes(int64_t n, const int32_t* __restrict__ child, const float* __restrict__ aabb,
+                             float4* __restrict__ nodes) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (n == 1) {
+        if (i == 0) {  // single Gaussian: synthetic root, left = leaf 0, right = empty box
+            const float* b = aabb;
+            nodes[0] = make_float4(b[0], b[1], b[2], b[3]);
+            nodes[1] = make_float4(b[4], b[5], INFINITY, INFINITY);
+            nodes[2] = make_float4(INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
+        }
+        return;
+    }
+    if (i >= n - 1) return;
+    int32_t l = child[i * 2 + 0], r = child[i * 2 + 1];
+    const float* bl = aabb + (int64_t)l * 6;
+    const float* br = aabb + (int64_t)r * 6;
+    int32_t le = l >= n - 1 ? ~(int32_t)(l - (n - 1)) : l;
+    int32_t re = r >= n - 1 ? ~(int32_t)(r - (n - 1)) : r;
+    nodes[i * 4 + 0] = make_float4(bl[0], bl[1], bl[2], bl[3]);
+    nodes[i * 4 + 1] = make_float4(bl[4], bl[5], br[0], br[1]);
+    nodes[i * 4 + 2] = make_float4(br[2], br[3], br[4], br[5]);
+    nodes[i * 4 + 3] = make_float4(__int_as_float(le), __int_as_float(re), 0.0f, 0.0f);
+}
+
+__global__ void k_init_bounds(unsigned int* b) {
+    if (threadIdx.x < 3) b[threadIdx.x] = 0xFFFFFFFFu;
+    else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
+}
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+};
+
+}  // namespace
+
+int rtgs_lbvh_build(rtgs_scene* s) {
+    const int64_t n = s->n;
+    cudaStream_t st = s->own_stream;
+    DevBuf<unsigned int> bnd, visit;
+    DevBuf<uint64_t> keys_a, keys_b;
+    DevBuf<uint32_t> hist;
+    CUDA_TRY(cudaMalloc(&bnd.p, 6 * sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc(&keys_a.p, n * sizeof(uint64_t)));
+    CUDA_TRY(cudaMalloc(&keys_b.p, n * sizeof(uint64_t)));
+    const int ntiles = (int)((n + RS_TILE - 1) / RS_TILE);
+    CUDA_TRY(cudaMalloc(&hist.p, (size_t)RS_BINS * ntiles * sizeof(uint32_t)));
+    CUDA_TRY(cudaMalloc(&visit.p, (size_t)(n > 1 ? n - 1 : 1) * sizeof(unsigned int)));
+
+    const int TB = 256;
+    const int nb = (int)((n + TB - 1) / TB);
+    k_init_bounds<<<1, 32, 0, st>>>(bnd.p);
+    k_bounds<<<min(nb, s->sm_count * 8), TB, 0, st>>>(s->pos, n, bnd.p);
+    k_morton<<<nb, TB, 0, st>>>(s->pos, n, bnd.p, s->morton, keys_a.p);
+    CUDA_TRY(cudaGetLastError());
+
+    uint64_t* src = keys_a.p;
+    uint64_t* dst = keys_b.p;
+    for (int pass = 0; pass < 4; ++pass) {
+        int shift = 32 + 8 * pass;
+        k_rs_hist<<<ntiles, RS_WARPS * 32, 0, st>>>(src, n, shift, hist.p, ntiles);
+        k_rs_scan<<<1, 1024, 0, st>>>(hist.p, (int64_t)RS_BINS * ntiles);
+        k_rs_scatter<<<ntiles, RS_WARPS * 32, 0, st>>>(src, dst, n, shift, hist.p, ntiles);
+        uint64_t* t = src;
+        src = dst;
+        dst = t;
+    }
+    CUDA_TRY(cudaGetLastError());
+    // src now holds the sorted keys
+    if (n > 1) {
+        k_karras<<<(int)((n - 1 + TB - 1) / TB), TB, 0, st>>>(src, n, s->child, s->parent);
+    } else {
+        int32_t m1 = -1;
+        CUDA_TRY(cudaMemcpyAsync(s->parent, &m1, sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    }
+    k_pack<<<nb, 128, 0, st>>>(n, src, s->pos, s->rot, s->scale, s->color, s->opacity, s->sh,
+                               s->sorted_idx, s->geo, s->shp, s->raw, s->aabb);
+    CUDA_TRY(cudaGetLastError());
+    if (n > 1) {
+        CUDA_TRY(cudaMemsetAsync(visit.p, 0, (size_t)(n - 1) * sizeof(unsigned int), st));
+        k_refit<<<nb, TB, 0, st>>>(n, s->child, s->parent, s->aabb, visit.p);
+    }
+    k_pack_nodes<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->child, s->aabb, s->nodes);
+    CUDA_TRY(cudaGetLastError());
+    unsigned int hb[6];
+    CUDA_TRY(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    for (int a = 0; a < 6; ++a) s->bounds[a] = ordered_to_float(hb[a]);
+    return RTGS_OK;
+}

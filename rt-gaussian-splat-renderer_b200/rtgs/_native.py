@@ -1,0 +1,100 @@
+"""ctypes binding of the C-ABI in include/rtgs_b200.h (librtgs_b200.so).
+
+There is NO CPU fallback: if the CUDA library is missing or fails to load, importing the render
+path raises.  Build it with ``python rt-gaussian-splat-renderer_b200/build.py``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+
+_PKG = Path(__file__).resolve().parent.parent
+LIB_PATH = Path(os.environ.get("RTGS_B200_LIB", _PKG / "lib" / "librtgs_b200.so"))
+
+
+class RtgsError(RuntimeError):
+    def __init__(self, status: int, message: str):
+        super().__init__(f"rtgs_b200 error {status}: {message}")
+        self.status = status
+
+
+class rtgs_camera(C.Structure):
+    _fields_ = [("position", C.c_float * 3), ("rotation", C.c_float * 4), ("focal", C.c_float * 2),
+                ("width", C.c_int32), ("height", C.c_int32)]
+
+
+class rtgs_render_stats(C.Structure):
+    _fields_ = [(n, C.c_uint64) for n in ("rays", "rays_hit", "layers", "nodes_tested", "candidates",
+                                          "pair_tests", "f64_refinements", "tiles")]
+
+    def as_dict(self):
+        return {n: int(getattr(self, n)) for n, _ in self._fields_}
+
+
+_fp = C.POINTER(C.c_float)
+_vp = C.c_void_p
+
+#: every symbol include/rtgs_b200.h declares -> (restype, argtypes)
+SIGNATURES = {
+    "rtgs_last_error": (C.c_char_p, []),
+    "rtgs_abi_version": (C.c_int, []),
+    "rtgs_device_count": (C.c_int, [C.POINTER(C.c_int)]),
+    "rtgs_scene_create": (C.c_int, [C.c_int, C.c_int64, _vp, _vp, _vp, _vp, _vp, _vp, C.POINTER(_vp)]),
+    "rtgs_scene_create_from_ply_rows": (C.c_int, [C.c_int, C.c_int64, _vp, C.c_int32, _vp, C.c_float,
+                                                  C.c_int32, C.POINTER(_vp)]),
+    "rtgs_scene_build_bvh": (C.c_int, [_vp, C.c_int32]),
+    "rtgs_scene_num_gaussians": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
+    "rtgs_scene_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "rtgs_scene_read_lbvh": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtgs_scene_read_gaussians": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtgs_render": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                              C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp,
+                              C.POINTER(rtgs_render_stats)]),
+    "rtgs_render_host": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                   C.c_int32, C.c_float, _vp, _vp]),
+    "rtgs_generate_rays": (C.c_int, [C.POINTER(rtgs_camera), C.c_int, _vp, _vp]),
+    "rtgs_trace_closest": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
+    "rtgs_scene_destroy": (C.c_int, [_vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (once) and bind every declared symbol."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise ImportError(
+            f"{LIB_PATH} not found: the rtgs render path is CUDA-only (no CPU fallback). "
+            f"Build it with `python {(_PKG / 'build.py')}`.")
+    lib = C.CDLL(str(LIB_PATH))
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status: int):
+    if status != 0:
+        msg = load().rtgs_last_error()
+        raise RtgsError(status, msg.decode() if msg else "")
+
+
+def make_camera(position, rotation, focal, width, height) -> rtgs_camera:
+    cam = rtgs_camera()
+    cam.position[:] = [float(v) for v in position]
+    cam.rotation[:] = [float(v) for v in rotation]
+    cam.focal[:] = [float(v) for v in focal]
+    cam.width, cam.height = int(width), int(height)
+    return cam
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(load().rtgs_device_count(C.byref(n)))
+    return n.value

@@ -1,0 +1,129 @@
+"""Ray tracer Gaussian splatting renderer — mirror of the reference's ``rtgs/ray_tracer.py``.
+
+The reference renders one compositing layer per ``sample()`` call (one full BVH traversal per
+pixel per layer, ray / T / accum round-tripping through global memory; ray_tracer.py:39-104).
+Here a whole sample — ray generation, one LBVH traversal per 4x8-pixel tile, ``depth`` nearest
+entries, front-to-back compositing — is ONE fused CUDA kernel (csrc/render.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native
+from .camera import Camera
+from .fields import DeviceField
+from .scene import Scene
+from .utils.types import vec2i
+
+MAX_DEPTH = 32  # RTGS_MAX_DEPTH
+
+
+class RayTracer:
+    """RayTracer(buf_size, scene, camera) — ray_tracer.py:25-37.
+
+    Buffers (shape (W,H[,3]), origin bottom-left, index [i, j] = [column, row from the bottom]):
+    ``sample_buf`` accumulated radiance, ``attenuation_buf`` transmittance T, ``disp_buf`` display.
+    ``t_cut`` is the transmittance early-termination threshold (the reference has none; 0 disables)."""
+
+    def __init__(self, buf_size, scene: Scene, camera: Camera, t_cut: float = 1e-4) -> None:
+        import torch
+        self.scene = scene
+        self.camera = camera
+        self.buf_size = vec2i(buf_size)
+        self.t_cut = float(t_cut)
+        dev = torch.device("cuda", scene.device if scene.device is not None else 0)
+        self._dev = dev
+        W, H = self.buf_size.x, self.buf_size.y
+        self.sample_buf = DeviceField(torch.zeros((W, H, 3), dtype=torch.float32, device=dev))
+        self.attenuation_buf = DeviceField(torch.zeros((W, H), dtype=torch.float32, device=dev))
+        self.disp_buf = DeviceField(torch.zeros((W, H, 3), dtype=torch.float32, device=dev))
+        self.num_steps = 0
+        self.num_samples = 0
+        self.last_stats = None
+
+    # ------------------------------------------------------------------ reference API
+    def sample(self, depth: int):
+        """Accumulate one sample into the sample buffer (ray_tracer.py:39-54).
+
+        Observable state (num_steps / num_samples, final sample_buf) follows the reference's state
+        machine: ``depth`` calls make one sample.  The whole sample is rendered by the fused kernel on
+        the FIRST call of the sample (num_steps == 0); the remaining calls only advance the counters
+        (SURVEY.md §7 hard part 8)."""
+        if self.num_steps == 0:
+            self._render_into(depth, accumulate=True)
+        self.num_steps += 1
+        if self.num_steps >= depth:
+            self.num_steps = 0
+            self.num_samples += 1
+
+    def clear_sample(self):
+        """ray_tracer.py:56-60."""
+        self.sample_buf.fill(0.0)
+
+    def clear_attenuation(self):
+        """ray_tracer.py:62-66."""
+        self.attenuation_buf.fill(1.0)
+
+    def generate_disp_buffer(self, num_samples: int, num_steps: int, num_depth: int):
+        """ray_tracer.py:68-77: disp = sample_buf / (num_samples + num_steps/num_depth).
+
+        Because a sample is complete after its first ``sample()`` call here, a sample in progress
+        (num_steps > 0) counts as a whole one; at sample boundaries (num_steps == 0) the result is the
+        reference's."""
+        import torch
+        denom = float(num_samples) + (1.0 if num_steps > 0 else 0.0)
+        if denom <= 0:
+            denom = 1.0
+        torch.div(self.sample_buf.tensor, denom, out=self.disp_buf.tensor)
+
+    def sample_step(self):
+        """ray_tracer.py:79-104 composites ONE layer; the fused kernel has no single-layer mode, so this
+        renders the complete sample when called at the start of a sample and is a no-op otherwise."""
+        if self.num_steps == 0:
+            self._render_into(MAX_DEPTH if getattr(self, "_depth", None) is None else self._depth, accumulate=True)
+
+    # ------------------------------------------------------------------ additive API
+    def render(self, depth: int = 16, tile=None, collect_stats: bool = False):
+        """Render one complete sample of the current camera and return the image as a host ndarray.
+
+        tile = (x0, y0, w, h) restricts the render to a pixel region (returned array is (w,h,3));
+        default is the full (W,H,3) frame.  Layout [i, j] (column, row from the bottom); a conventional
+        top-left-origin image is ``img.transpose(1, 0, 2)[::-1]``."""
+        W, H = self.buf_size.x, self.buf_size.y
+        x0, y0, w, h = (0, 0, W, H) if tile is None else tile
+        out = np.empty((w, h, 3), dtype=np.float32)
+        cam = self.camera.native()
+        _native.check(_native.load().rtgs_render_host(self.scene.handle, cam, x0, y0, w, h, int(depth), self.t_cut,
+                                                      out.ctypes.data, None))
+        return out
+
+    def render_device(self, depth: int = 16, tile=None, out=None, out_T=None, collect_stats: bool = False):
+        """Render into device memory (a torch CUDA tensor) on the current stream; no host copy."""
+        import torch
+        W, H = self.buf_size.x, self.buf_size.y
+        x0, y0, w, h = (0, 0, W, H) if tile is None else tile
+        if out is None:
+            out = torch.empty((w, h, 3), dtype=torch.float32, device=self._dev)
+        stats = _native.rtgs_render_stats() if collect_stats else None
+        cam = self.camera.native()
+        _native.check(_native.load().rtgs_render(
+            self.scene.handle, cam, x0, y0, w, h, int(depth), self.t_cut, 0, 0, out.data_ptr(),
+            None if out_T is None else out_T.data_ptr(), torch.cuda.current_stream(self._dev).cuda_stream,
+            None if stats is None else C.byref(stats)))
+        if stats is not None:
+            self.last_stats = stats.as_dict()
+        return out
+
+    def _render_into(self, depth, accumulate):
+        import torch
+        if depth > MAX_DEPTH:
+            raise ValueError(f"depth {depth} > {MAX_DEPTH} is not supported by the fused kernel")
+        self._depth = int(depth)
+        W, H = self.buf_size.x, self.buf_size.y
+        cam = self.camera.native()
+        _native.check(_native.load().rtgs_render(
+            self.scene.handle, cam, 0, 0, W, H, int(depth), self.t_cut, 1 if accumulate else 0, 1,
+            self.sample_buf.data_ptr(), self.attenuation_buf.data_ptr(),
+            torch.cuda.current_stream(self._dev).cuda_stream, None))

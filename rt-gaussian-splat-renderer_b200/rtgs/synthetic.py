@@ -1,0 +1,45 @@
+"""Synthetic random-Gaussian scenes for the benchmark configurations.
+
+``numpy.random.default_rng(seed)`` draws, in this order, all cast to float32:
+pos ~ U[-1,1)^3; quat ~ N(0,1)^4 normalised (x,y,z,w); log_scale ~ N(ln s, 0.5^2) per axis;
+opacity_logit ~ N(0, 1.5^2); f_dc ~ N(0,1); f_rest ~ N(0, 0.15^2) shape (N,15,3) (SH degree 3) or none
+(degree 0).  Activations exactly as the reference's loader (scene.py:110-114).
+s = 2 sqrt(H/(3 pi N)) with H = 16 expected ellipsoid crossings per cube-spanning ray.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .utils.math import sigmoid
+
+CONFIGS = {
+    # name: (N, seed, sh_degree, (W, H))
+    "100k_deg0_1080p": (100_000, 1001, 0, (1920, 1080)),
+    "1m_deg3_1080p": (1_000_000, 1002, 3, (1920, 1080)),
+    "3m_deg3_2160p": (3_000_000, 1003, 3, (3840, 2160)),
+}
+ORBIT_R = 2.2
+FOV_DEG = 60.0
+H_TARGET = 16.0
+
+
+def mean_scale(n: int, h_target: float = H_TARGET) -> float:
+    return 2.0 * float(np.sqrt(h_target / (3.0 * np.pi * n)))
+
+
+def make_scene(n: int, seed: int, sh_degree: int = 3, h_target: float = H_TARGET) -> dict:
+    """Post-activation parameter arrays: pos, rot, scale, color, opacity, sh (or None)."""
+    f32 = np.float32
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(-1.0, 1.0, size=(n, 3)).astype(f32)
+    quat = rng.normal(0.0, 1.0, size=(n, 4)).astype(f32)
+    log_scale = rng.normal(np.log(mean_scale(n, h_target)), 0.5, size=(n, 3)).astype(f32)
+    opacity_logit = rng.normal(0.0, 1.5, size=(n,)).astype(f32)
+    f_dc = rng.normal(0.0, 1.0, size=(n, 3)).astype(f32)
+    sh = rng.normal(0.0, 0.15, size=(n, 15, 3)).astype(f32) if sh_degree > 0 else None
+    rot = quat / np.linalg.norm(quat, axis=-1)[:, np.newaxis]     # scene.py:110-111
+    scale = np.exp(log_scale) * f32(1.0)                           # scene.py:112
+    color = sigmoid(f_dc)                                          # scene.py:113
+    opacity = sigmoid(opacity_logit)                               # scene.py:114
+    return dict(pos=pos, rot=rot.astype(f32), scale=scale.astype(f32), color=color.astype(f32),
+                opacity=opacity.astype(f32), sh=sh)
