@@ -76,13 +76,13 @@ int rtgs_scene_create(int device, int64_t n,
                       rtgs_scene** out);
 
 /* Scene.load_file front half on the GPU — scene.py:95-114: `vertices` is the raw binary
- * little-endian PLY vertex block (n rows of `stride_floats` float32), `col` the 62 column
+ * little-endian PLY vertex block (n rows of `stride_floats` float32), `col` the 59 column
  * offsets in the order x,y,z, f_dc_0..2, f_rest_0..44, opacity, scale_0..2, rot_0..3 (any
  * offset < 0 = property absent -> 0).  Applies the activations of scene.py:110-114 on device.
  * sh_layout: 0 = channel-major (sh_k[c] = f_rest_{15c+k}), 1 = "taichi as executed"
  * (sh_k[c] = f_rest_{3k+c}); see SURVEY.md §7 hard part 7. */
 int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices,
-                                    int32_t stride_floats, const int32_t* col /*[62]*/,
+                                    int32_t stride_floats, const int32_t* col /*[59]*/,
                                     float scale, int32_t sh_layout, rtgs_scene** out);
 
 /* BVH build — replaces scene.py:162-404 (binned-SAH host loop) with a GPU LBVH:

@@ -178,7 +178,7 @@ int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices
     RTGS_CHECK_ARG(sh_layout == 0 || sh_layout == 1);
     bool has_sh = false;
     for (int k = 6; k < 51; ++k) has_sh = has_sh || col[k] >= 0;
-    for (int k = 0; k < 62; ++k) RTGS_CHECK_ARG(col[k] < stride_floats);
+    for (int k = 0; k < 59; ++k) RTGS_CHECK_ARG(col[k] < stride_floats);
     DeviceGuard g(device);
     if (!g.ok) {
         rtgs_set_error("cudaSetDevice(%d) failed", device);
@@ -189,10 +189,10 @@ int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices
     float* rows = nullptr;
     int32_t* dcol = nullptr;
     if (r == RTGS_OK) r = dev_alloc(&rows, (size_t)n * stride_floats);
-    if (r == RTGS_OK) r = dev_alloc(&dcol, 62);
+    if (r == RTGS_OK) r = dev_alloc(&dcol, 59);
     if (r == RTGS_OK) {
         cudaError_t e = cudaMemcpy(rows, vertices, (size_t)n * stride_floats * sizeof(float), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(dcol, col, 62 * sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(dcol, col, 59 * sizeof(int32_t), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) {
             rtgs_set_error("host->device upload failed: %s", cudaGetErrorString(e));
             r = RTGS_ERR_CUDA;

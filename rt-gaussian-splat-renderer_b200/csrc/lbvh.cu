@@ -379,7 +379,7 @@ int rtgs_lbvh_build(rtgs_scene* s) {
         int32_t m1 = -1;
         CUDA_TRY(cudaMemcpyAsync(s->parent, &m1, sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
-    k_pack<<<nb, 128, 0, st>>>(n, src, s->pos, s->rot, s->scale, s->color, s->opacity, s->sh,
+    k_pack<<<(int)((n + 127) / 128), 128, 0, st>>>(n, src, s->pos, s->rot, s->scale, s->color, s->opacity, s->sh,
                                s->sorted_idx, s->geo, s->shp, s->raw, s->aabb);
     CUDA_TRY(cudaGetLastError());
     if (n > 1) {
