@@ -45,8 +45,8 @@ FALLBACK_HBM_GBS = 6650.0   # B200_PROFILING.md fallback
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="1m_deg3_1080p")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -62,52 +62,54 @@ def make_views(W, H):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled through NVML every few ms DURING the timed region
+    (the same counters `nvidia-smi --query-gpu=clocks.sm,clocks_event_reasons.*` prints)."""
 
-    def __init__(self, index):
-        self.index = index
-        self.lines = []
-        self.proc = None
+    def __init__(self, index, period_s=0.002):
+        self.index, self.period, self.samples, self.reasons = index, period_s, [], set()
+        self.stop_flag = threading.Event()
+        self.thread = None
+        self.max_mhz = None
+        self.power_w = []
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE,
-                                         stderr=subprocess.DEVNULL, text=True)
-            threading.Thread(target=self._pump, daemon=True).start()
-        except OSError:
-            self.proc = None
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+            return
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
 
-    def _pump(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": nv.nvmlClocksThrottleReasonHwSlowdown,
+                 "hw_thermal_slowdown": nv.nvmlClocksThrottleReasonHwThermalSlowdown,
+                 "sw_thermal_slowdown": nv.nvmlClocksThrottleReasonSwThermalSlowdown,
+                 "sw_power_cap": nv.nvmlClocksThrottleReasonSwPowerCap}
+        while not self.stop_flag.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+                self.power_w.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+            except Exception:
+                pass
+            time.sleep(self.period)
 
     def stop(self):
-        if self.proc is not None:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
-        sm, smax, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
-            tok = [t.strip() for t in line.split(",")]
-            if len(tok) < 7:
-                continue
-            try:
-                sm.append(float(tok[0]))
-                smax.append(float(tok[1]))
-            except ValueError:
-                continue
-            for name, v in zip(names, tok[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.stop_flag.set()
+        if self.thread is not None:
+            self.thread.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples),
+                "power_w_max": max(self.power_w) if self.power_w else None}
 
 
 def load_peak():
@@ -228,7 +230,7 @@ def main():
 
     # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views
     agg = {}
-    for s in range(args.steps):
+    for s in range(min(args.steps, N_VIEWS)):
         set_view(s)
         rt.render_device(DEPTH, out=out, collect_stats=True)
         for k, v in rt.last_stats.items():
@@ -300,12 +302,14 @@ def main():
                             "child_boxes_tested_per_ray": agg["nodes_tested"] / agg["rays"],
                             "candidates_per_tile": agg["candidates"] / max(agg["tiles"], 1),
                             "pair_tests_per_ray": agg["pair_tests"] / agg["rays"],
-                            "f64_refinements_per_Mray": 1e6 * agg["f64_refinements"] / agg["rays"]},
+                            "f64_refinements_per_Mray": 1e6 * agg["f64_refinements"] / agg["rays"],
+                            "traversal_steps_per_tile": agg["traversal_steps"] / max(agg["tiles"], 1),
+                            "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1)},
             "bvh_build_ms": build_ms,
         }
         if world == 1 and not args.no_cpu_baseline:
             stride = args.cpu_stride or 8
-            r = cpu_leg(args.config, arrays, W, H, focal, views, min(args.steps, 4), 1, stride)
+            r = cpu_leg(args.config, arrays, W, H, focal, views, min(args.steps, 8), 1, stride)
             line["cpu_baseline"] = {"value": r["mrays"], "unit": "Mrays/s", "cores": r["cores"], "kind": "port",
                                     "sample": r["sample"]}
         else:

@@ -60,6 +60,9 @@ typedef struct rtgs_render_stats {
     uint64_t pair_tests;         /* ray-Gaussian intersection tests */
     uint64_t f64_refinements;    /* borderline decisions re-evaluated in float64 */
     uint64_t tiles;              /* warp tiles processed */
+    uint64_t traversal_steps;    /* warp-wide traversal iterations (each pops <= 32 nodes) */
+    uint64_t insert_rounds;      /* warp-wide k-buffer insertion rounds */
+    uint64_t reserved[2];
 } rtgs_render_stats;
 
 const char* rtgs_last_error(void);
@@ -123,10 +126,17 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
                 int32_t depth, float t_cut, int32_t accumulate, int32_t full_image_pitch,
                 float* out_rgb, float* out_T, void* stream, rtgs_render_stats* stats);
 
+/* Pinned (page-locked, device-mapped) host memory for image outputs.  rtgs_render_host is
+ * fastest when its output buffers come from here (the kernel then writes the framebuffer
+ * straight into host memory over PCIe while it renders); any host pointer is accepted. */
+int rtgs_host_alloc(size_t bytes, void** out);
+int rtgs_host_free(void* p);
+
 /* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
- * RayTracer makes: camera in, image out).  Renders the region into a library-owned device
- * buffer and copies it to `host_rgb` ((w,h,3) float32) and optionally `host_T` ((w,h));
- * synchronous. */
+ * RayTracer makes: camera in, image out): `host_rgb` ((w,h,3) float32) and optionally
+ * `host_T` ((w,h)).  Synchronous.  Pinned buffers (rtgs_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) are written by the render kernel directly (zero-copy) or by one DMA;
+ * pageable buffers are staged through library-owned pinned memory. */
 int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam,
                      int32_t x0, int32_t y0, int32_t w, int32_t h,
                      int32_t depth, float t_cut, float* host_rgb, float* host_T);

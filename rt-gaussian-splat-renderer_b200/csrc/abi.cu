@@ -1,5 +1,6 @@
 // abi.cu — extern "C" boundary (include/rtgs_b200.h): scene lifetime, build, render, read-back.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -91,7 +92,7 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->raw, n * 3));
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->tile_counter, 1));
-    TRY(dev_alloc(&s->stats_dev, 8));
+    TRY(dev_alloc(&s->stats_dev, 12));
     return RTGS_OK;
 }
 
@@ -105,6 +106,10 @@ int ensure_stage(rtgs_scene* s, size_t pixels) {
         TRY(dev_alloc(&s->stage_T, pixels));
         s->stage_pixels = pixels;
     }
+    return RTGS_OK;
+}
+
+int ensure_pinned(rtgs_scene* s, size_t pixels) {
     if (s->pinned_pixels < pixels) {
         if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
         if (s->pinned_T) cudaFreeHost(s->pinned_T);
@@ -288,13 +293,48 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
     TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_image_pitch, out_rgb, out_T, st,
                            stats != nullptr));
     if (stats) {
-        unsigned long long hs[8];
+        unsigned long long hs[12];
         CUDA_TRY(cudaMemcpyAsync(hs, s->stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
         stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
+        stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->reserved[0] = stats->reserved[1] = 0;
     }
     return RTGS_OK;
+}
+
+int rtgs_host_alloc(size_t bytes, void** out) {
+    RTGS_CHECK_ARG(out != nullptr && bytes > 0);
+    *out = nullptr;
+    CUDA_TRY(cudaHostAlloc(out, bytes, cudaHostAllocPortable | cudaHostAllocMapped));
+    return RTGS_OK;
+}
+
+int rtgs_host_free(void* p) {
+    if (p) CUDA_TRY(cudaFreeHost(p));
+    return RTGS_OK;
+}
+
+// How rtgs_render_host delivers the image: 0 = render to device memory, then one DMA (+ a host
+// memcpy for pageable destinations); 1 = the kernel stores straight into pinned host memory
+// (zero-copy; the PCIe writes overlap the rendering).  RTGS_HOST_MODE overrides the default.
+static int host_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("RTGS_HOST_MODE");
+        mode = e ? atoi(e) : 1;
+    }
+    return mode;
+}
+
+static void* pinned_device_ptr(const void* host) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, host) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    if (at.type != cudaMemoryTypeHost) return nullptr;
+    return at.devicePointer;
 }
 
 int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
@@ -311,10 +351,26 @@ int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t 
     }
     DeviceGuard g(s->device);
     const size_t px = (size_t)w * h;
-    TRY(ensure_stage(s, px));
     cudaStream_t st = s->own_stream;
+    float* d_rgb = (float*)pinned_device_ptr(host_rgb);
+    float* d_T = host_T ? (float*)pinned_device_ptr(host_T) : nullptr;
+    const bool pinned = d_rgb != nullptr && (!host_T || d_T != nullptr);
+    if (pinned && host_mode() == 1) {
+        // zero-copy: the render kernel writes the framebuffer into mapped host memory
+        TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, d_rgb, d_T, st, false));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return RTGS_OK;
+    }
+    TRY(ensure_stage(s, px));
     TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, s->stage_rgb, host_T ? s->stage_T : nullptr, st,
                            false));
+    if (pinned) {
+        CUDA_TRY(cudaMemcpyAsync(host_rgb, s->stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (host_T) CUDA_TRY(cudaMemcpyAsync(host_T, s->stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return RTGS_OK;
+    }
+    TRY(ensure_pinned(s, px));
     CUDA_TRY(cudaMemcpyAsync(s->pinned_rgb, s->stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
     if (host_T) CUDA_TRY(cudaMemcpyAsync(s->pinned_T, s->stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));

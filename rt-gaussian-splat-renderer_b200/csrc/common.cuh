@@ -41,9 +41,9 @@ void rtgs_set_error(const char* fmt, ...);
 // shp  [s*12 .. s*12+11] = 45 SH floats (sh_10.rgb, sh_11.rgb, ... sh_36.rgb) + 3 pad
 // raw  [s*3 .. s*3+2]    = { p.xyz, q.x } { q.yzw, s.x } { s.yz, original index (int bits), 0 }
 //                          (inputs of the float64 exact-decision path)
-// node [k*4 + 0] = { lmin.x, lmin.y, lmin.z, lmax.x }
-//      [k*4 + 1] = { lmax.y, lmax.z, rmin.x, rmin.y }
-//      [k*4 + 2] = { rmin.z, rmax.x, rmax.y, rmax.z }
+// node [k*4 + 0] = { lc.x, lc.y, lc.z, lh.x }      child boxes as (centre c, half extent h), h rounded up
+//      [k*4 + 1] = { lh.y, lh.z, rc.x, rc.y }
+//      [k*4 + 2] = { rc.z, rh.x, rh.y, rh.z }
 //      [k*4 + 3] = { left, right (int bits), 0, 0 }   child >= 0: internal node id;
 //                                                      child <  0: leaf, sorted position = ~child
 struct rtgs_scene {

@@ -70,16 +70,30 @@ __host__ __device__ inline void local_frame(const double q[4], const double s[3]
 struct CamD {
     double o[3];
     double q[4];
+    double R[9];     // as_rotation_mat3(q), row-major, float64 (host-computed once per launch)
     double fx, fy;
+    double ifx, ify; // 1/fx, 1/fy
     int W, H;
 };
 
+// dir = R normalize(px, py, -1) with px = (ci - W/2)/fx  (camera.py:46-52; W*u - W/2 with u = ci/W).
 __host__ __device__ inline d3 cam_dir(const CamD& c, double ci, double cj) {
-    double u = ci / (double)c.W, v = cj / (double)c.H;
-    double px = ((double)c.W * u - 0.5 * (double)c.W) / c.fx;
-    double py = ((double)c.H * v - 0.5 * (double)c.H) / c.fy;
-    double inv = 1.0 / sqrt(px * px + py * py + 1.0);
-    return quat_rot(c.q, d3make(px * inv, py * inv, -inv));
+    const double px = (ci - 0.5 * (double)c.W) * c.ifx;
+    const double py = (cj - 0.5 * (double)c.H) * c.ify;
+#ifdef __CUDA_ARCH__
+    const double inv = rsqrt(px * px + py * py + 1.0);
+#else
+    const double inv = 1.0 / sqrt(px * px + py * py + 1.0);
+#endif
+    const double x = px * inv, y = py * inv, z = -inv;
+    return d3make(c.R[0] * x + c.R[1] * y + c.R[2] * z, c.R[3] * x + c.R[4] * y + c.R[5] * z,
+                  c.R[6] * x + c.R[7] * y + c.R[8] * z);
+}
+
+// plane-normal helper: R v
+__host__ __device__ inline d3 cam_rot(const CamD& c, double x, double y, double z) {
+    return d3make(c.R[0] * x + c.R[1] * y + c.R[2] * z, c.R[3] * x + c.R[4] * y + c.R[5] * z,
+                  c.R[6] * x + c.R[7] * y + c.R[8] * z);
 }
 
 // Exact (float64) ray / sqrt(3)-sigma ellipsoid evaluation from the RAW stored parameters

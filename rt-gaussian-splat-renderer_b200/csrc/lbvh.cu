@@ -300,28 +300,39 @@ __global__ void k_refit(int64_t n, const int32_t* __restrict__ child, const int3
 }
 
 // ------------------------------------------------------------------ traversal nodes (64 B)
+// Child boxes are stored as (centre, half extent) with the half extent rounded UP so that
+// [c-h, c+h] contains the exact float32 [min, max] box.
+__device__ __forceinline__ void box_ch(const float* __restrict__ b, float c[3], float h[3]) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        c[a] = 0.5f * (b[a] + b[3 + a]);
+        h[a] = fmaxf(__fsub_ru(b[3 + a], c[a]), __fsub_ru(c[a], b[a]));
+    }
+}
+
 __global__ void k_pack_nodes(int64_t n, const int32_t* __restrict__ child, const float* __restrict__ aabb,
                              float4* __restrict__ nodes) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    float lc[3], lh[3], rc[3], rh[3];
     if (n == 1) {
-        if (i == 0) {  // single Gaussian: synthetic root, left = leaf 0, right = empty box
-            const float* b = aabb;
-            nodes[0] = make_float4(b[0], b[1], b[2], b[3]);
-            nodes[1] = make_float4(b[4], b[5], INFINITY, INFINITY);
-            nodes[2] = make_float4(INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (i == 0) {  // single Gaussian: synthetic root, left = leaf 0, right = empty box (h = -inf)
+            box_ch(aabb, lc, lh);
+            nodes[0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
+            nodes[1] = make_float4(lh[1], lh[2], 0.0f, 0.0f);
+            nodes[2] = make_float4(0.0f, -INFINITY, -INFINITY, -INFINITY);
             nodes[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
         }
         return;
     }
     if (i >= n - 1) return;
     int32_t l = child[i * 2 + 0], r = child[i * 2 + 1];
-    const float* bl = aabb + (int64_t)l * 6;
-    const float* br = aabb + (int64_t)r * 6;
+    box_ch(aabb + (int64_t)l * 6, lc, lh);
+    box_ch(aabb + (int64_t)r * 6, rc, rh);
     int32_t le = l >= n - 1 ? ~(int32_t)(l - (n - 1)) : l;
     int32_t re = r >= n - 1 ? ~(int32_t)(r - (n - 1)) : r;
-    nodes[i * 4 + 0] = make_float4(bl[0], bl[1], bl[2], bl[3]);
-    nodes[i * 4 + 1] = make_float4(bl[4], bl[5], br[0], br[1]);
-    nodes[i * 4 + 2] = make_float4(br[2], br[3], br[4], br[5]);
+    nodes[i * 4 + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
+    nodes[i * 4 + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
+    nodes[i * 4 + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
     nodes[i * 4 + 3] = make_float4(__int_as_float(le), __int_as_float(re), 0.0f, 0.0f);
 }
 

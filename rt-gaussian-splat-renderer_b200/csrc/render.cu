@@ -63,7 +63,7 @@ struct __align__(16) WarpShared {
     int cq[CQ_CAP];
 };
 
-enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES };
+enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS, ST_COUNT = 12 };
 
 // ---- float64 exact evaluation from raw parameters (rare path) ---------------------------------
 __device__ __noinline__ ExactHit exact_eval(const float4* __restrict__ raw, const CamD& cam, int s,
@@ -125,23 +125,33 @@ __device__ __forceinline__ void sh_basis(float x, float y, float z, float (&Y)[1
 }
 
 struct Frustum {
-    // 4 planes through the camera origin, inward normals n[k] and |n[k]|; a box (centre c
-    // relative to the origin, half size h) is outside plane k iff n.c + |n|.h < 0.
+    // 4 planes through the camera origin o, inward normals n[k]; a box (centre c, half size h) is
+    // outside plane k iff n.c + |n|.h - n.o < 0.
     float nx[4], ny[4], nz[4];
     float ax[4], ay[4], az[4];
+    float d[4];   // n.o
 };
 
-__device__ __forceinline__ bool box_in_frustum(const Frustum& f, float ox, float oy, float oz, float mnx,
-                                               float mny, float mnz, float mxx, float mxy, float mxz) {
-    const float cx = 0.5f * (mnx + mxx) - ox, cy = 0.5f * (mny + mxy) - oy, cz = 0.5f * (mnz + mxz) - oz;
-    const float hx = 0.5f * (mxx - mnx), hy = 0.5f * (mxy - mny), hz = 0.5f * (mxz - mnz);
+__device__ __forceinline__ bool box_in_frustum(const Frustum& f, float cx, float cy, float cz, float hx,
+                                               float hy, float hz) {
     bool in = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         float v = f.nx[k] * cx + f.ny[k] * cy + f.nz[k] * cz + f.ax[k] * hx + f.ay[k] * hy + f.az[k] * hz;
-        in = in && (v >= 0.0f);  // NaN (empty box) -> false
+        in = in && (v >= f.d[k]);  // NaN / -inf (empty box) -> false
     }
     return in;
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
 }
 
 template <int K>
@@ -154,7 +164,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
 
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
-                       st_rays = 0, st_tiles = 0;
+                       st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
 
     for (;;) {
         int tile = 0;
@@ -182,17 +192,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         // ---- tile frustum: planes through the origin along the tile's pixel EDGES -------------
         Frustum fr;
         {
-            const double pxl = ((double)i0 - 0.5 * cam.W) / cam.fx, pxh = ((double)(i0 + TILE_I) - 0.5 * cam.W) / cam.fx;
-            const double pyl = ((double)j0 - 0.5 * cam.H) / cam.fy, pyh = ((double)(j0 + TILE_J) - 0.5 * cam.H) / cam.fy;
+            const double pxl = ((double)i0 - 0.5 * cam.W) * cam.ifx, pxh = ((double)(i0 + TILE_I) - 0.5 * cam.W) * cam.ifx;
+            const double pyl = ((double)j0 - 0.5 * cam.H) * cam.ify, pyh = ((double)(j0 + TILE_J) - 0.5 * cam.H) * cam.ify;
             d3 n[4];
-            n[0] = quat_rot(cam.q, d3make(1.0, 0.0, pxl));     // px >= pxl
-            n[1] = quat_rot(cam.q, d3make(-1.0, 0.0, -pxh));   // px <= pxh
-            n[2] = quat_rot(cam.q, d3make(0.0, 1.0, pyl));     // py >= pyl
-            n[3] = quat_rot(cam.q, d3make(0.0, -1.0, -pyh));   // py <= pyh
+            n[0] = cam_rot(cam, 1.0, 0.0, pxl);     // px >= pxl
+            n[1] = cam_rot(cam, -1.0, 0.0, -pxh);   // px <= pxh
+            n[2] = cam_rot(cam, 0.0, 1.0, pyl);     // py >= pyl
+            n[3] = cam_rot(cam, 0.0, -1.0, -pyh);   // py <= pyh
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
                 fr.nx[k] = (float)n[k].x; fr.ny[k] = (float)n[k].y; fr.nz[k] = (float)n[k].z;
                 fr.ax[k] = fabsf(fr.nx[k]); fr.ay[k] = fabsf(fr.ny[k]); fr.az[k] = fabsf(fr.nz[k]);
+                fr.d[k] = fr.nx[k] * ox + fr.ny[k] * oy + fr.nz[k] * oz;
             }
         }
 
@@ -205,9 +216,35 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             ka[k] = 0.0f;
             ki[k] = -1;
         }
+        // one pending candidate hit per lane; the hit-only work (entry distance, alpha, float64
+        // refinement, k-buffer insertion) runs in warp-wide rounds when some lane gets a second one
         bool pend = false;
-        float pend_t = 0.0f, pend_a = 0.0f;
-        int pend_i = 0;
+        float pend_q = 0.0f, pend_iA = 0.0f, pend_Bh = 0.0f;
+        int pend_c = 0;
+        auto flush = [&]() {
+            if (pend) {
+                const float4 ax = ws.aux[pend_c];
+                const float tc = ws.rec[pend_c][3].w;
+                float q = pend_q;
+                // disc/A^2 = (3 - q)/A  ->  tau = -Bh/A - sqrt((3 - q)/A)
+                const float tau = -pend_Bh * pend_iA - sqrt_approx(fmaxf(3.0f - q, 0.0f) * pend_iA);
+                float t1 = tc + tau;
+                bool hit = (q < 3.0f) && (t1 > 0.0f);
+                const bool near_q = fabsf(q - 3.0f) < ax.z;
+                const bool near_t = fabsf(t1) <= 2e-6f * (fabsf(tc) + fabsf(tau));
+                if (near_q || near_t) {
+                    const ExactHit e = exact_eval(P.raw, cam, __float_as_int(ax.y), pi, pj);
+                    hit = e.hit && (e.t1 > 0.0);
+                    q = (float)e.q;
+                    t1 = (float)e.t1;
+                    st_f64 += 1;
+                }
+                // alpha = opacity * exp(-q)  (gaussian.py:197-198)
+                if (hit) kb_insert<K>(kt, ki, ka, t1, __float_as_int(ax.y), ax.x * __expf(-q));
+                pend = false;
+            }
+            st_ins += 1;
+        };
 
         int top = 1, ncq = 0;
         if (lane == 0) ws.stack[0] = 0;
@@ -230,10 +267,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     const float4 d = __ldg(P.nodes + (int64_t)node * 4 + 3);
                     c0 = __float_as_int(d.x);
                     c1 = __float_as_int(d.y);
-                    h0 = box_in_frustum(fr, ox, oy, oz, a.x, a.y, a.z, a.w, b.x, b.y);
-                    h1 = box_in_frustum(fr, ox, oy, oz, b.z, b.w, c.x, c.y, c.z, c.w);
+                    h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
+                    h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
                 }
                 st_nodes += 2ull * (unsigned)take;
+                st_steps += 1;
                 const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
                 const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
                 if (h0 && c0 >= 0) ws.stack[top + __popc(mI0 & lt_mask)] = c0;
@@ -279,7 +317,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 st_pairs += 32ull * (unsigned)m;
                 for (int c = 0; c < m; ++c) {
                     const float4 r0 = ws.rec[c][0], r1 = ws.rec[c][1], r2 = ws.rec[c][2], r3 = ws.rec[c][3];
-                    const float4 ax = ws.aux[c];
+                    const float band = ws.aux[c].z;
                     const float wx = r0.x * dlx + r0.y * dly + r0.z * dlz;
                     const float wy = r0.w * dlx + r1.x * dly + r1.y * dlz;
                     const float wz = r1.z * dlx + r1.w * dly + r2.x * dlz;
@@ -289,35 +327,22 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     const float A = dx * dx + dy * dy + dz * dz;
                     const float Bh = ex * dx + ey * dy + ez * dz;
                     const float mx = ey * dz - ez * dy, my = ez * dx - ex * dz, mz = ex * dy - ey * dx;
-                    const float iA = __frcp_rn(A);
-                    float q = (mx * mx + my * my + mz * mz) * iA;   // min Mahalanobis^2 along the ray
-                    const float tau = (-Bh - sqrtf(A * fmaxf(3.0f - q, 0.0f))) * iA;
-                    float t1 = tc + tau;
-                    bool hit = active && (q < 3.0f) && (t1 > 0.0f);
-                    const bool near_q = fabsf(q - 3.0f) < ax.z;
-                    const bool near_t = (q < 3.0f + ax.z) && fabsf(t1) <= 1e-6f * (fabsf(tc) + fabsf(tau));
-                    if (active && (near_q || near_t)) {
-                        const ExactHit e = exact_eval(P.raw, cam, __float_as_int(ax.y), pi, pj);
-                        hit = e.hit && (e.t1 > 0.0);
-                        q = (float)e.q;
-                        t1 = (float)e.t1;
-                        st_f64 += 1;
-                    }
-                    if (__any_sync(FULL, hit && pend)) {
-                        if (pend) kb_insert<K>(kt, ki, ka, pend_t, pend_i, pend_a);
-                        pend = false;
-                    }
-                    if (hit) {
+                    const float iA = rcp_approx(A);
+                    const float q = (mx * mx + my * my + mz * mz) * iA;   // min Mahalanobis^2 along the ray
+                    const bool cand = active && (q < 3.0f + band);
+                    if (__any_sync(FULL, cand && pend)) flush();
+                    if (cand) {
                         pend = true;
-                        pend_t = t1;
-                        pend_i = __float_as_int(ax.y);
-                        pend_a = ax.x * __expf(-q);   // alpha = opacity * exp(-q)  (gaussian.py:197-198)
+                        pend_q = q;
+                        pend_iA = iA;
+                        pend_Bh = Bh;
+                        pend_c = c;
                     }
                 }
+                if (__any_sync(FULL, pend)) flush();   // the staged records are about to be overwritten
                 __syncwarp();
             }
         }
-        if (pend) kb_insert<K>(kt, ki, ka, pend_t, pend_i, pend_a);
 
         // ---- near-tie resolution: adjacent entries closer than a few ulp are ordered in f64 ---
 #pragma unroll
@@ -373,15 +398,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 ++nl;
             }
         }
+        // ---- framebuffer write: stage the tile in shared memory so that every store instruction
+        // covers whole 32-byte sectors (each tile column is 8 pixels = 96 contiguous bytes) --------
+        {
+            float* ob = reinterpret_cast<float*>(&ws.rec[0][0]);
+            __syncwarp();
+            ob[lane * 3 + 0] = cr;
+            ob[lane * 3 + 1] = cg;
+            ob[lane * 3 + 2] = cb;
+            __syncwarp();
+            const int pitch = P.full_pitch ? cam.H : P.h;
+            const int bi = P.full_pitch ? 0 : P.x0, bj = P.full_pitch ? 0 : P.y0;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                const int f = r * 32 + lane;
+                const int row = f / (3 * TILE_J), col = f % (3 * TILE_J);
+                const int qi = i0 + row, qj = j0 + col / 3;
+                if (qi < P.x0 + P.w && qj < P.y0 + P.h) {
+                    float* o = P.out_rgb + ((int64_t)(qi - bi) * pitch + (j0 - bj)) * 3 + col;
+                    if (P.accumulate) *o += ob[f];
+                    else *o = ob[f];
+                }
+            }
+            __syncwarp();
+        }
         if (active) {
             const int64_t idx = P.full_pitch ? ((int64_t)pi * cam.H + pj)
                                              : ((int64_t)(pi - P.x0) * P.h + (pj - P.y0));
-            float* o = P.out_rgb + idx * 3;
-            if (P.accumulate) {
-                o[0] += cr; o[1] += cg; o[2] += cb;
-            } else {
-                o[0] = cr; o[1] = cg; o[2] = cb;
-            }
             if (P.out_T) P.out_T[idx] = T;
             st_rays += 1;
             st_hit += nl > 0;
@@ -391,15 +434,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     }
 
     if (P.stats) {
-        unsigned long long v[8] = {st_rays, st_hit, st_layers, 0, 0, 0, st_f64, st_tiles};
+        unsigned long long v[10] = {st_rays, st_hit, st_layers, 0, 0, 0, st_f64, st_tiles, 0, 0};
         // warp-uniform counters are taken from lane 0 only
         if (lane == 0) {
             v[ST_NODES] = st_nodes;
             v[ST_CANDS] = st_cands;
             v[ST_PAIRS] = st_pairs;
+            v[ST_STEPS] = st_steps;
+            v[ST_INSERTS] = st_ins;
         }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) {
+        for (int k = 0; k < 10; ++k) {
             unsigned long long x = v[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
@@ -462,7 +507,9 @@ __global__ void k_trace_closest(const float4* __restrict__ nodes, const float4* 
         const float4 a = __ldg(nodes + (int64_t)node * 4 + 0), b = __ldg(nodes + (int64_t)node * 4 + 1),
                      c = __ldg(nodes + (int64_t)node * 4 + 2), dd = __ldg(nodes + (int64_t)node * 4 + 3);
         const int ch[2] = {__float_as_int(dd.x), __float_as_int(dd.y)};
-        float te[2] = {slab(a.x, a.y, a.z, a.w, b.x, b.y), slab(b.z, b.w, c.x, c.y, c.z, c.w)};
+        // child boxes are (centre, half extent): min = c - h, max = c + h
+        float te[2] = {slab(a.x - a.w, a.y - b.x, a.z - b.y, a.x + a.w, a.y + b.x, a.z + b.y),
+                       slab(b.z - c.y, b.w - c.z, c.x - c.w, b.z + c.y, b.w + c.z, c.x + c.w)};
         // visit near child first: push far first
         const int first = te[0] <= te[1] ? 0 : 1;
         for (int k = 1; k >= 0; --k) {
@@ -529,8 +576,14 @@ CamD make_camd(const rtgs_camera* cam) {
     CamD c;
     for (int a = 0; a < 3; ++a) c.o[a] = cam->position[a];
     for (int a = 0; a < 4; ++a) c.q[a] = cam->rotation[a];
+    double Rm[3][3];
+    quat_to_mat(c.q, Rm);   // utils/quaternion.py:99-121 in float64 (rotation used as given, not normalised)
+    for (int r = 0; r < 3; ++r)
+        for (int k = 0; k < 3; ++k) c.R[r * 3 + k] = Rm[r][k];
     c.fx = cam->focal[0];
     c.fy = cam->focal[1];
+    c.ifx = 1.0 / c.fx;
+    c.ify = 1.0 / c.fy;
     c.W = cam->width;
     c.H = cam->height;
     return c;
@@ -587,7 +640,7 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.tile_counter = s->tile_counter;
     P.stats = want_stats ? s->stats_dev : nullptr;
     CUDA_TRY(cudaMemsetAsync(s->tile_counter, 0, sizeof(unsigned int), stream));
-    if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, 8 * sizeof(unsigned long long), stream));
+    if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, 12 * sizeof(unsigned long long), stream));
     if (depth <= 16) return launch_render_k<16>(s, P, stream);
     return launch_render_k<32>(s, P, stream);
 }

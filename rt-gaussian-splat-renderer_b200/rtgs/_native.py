@@ -26,7 +26,8 @@ class rtgs_camera(C.Structure):
 
 class rtgs_render_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "rays_hit", "layers", "nodes_tested", "candidates",
-                                          "pair_tests", "f64_refinements", "tiles")]
+                                          "pair_tests", "f64_refinements", "tiles", "traversal_steps",
+                                          "insert_rounds", "reserved0", "reserved1")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -51,6 +52,8 @@ SIGNATURES = {
     "rtgs_render": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                               C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp,
                               C.POINTER(rtgs_render_stats)]),
+    "rtgs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
+    "rtgs_host_free": (C.c_int, [_vp]),
     "rtgs_render_host": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_float, _vp, _vp]),
     "rtgs_generate_rays": (C.c_int, [C.POINTER(rtgs_camera), C.c_int, _vp, _vp]),
@@ -98,3 +101,35 @@ def device_count() -> int:
     n = C.c_int(0)
     check(load().rtgs_device_count(C.byref(n)))
     return n.value
+
+
+class PinnedBuffer:
+    """A pinned, device-mapped host buffer (rtgs_host_alloc).  ``view()`` returns a NumPy array over it;
+    every view keeps the buffer alive, so the memory is released only after the last view is gone."""
+
+    def __init__(self, shape, dtype="float32"):
+        import numpy as np
+        self.shape = tuple(int(v) for v in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        check(load().rtgs_host_alloc(self.nbytes, C.byref(p)))
+        self._ptr = p
+
+    @property
+    def ptr(self):
+        return self._ptr.value
+
+    def view(self):
+        import numpy as np
+        buf = (C.c_char * self.nbytes).from_address(self._ptr.value)
+        buf._owner = self          # the ndarray's base keeps `buf`, which keeps this buffer alive
+        return np.frombuffer(buf, dtype=self.dtype).reshape(self.shape)
+
+    def __del__(self):
+        try:
+            if self._ptr is not None and self._ptr.value:
+                load().rtgs_host_free(self._ptr)
+                self._ptr = None
+        except Exception:
+            pass

@@ -42,6 +42,7 @@ class RayTracer:
         self.num_steps = 0
         self.num_samples = 0
         self.last_stats = None
+        self._pinned = None
 
     # ------------------------------------------------------------------ reference API
     def sample(self, depth: int):
@@ -85,15 +86,28 @@ class RayTracer:
             self._render_into(MAX_DEPTH if getattr(self, "_depth", None) is None else self._depth, accumulate=True)
 
     # ------------------------------------------------------------------ additive API
-    def render(self, depth: int = 16, tile=None, collect_stats: bool = False):
+    def render(self, depth: int = 16, tile=None, out=None, pinned: bool = True):
         """Render one complete sample of the current camera and return the image as a host ndarray.
 
         tile = (x0, y0, w, h) restricts the render to a pixel region (returned array is (w,h,3));
         default is the full (W,H,3) frame.  Layout [i, j] (column, row from the bottom); a conventional
-        top-left-origin image is ``img.transpose(1, 0, 2)[::-1]``."""
+        top-left-origin image is ``img.transpose(1, 0, 2)[::-1]``.
+
+        With ``pinned=True`` (default) the image lands in a pinned host buffer owned by this RayTracer
+        and reused by the next ``render()`` of the same size (copy it if you need to keep it); the
+        kernel writes that buffer directly over PCIe.  ``out`` may name any float32 (w,h,3) host array
+        instead; ``pinned=False`` returns a fresh pageable array."""
         W, H = self.buf_size.x, self.buf_size.y
         x0, y0, w, h = (0, 0, W, H) if tile is None else tile
-        out = np.empty((w, h, 3), dtype=np.float32)
+        if out is None:
+            if pinned:
+                if self._pinned is None or self._pinned.shape != (w, h, 3):
+                    self._pinned = _native.PinnedBuffer((w, h, 3))
+                out = self._pinned.view()
+            else:
+                out = np.empty((w, h, 3), dtype=np.float32)
+        elif out.shape != (w, h, 3) or out.dtype != np.float32 or not out.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float32 array of shape (w, h, 3)")
         cam = self.camera.native()
         _native.check(_native.load().rtgs_render_host(self.scene.handle, cam, x0, y0, w, h, int(depth), self.t_cut,
                                                       out.ctypes.data, None))
