@@ -15,8 +15,11 @@
 // ballot/popc (internal children -> stack, leaves -> candidate queue).  Candidates are staged 32 at
 // a time (one lane each, float64: origin shifted to the closest point of the tile's centre ray)
 // and then every lane tests its own ray against every staged candidate with broadcast
-// shared-memory reads.  Hits enter a per-lane sorted k-buffer held in registers (K = 16 or 32
-// nearest entry distances); after the traversal the lane composites its k-buffer front to back.
+// shared-memory reads: first a conservative 5-FMA quadratic (q - 3 as a polynomial of the pixel
+// offset), then - in warp-wide rounds, one pending candidate per lane - the precise test, the entry
+// distance and alpha.  Hits are appended to a per-lane K-entry buffer in shared memory (replace-max
+// when full); after the traversal each lane loads its entries into registers, sorts them with a
+// bitonic network and composites front to back (register-resident k-buffer compositor).
 //
 // Numerics.  The reference's f32 formulation (B^2 - 4AC with a cofactor inverse) is ill-conditioned
 // (SURVEY.md §7 hard part 1), and parity is defined against a float64 evaluation of the
@@ -32,10 +35,11 @@ namespace {
 constexpr int TILE_I = 4, TILE_J = 8;    // pixels per warp tile; lane = li * TILE_J + lj
 constexpr int MACRO_I = 8, MACRO_J = 4;  // tiles per 32x32-pixel macro tile (scheduling locality)
 constexpr int WARPS_PER_CTA = 8;
-constexpr int STACK_CAP = 1024;
+constexpr int STACK_CAP = 512;
 constexpr int STACK_SINGLE = STACK_CAP - 160;  // above this, pop one node at a time (DFS bound)
 constexpr int CQ_CAP = 96;
 constexpr int BATCH = 32;
+constexpr int REC_Q = 5;                 // quads per staged record (80-byte stride: conflict-free gathers)
 constexpr unsigned FULL = 0xffffffffu;
 
 struct RenderParams {
@@ -56,11 +60,27 @@ struct RenderParams {
     unsigned long long* stats;
 };
 
-struct __align__(16) WarpShared {
-    float4 rec[BATCH][4];  // {W00 W01 W02 W10} {W11 W12 W20 W21} {W22 e0.xyz} {g0.xyz t_c}
-    float4 aux[BATCH];     // {opacity, sorted position (int bits), q band, unused}
+struct __align__(16) TraversalScratch {
+    // precise record: {W00 W01 W02 W10} {W11 W12 W20 W21} {W22 e0.xyz} {g0.xyz t_c} {opacity, s, band, -}
+    float4 rec[BATCH][REC_Q];
+    // coarse test: S(a,b) = c0 + a (c1 + a c3 + b c4) + b (c2 + b c5) < 0  <=>  possibly q < 3 + band
+    float4 poly[BATCH][2];
     int stack[STACK_CAP];
     int cq[CQ_CAP];
+};
+
+template <int K>
+struct __align__(16) WarpShared {
+    union {
+        TraversalScratch t;        // traversal phase
+        struct {                   // compositing phase: hits in ascending entry distance
+            int so_i[K][32];
+            float so_a[K][32];
+        } c;
+    };
+    float kb_t[K][32];     // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
+    int kb_i[K][32];
+    float kb_a[K][32];
 };
 
 enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS, ST_COUNT = 12 };
@@ -77,24 +97,13 @@ __device__ __noinline__ ExactHit exact_eval(const float4* __restrict__ raw, cons
     return exact_intersect(p, q, sc, cam.o, d);
 }
 
-// ---- register k-buffer: sorted ascending by entry distance, ties keep arrival order -----------
-template <int K>
-__device__ __forceinline__ void kb_insert(float (&kt)[K], int (&ki)[K], float (&ka)[K], float t, int id,
-                                          float a) {
-    if (!(t < kt[K - 1])) return;
-#pragma unroll
-    for (int s = K - 1; s >= 1; --s) {
-        const bool up = t < kt[s - 1];
-        const bool here = (!up) && (t < kt[s]);
-        kt[s] = up ? kt[s - 1] : (here ? t : kt[s]);
-        ki[s] = up ? ki[s - 1] : (here ? id : ki[s]);
-        ka[s] = up ? ka[s - 1] : (here ? a : ka[s]);
-    }
-    if (t < kt[0]) {
-        kt[0] = t;
-        ki[0] = id;
-        ka[0] = a;
-    }
+// Exact ordering of two hits of one ray whose float32 entry distances are within rounding of each
+// other: float64 t1 from the raw parameters, ties broken by sorted position (rare path).
+__device__ __noinline__ bool exact_less(const float4* __restrict__ raw, const CamD& cam, int sa, int sb, int pi,
+                                        int pj) {
+    const ExactHit a = exact_eval(raw, cam, sa, pi, pj);
+    const ExactHit b = exact_eval(raw, cam, sb, pi, pj);
+    return a.t1 < b.t1 || (a.t1 == b.t1 && sa < sb);
 }
 
 // ---- SH basis, gaussian.py:149-163 (incl. the `5z^2 - 3z` term at :160 exactly as coded) ------
@@ -157,7 +166,8 @@ __device__ __forceinline__ float sqrt_approx(float x) {
 template <int K>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_render(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    WarpShared<K>& ws = reinterpret_cast<WarpShared<K>*>(smem_raw)[threadIdx.x >> 5];
+    TraversalScratch& tr = ws.t;
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const CamD& cam = P.cam;
@@ -166,6 +176,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
 
+#pragma unroll 1
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(P.tile_counter, 1u);
@@ -179,13 +190,33 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
         const bool active = pi < P.x0 + P.w && pj < P.y0 + P.h;
 
-        // ---- rays (float64 setup, camera.py:46-52): centre ray d0, own ray d = d0 + delta -----
-        const d3 d0 = cam_dir(cam, (double)i0 + 0.5 * TILE_I, (double)j0 + 0.5 * TILE_J);
+        // ---- rays (float64 setup, camera.py:46-52) ---------------------------------------------
+        // Image-plane coordinates: px = (i + 0.5 - W/2)/fx.  Tile centre (px0, py0); own offset
+        // (a, b) = (px - px0, py - py0).  UNNORMALISED directions are linear in (a, b):
+        //   D(a,b) = R (px0 + a, py0 + b, -1) = D0 + a Rx + b Ry,
+        // the reference's direction is d = D / sqrt(px^2 + py^2 + 1); d0 likewise, d = d0 + delta.
+        const double px0 = ((double)i0 + 0.5 * TILE_I - 0.5 * cam.W) * cam.ifx;
+        const double py0 = ((double)j0 + 0.5 * TILE_J - 0.5 * cam.H) * cam.ify;
+        const d3 D0 = cam_rot(cam, px0, py0, -1.0);
+        const double n0 = rsqrt(px0 * px0 + py0 * py0 + 1.0);
+        const d3 d0 = d3make(D0.x * n0, D0.y * n0, D0.z * n0);
         const double inv_d0d0 = 1.0 / d3dot(d0, d0);
-        d3 dw = active ? cam_dir(cam, (double)pi + 0.5, (double)pj + 0.5) : d0;
-        const float dlx = (float)(dw.x - d0.x), dly = (float)(dw.y - d0.y), dlz = (float)(dw.z - d0.z);
-        const float dlen = sqrtf(dlx * dlx + dly * dly + dlz * dlz);
-        float dl_max = dlen;
+        const double ad = active ? ((double)(pi - i0) + 0.5 - 0.5 * TILE_I) * cam.ifx : 0.0;
+        const double bd = active ? ((double)(pj - j0) + 0.5 - 0.5 * TILE_J) * cam.ify : 0.0;
+        float dlx, dly, dlz;          // delta = d - d0
+        float dnx, dny, dnz;          // normalize(d) for the SH basis (gaussian.py:200)
+        {
+            const double px = px0 + ad, py = py0 + bd;
+            const double nn = rsqrt(px * px + py * py + 1.0);
+            const d3 dw = d3make((D0.x + ad * cam.R[0] + bd * cam.R[1]) * nn, (D0.y + ad * cam.R[3] + bd * cam.R[4]) * nn,
+                                 (D0.z + ad * cam.R[6] + bd * cam.R[7]) * nn);
+            dlx = (float)(dw.x - d0.x); dly = (float)(dw.y - d0.y); dlz = (float)(dw.z - d0.z);
+            const double il = rsqrt(d3dot(dw, dw));
+            dnx = (float)(dw.x * il); dny = (float)(dw.y * il); dnz = (float)(dw.z * il);
+        }
+        const float pa = (float)ad, pb = (float)bd;
+        const float a_max = (float)(0.5 * TILE_I * fabs(cam.ifx)), b_max = (float)(0.5 * TILE_J * fabs(cam.ify));
+        float dl_max = sqrtf(dlx * dlx + dly * dly + dlz * dlz);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) dl_max = fmaxf(dl_max, __shfl_xor_sync(FULL, dl_max, o));
 
@@ -207,55 +238,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             }
         }
 
-        // ---- k-buffer ------------------------------------------------------------------------
-        float kt[K], ka[K];
-        int ki[K];
-#pragma unroll
-        for (int k = 0; k < K; ++k) {
-            kt[k] = INFINITY;
-            ka[k] = 0.0f;
-            ki[k] = -1;
-        }
-        // one pending candidate hit per lane; the hit-only work (entry distance, alpha, float64
-        // refinement, k-buffer insertion) runs in warp-wide rounds when some lane gets a second one
+        // ---- per-lane hit buffer (shared memory, unsorted; replace-max once K entries are held) --
+        int cnt = 0;
+        float kmax_t = INFINITY;
+        int kmax_slot = 0;
+
+        // one pending candidate per lane; the precise test and the hit-only work (entry distance,
+        // alpha, float64 refinement, buffer append) run in warp-wide rounds
         bool pend = false;
-        float pend_q = 0.0f, pend_iA = 0.0f, pend_Bh = 0.0f;
         int pend_c = 0;
-        auto flush = [&]() {
-            if (pend) {
-                const float4 ax = ws.aux[pend_c];
-                const float tc = ws.rec[pend_c][3].w;
-                float q = pend_q;
-                // disc/A^2 = (3 - q)/A  ->  tau = -Bh/A - sqrt((3 - q)/A)
-                const float tau = -pend_Bh * pend_iA - sqrt_approx(fmaxf(3.0f - q, 0.0f) * pend_iA);
-                float t1 = tc + tau;
-                bool hit = (q < 3.0f) && (t1 > 0.0f);
-                const bool near_q = fabsf(q - 3.0f) < ax.z;
-                const bool near_t = fabsf(t1) <= 2e-6f * (fabsf(tc) + fabsf(tau));
-                if (near_q || near_t) {
-                    const ExactHit e = exact_eval(P.raw, cam, __float_as_int(ax.y), pi, pj);
-                    hit = e.hit && (e.t1 > 0.0);
-                    q = (float)e.q;
-                    t1 = (float)e.t1;
-                    st_f64 += 1;
-                }
-                // alpha = opacity * exp(-q)  (gaussian.py:197-198)
-                if (hit) kb_insert<K>(kt, ki, ka, t1, __float_as_int(ax.y), ax.x * __expf(-q));
-                pend = false;
-            }
-            st_ins += 1;
-        };
 
         int top = 1, ncq = 0;
-        if (lane == 0) ws.stack[0] = 0;
+        if (lane == 0) tr.stack[0] = 0;
         __syncwarp();
 
         // ================================ traversal ==========================================
+#pragma unroll 1
         while (top > 0 || ncq > 0) {
             if (top > 0) {
                 const int take = top > STACK_SINGLE ? 1 : min(32, top);
                 int node = -1;
-                if (lane < take) node = ws.stack[top - 1 - lane];
+                if (lane < take) node = tr.stack[top - 1 - lane];
                 top -= take;
                 __syncwarp();
                 bool h0 = false, h1 = false;
@@ -274,134 +277,234 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 st_steps += 1;
                 const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
                 const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
-                if (h0 && c0 >= 0) ws.stack[top + __popc(mI0 & lt_mask)] = c0;
+                if (h0 && c0 >= 0) tr.stack[top + __popc(mI0 & lt_mask)] = c0;
                 const int topa = top + __popc(mI0);
-                if (h1 && c1 >= 0) ws.stack[topa + __popc(mI1 & lt_mask)] = c1;
+                if (h1 && c1 >= 0) tr.stack[topa + __popc(mI1 & lt_mask)] = c1;
                 top = topa + __popc(mI1);
-                if (h0 && c0 < 0) ws.cq[ncq + __popc(mL0 & lt_mask)] = ~c0;
+                if (h0 && c0 < 0) tr.cq[ncq + __popc(mL0 & lt_mask)] = ~c0;
                 const int ncqa = ncq + __popc(mL0);
-                if (h1 && c1 < 0) ws.cq[ncqa + __popc(mL1 & lt_mask)] = ~c1;
+                if (h1 && c1 < 0) tr.cq[ncqa + __popc(mL1 & lt_mask)] = ~c1;
                 ncq = ncqa + __popc(mL1);
                 __syncwarp();
             }
             // -------- candidate batch: stage (one lane each, float64) then test (all lanes) --
+#pragma unroll 1
             while (ncq >= BATCH || (top == 0 && ncq > 0)) {
                 const int m = min(BATCH, ncq);
                 ncq -= m;
                 if (lane < m) {
-                    const int s = ws.cq[ncq + lane];
+                    const int s = tr.cq[ncq + lane];
                     const float4 g0 = __ldg(P.geo + (int64_t)s * 4 + 0), g1 = __ldg(P.geo + (int64_t)s * 4 + 1),
                                  g2 = __ldg(P.geo + (int64_t)s * 4 + 2), g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
                     const double W00 = g1.x, W01 = g1.y, W02 = g1.z, W10 = g1.w, W11 = g2.x, W12 = g2.y,
                                  W20 = g2.z, W21 = g2.w, W22 = g3.x;
+                    auto Wmul = [&](const d3& v) {
+                        return d3make(W00 * v.x + W01 * v.y + W02 * v.z, W10 * v.x + W11 * v.y + W12 * v.z,
+                                      W20 * v.x + W21 * v.y + W22 * v.z);
+                    };
                     const d3 v = d3make((double)g0.x - cam.o[0], (double)g0.y - cam.o[1], (double)g0.z - cam.o[2]);
+                    // precise record: origin shifted to the closest point of the tile-centre ray
                     const double tc = d3dot(v, d0) * inv_d0d0;
-                    const d3 u = d3make(tc * d0.x - v.x, tc * d0.y - v.y, tc * d0.z - v.z);
-                    const double e0x = W00 * u.x + W01 * u.y + W02 * u.z, e0y = W10 * u.x + W11 * u.y + W12 * u.z,
-                                 e0z = W20 * u.x + W21 * u.y + W22 * u.z;
-                    const double gx = W00 * d0.x + W01 * d0.y + W02 * d0.z, gy = W10 * d0.x + W11 * d0.y + W12 * d0.z,
-                                 gz = W20 * d0.x + W21 * d0.y + W22 * d0.z;
-                    // conservative bound on |e| over the tile for the float32 error band of q
+                    const d3 e0 = Wmul(d3make(tc * d0.x - v.x, tc * d0.y - v.y, tc * d0.z - v.z));
+                    const d3 gd = Wmul(d0);
                     const float wn = sqrtf(g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w + g2.x * g2.x +
                                            g2.y * g2.y + g2.z * g2.z + g2.w * g2.w + g3.x * g3.x);
-                    const float eb = (float)sqrt(e0x * e0x + e0y * e0y + e0z * e0z) + fabsf((float)tc) * dl_max * wn;
+                    const float eb = (float)sqrt(d3dot(e0, e0)) + fabsf((float)tc) * dl_max * wn;
                     const float band = 4e-6f * (3.0f + eb * eb);
-                    ws.rec[lane][0] = g1;
-                    ws.rec[lane][1] = g2;
-                    ws.rec[lane][2] = make_float4(g3.x, (float)e0x, (float)e0y, (float)e0z);
-                    ws.rec[lane][3] = make_float4((float)gx, (float)gy, (float)gz, (float)tc);
-                    ws.aux[lane] = make_float4(g0.w, __int_as_float(s), band, 0.0f);
+                    tr.rec[lane][0] = g1;
+                    tr.rec[lane][1] = g2;
+                    tr.rec[lane][2] = make_float4(g3.x, (float)e0.x, (float)e0.y, (float)e0.z);
+                    tr.rec[lane][3] = make_float4((float)gd.x, (float)gd.y, (float)gd.z, (float)tc);
+                    tr.rec[lane][4] = make_float4(g0.w, __int_as_float(s), band, 0.0f);
+                    // coarse quadratic: with o' = W (o - p) = -W v and G(a,b) = W D(a,b) = G0 + a Gx + b Gy,
+                    //   q(a,b) = |o' x G|^2 / |G|^2 = N/Dn,  m = o' x G = M0 + a Mx + b My.
+                    // S = N - (3 + band) Dn - margin, margin bounding the float32 evaluation error.
+                    const d3 op = Wmul(d3make(-v.x, -v.y, -v.z));
+                    const d3 G0 = Wmul(D0);
+                    const d3 Gx = Wmul(d3make(cam.R[0], cam.R[3], cam.R[6]));
+                    const d3 Gy = Wmul(d3make(cam.R[1], cam.R[4], cam.R[7]));
+                    const d3 M0 = d3cross(op, G0), Mx = d3cross(op, Gx), My = d3cross(op, Gy);
+                    const double lim = 3.0 + (double)band;
+                    const double m00 = d3dot(M0, M0), m0x = d3dot(M0, Mx), m0y = d3dot(M0, My), mxx = d3dot(Mx, Mx),
+                                 mxy = d3dot(Mx, My), myy = d3dot(My, My);
+                    const double g00 = lim * d3dot(G0, G0), g0x = lim * d3dot(G0, Gx), g0y = lim * d3dot(G0, Gy),
+                                 gxx = lim * d3dot(Gx, Gx), gxy = lim * d3dot(Gx, Gy), gyy = lim * d3dot(Gy, Gy);
+                    const double am = a_max, bm = b_max;
+                    // magnitude of the terms BEFORE cancellation (N and Dn parts separately)
+                    const double E = m00 + g00 + 2.0 * am * (fabs(m0x) + fabs(g0x)) + 2.0 * bm * (fabs(m0y) + fabs(g0y)) +
+                                     am * am * (mxx + gxx) + 2.0 * am * bm * (fabs(mxy) + fabs(gxy)) + bm * bm * (myy + gyy);
+                    tr.poly[lane][0] = make_float4((float)(m00 - g00 - 2e-6 * E), (float)(2.0 * (m0x - g0x)),
+                                                   (float)(2.0 * (m0y - g0y)), (float)(mxx - gxx));
+                    tr.poly[lane][1] = make_float4((float)(2.0 * (mxy - gxy)), (float)(myy - gyy), 0.0f, 0.0f);
                 }
                 __syncwarp();
                 st_cands += (unsigned)m;
                 st_pairs += 32ull * (unsigned)m;
-                for (int c = 0; c < m; ++c) {
-                    const float4 r0 = ws.rec[c][0], r1 = ws.rec[c][1], r2 = ws.rec[c][2], r3 = ws.rec[c][3];
-                    const float band = ws.aux[c].z;
-                    const float wx = r0.x * dlx + r0.y * dly + r0.z * dlz;
-                    const float wy = r0.w * dlx + r1.x * dly + r1.y * dlz;
-                    const float wz = r1.z * dlx + r1.w * dly + r2.x * dlz;
-                    const float tc = r3.w;
-                    const float dx = r3.x + wx, dy = r3.y + wy, dz = r3.z + wz;        // d' = W d
-                    const float ex = r2.y + tc * wx, ey = r2.z + tc * wy, ez = r2.w + tc * wz;  // W (r(tc) - p)
-                    const float A = dx * dx + dy * dy + dz * dz;
-                    const float Bh = ex * dx + ey * dy + ez * dz;
-                    const float mx = ey * dz - ez * dy, my = ez * dx - ex * dz, mz = ex * dy - ey * dx;
-                    const float iA = rcp_approx(A);
-                    const float q = (mx * mx + my * my + mz * mz) * iA;   // min Mahalanobis^2 along the ray
-                    const bool cand = active && (q < 3.0f + band);
-                    if (__any_sync(FULL, cand && pend)) flush();
+#pragma unroll 1
+                for (int c = 0; c <= m; ++c) {
+                    bool cand = false;
+                    if (c < m) {
+                        const float4 p0 = tr.poly[c][0];
+                        const float2 p1 = *reinterpret_cast<const float2*>(&tr.poly[c][1]);
+                        const float ta = fmaf(pa, p0.w, fmaf(pb, p1.x, p0.y));   // c1 + a c3 + b c4
+                        const float tb = fmaf(pb, p1.y, p0.z);                   // c2 + b c5
+                        const float S = fmaf(pa, ta, fmaf(pb, tb, p0.x));
+                        cand = active && (S < 0.0f);
+                    }
+                    // flush when a lane gets a second candidate, and once at the end of the batch
+                    // (the staged records are about to be overwritten)
+                    if (__any_sync(FULL, pend && (cand || c == m))) {
+                        if (pend) {
+                            const float4* rc = tr.rec[pend_c];
+                            const float4 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3], ax = rc[4];
+                            const float wx = r0.x * dlx + r0.y * dly + r0.z * dlz;
+                            const float wy = r0.w * dlx + r1.x * dly + r1.y * dlz;
+                            const float wz = r1.z * dlx + r1.w * dly + r2.x * dlz;
+                            const float tc = r3.w;
+                            const float dx = r3.x + wx, dy = r3.y + wy, dz = r3.z + wz;        // d' = W d
+                            const float ex = r2.y + tc * wx, ey = r2.z + tc * wy, ez = r2.w + tc * wz;  // W (r(tc) - p)
+                            const float A = dx * dx + dy * dy + dz * dz;
+                            const float Bh = ex * dx + ey * dy + ez * dz;
+                            const float mx = ey * dz - ez * dy, my = ez * dx - ex * dz, mz = ex * dy - ey * dx;
+                            const float iA = rcp_approx(A);
+                            float q = (mx * mx + my * my + mz * mz) * iA;   // min Mahalanobis^2 along the ray
+                            // tau = -Bh/A - sqrt((3 - q)/A)  (near root relative to tc)
+                            const float tau = -Bh * iA - sqrt_approx(fmaxf(3.0f - q, 0.0f) * iA);
+                            float t1 = tc + tau;
+                            bool hit = (q < 3.0f) && (t1 > 0.0f);
+                            const bool near_q = fabsf(q - 3.0f) < ax.z;
+                            const bool near_t = (q < 3.0f + ax.z) && fabsf(t1) <= 2e-6f * (fabsf(tc) + fabsf(tau));
+                            if (near_q || near_t) {
+                                const ExactHit e = exact_eval(P.raw, cam, __float_as_int(ax.y), pi, pj);
+                                hit = e.hit && (e.t1 > 0.0);
+                                q = (float)e.q;
+                                t1 = (float)e.t1;
+                                st_f64 += 1;
+                            }
+                            if (hit) {
+                                const float alpha = ax.x * __expf(-q);   // opacity * exp(-q)  (gaussian.py:197-198)
+                                int slot = -1;
+                                if (cnt < K) slot = cnt++;
+                                else if (t1 < kmax_t) slot = kmax_slot;
+                                if (slot >= 0) {
+                                    ws.kb_t[slot][lane] = t1;
+                                    ws.kb_i[slot][lane] = __float_as_int(ax.y);
+                                    ws.kb_a[slot][lane] = alpha;
+                                    if (cnt == K) {   // buffer full: track the farthest entry
+                                        float mt = -INFINITY;
+                                        int ms = 0;
+#pragma unroll 4
+                                        for (int k = 0; k < K; ++k) {
+                                            const float t = ws.kb_t[k][lane];
+                                            if (t > mt) { mt = t; ms = k; }
+                                        }
+                                        kmax_t = mt;
+                                        kmax_slot = ms;
+                                    }
+                                }
+                            }
+                            pend = false;
+                        }
+                        st_ins += 1;
+                    }
                     if (cand) {
                         pend = true;
-                        pend_q = q;
-                        pend_iA = iA;
-                        pend_Bh = Bh;
                         pend_c = c;
                     }
                 }
-                if (__any_sync(FULL, pend)) flush();   // the staged records are about to be overwritten
                 __syncwarp();
             }
         }
 
-        // ---- near-tie resolution: adjacent entries closer than a few ulp are ordered in f64 ---
+        // ---- order the hits by ascending entry distance: rank counting into the compositing list --
+        // rank_i = #{j : t_j < t_i}; pairs within float32 rounding of each other are ordered by their
+        // float64 entry distances (exact_less).  The traversal scratch is dead from here on.
+        int maxcnt = cnt;
 #pragma unroll
-        for (int k = 0; k + 1 < K; ++k) {
-            if (kt[k + 1] < INFINITY && (kt[k + 1] - kt[k]) <= 2e-6f * fabsf(kt[k + 1])) {
-                const ExactHit ea = exact_eval(P.raw, cam, ki[k], pi, pj);
-                const ExactHit eb = exact_eval(P.raw, cam, ki[k + 1], pi, pj);
-                st_f64 += 2;
-                if (eb.t1 < ea.t1 || (eb.t1 == ea.t1 && ki[k + 1] < ki[k])) {
-                    const float tt = kt[k]; kt[k] = kt[k + 1]; kt[k + 1] = tt;
-                    const float ta = ka[k]; ka[k] = ka[k + 1]; ka[k + 1] = ta;
-                    const int tid = ki[k]; ki[k] = ki[k + 1]; ki[k + 1] = tid;
+        for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
+        __syncwarp();
+        if (maxcnt > 0) {
+            float tk[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) tk[k] = k < cnt ? ws.kb_t[k][lane] : INFINITY;
+#pragma unroll 1
+            for (int i = 0; i < maxcnt; ++i) {
+                if (i < cnt) {
+                    const float ti_ = ws.kb_t[i][lane];
+                    const float band = 2e-6f * fabsf(ti_);
+                    int rank = 0, nnear = 0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        rank += tk[j] < ti_;
+                        nnear += fabsf(tk[j] - ti_) <= band;
+                    }
+                    const int id = ws.kb_i[i][lane];
+                    if (nnear > 1) {   // rare: resolve near ties exactly
+                        rank = 0;
+#pragma unroll 1
+                        for (int j = 0; j < cnt; ++j) {
+                            if (j == i) continue;
+                            const float tj_ = ws.kb_t[j][lane];
+                            if (fabsf(tj_ - ti_) <= band) {
+                                rank += exact_less(P.raw, cam, ws.kb_i[j][lane], id, pi, pj);
+                                st_f64 += 2;
+                            } else {
+                                rank += tj_ < ti_;
+                            }
+                        }
+                    }
+                    ws.c.so_i[rank][lane] = id;
+                    ws.c.so_a[rank][lane] = ws.kb_a[i][lane];
                 }
             }
         }
+        __syncwarp();
 
         // ================================ compositing ========================================
         // accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98), rgb = color +
         // eval_sh(normalize(dir)) (gaussian.py:199-200).
-        float Y[15];
-        {
-            const double il = 1.0 / sqrt(d3dot(dw, dw));
-            sh_basis((float)(dw.x * il), (float)(dw.y * il), (float)(dw.z * il), Y);
-        }
         float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
         int nl = 0;
+        {
+            float Y[15];
+            sh_basis(dnx, dny, dnz, Y);
+            const int nmine = min(cnt, P.depth);
+            const int nloop = min(maxcnt, P.depth);
+#pragma unroll 1
+            for (int k = 0; k < nloop; ++k) {
+                if (k < nmine && T >= P.t_cut) {
+                    const int s = ws.c.so_i[k][lane];
+                    const float alpha = ws.c.so_a[k][lane];
+                    const float4 g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
+                    float r = g3.y, g = g3.z, b = g3.w;
+                    if (P.has_sh) {
+                        const float4* sp = P.shp + (int64_t)s * 12;
+                        float v[48];
 #pragma unroll
-        for (int k = 0; k < K; ++k) {
-            if (k < P.depth && ki[k] >= 0 && T >= P.t_cut) {
-                const int s = ki[k];
-                const float4 g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
-                float r = g3.y, g = g3.z, b = g3.w;
-                if (P.has_sh) {
-                    const float4* sp = P.shp + (int64_t)s * 12;
-                    float v[48];
+                        for (int f = 0; f < 12; ++f) {
+                            const float4 x = __ldg(sp + f);
+                            v[4 * f] = x.x; v[4 * f + 1] = x.y; v[4 * f + 2] = x.z; v[4 * f + 3] = x.w;
+                        }
 #pragma unroll
-                    for (int f = 0; f < 12; ++f) {
-                        const float4 x = __ldg(sp + f);
-                        v[4 * f] = x.x; v[4 * f + 1] = x.y; v[4 * f + 2] = x.z; v[4 * f + 3] = x.w;
+                        for (int j = 0; j < 15; ++j) {
+                            r = fmaf(Y[j], v[3 * j + 0], r);
+                            g = fmaf(Y[j], v[3 * j + 1], g);
+                            b = fmaf(Y[j], v[3 * j + 2], b);
+                        }
                     }
-#pragma unroll
-                    for (int j = 0; j < 15; ++j) {
-                        r = fmaf(Y[j], v[3 * j + 0], r);
-                        g = fmaf(Y[j], v[3 * j + 1], g);
-                        b = fmaf(Y[j], v[3 * j + 2], b);
-                    }
+                    const float wgt = T * alpha;
+                    cr = fmaf(wgt, r, cr);
+                    cg = fmaf(wgt, g, cg);
+                    cb = fmaf(wgt, b, cb);
+                    T *= 1.0f - alpha;
+                    ++nl;
                 }
-                const float wgt = T * ka[k];
-                cr = fmaf(wgt, r, cr);
-                cg = fmaf(wgt, g, cg);
-                cb = fmaf(wgt, b, cb);
-                T *= 1.0f - ka[k];
-                ++nl;
             }
         }
         // ---- framebuffer write: stage the tile in shared memory so that every store instruction
         // covers whole 32-byte sectors (each tile column is 8 pixels = 96 contiguous bytes) --------
         {
-            float* ob = reinterpret_cast<float*>(&ws.rec[0][0]);
+            float* ob = reinterpret_cast<float*>(&ws.kb_t[0][0]);
             __syncwarp();
             ob[lane * 3 + 0] = cr;
             ob[lane * 3 + 1] = cg;
@@ -592,7 +695,7 @@ CamD make_camd(const rtgs_camera* cam) {
 template <int K>
 int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     static int blocks_per_sm[16] = {0};
-    const size_t smem = sizeof(WarpShared) * WARPS_PER_CTA;
+    const size_t smem = sizeof(WarpShared<K>) * WARPS_PER_CTA;
     int dev = s->device;
     if (dev < 0 || dev >= 16) dev = 0;
     if (blocks_per_sm[dev] == 0) {
