@@ -16,7 +16,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIBDIR = HERE / "lib"
-LIB = LIBDIR / "librtgs_b200.so"
+LIB = LIBDIR / os.environ.get("RTGS_LIB_NAME", "librtgs_b200.so")
 SOURCES = ["abi.cu", "lbvh.cu", "render.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
@@ -24,7 +24,7 @@ FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
-]
+] + os.environ.get("RTGS_NVCC_EXTRA", "").split()
 
 
 def _stale() -> bool:

@@ -35,10 +35,16 @@ namespace {
 constexpr int TILE_I = 4, TILE_J = 8;    // pixels per warp tile; lane = li * TILE_J + lj
 constexpr int MACRO_I = 8, MACRO_J = 4;  // tiles per 32x32-pixel macro tile (scheduling locality)
 constexpr int WARPS_PER_CTA = 8;
-constexpr int STACK_CAP = 512;
-constexpr int STACK_SINGLE = STACK_CAP - 160;  // above this, pop one node at a time (DFS bound)
+#ifndef RTGS_STACK_CAP
+#define RTGS_STACK_CAP 512
+#endif
+#ifndef RTGS_BATCH
+#define RTGS_BATCH 32
+#endif
+constexpr int STACK_CAP = RTGS_STACK_CAP;
+constexpr int STACK_SINGLE = STACK_CAP - 100;   // growth/step <= 32, then DFS depth <= 62  // above this, pop one node at a time (DFS bound)
 constexpr int CQ_CAP = 96;
-constexpr int BATCH = 32;
+constexpr int BATCH = RTGS_BATCH;
 constexpr int REC_Q = 5;                 // quads per staged record (80-byte stride: conflict-free gathers)
 constexpr unsigned FULL = 0xffffffffu;
 
@@ -163,7 +169,9 @@ __device__ __forceinline__ float sqrt_approx(float x) {
     return r;
 }
 
-template <int K>
+// STATS = true compiles the per-render counters in (rtgs_render with a stats pointer); the timed path
+// uses STATS = false so that the ten 64-bit counters do not occupy registers.
+template <int K, bool STATS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_render(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpShared<K>& ws = reinterpret_cast<WarpShared<K>*>(smem_raw)[threadIdx.x >> 5];
@@ -175,6 +183,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
 
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
+#define ST(expr) do { if (STATS) { expr; } } while (0)
 
 #pragma unroll 1
     for (;;) {
@@ -273,8 +282,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
                     h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
                 }
-                st_nodes += 2ull * (unsigned)take;
-                st_steps += 1;
+                ST(st_nodes += 2ull * (unsigned)take);
+                ST(st_steps += 1);
                 const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
                 const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
                 if (h0 && c0 >= 0) tr.stack[top + __popc(mI0 & lt_mask)] = c0;
@@ -338,8 +347,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     tr.poly[lane][1] = make_float4((float)(2.0 * (mxy - gxy)), (float)(myy - gyy), 0.0f, 0.0f);
                 }
                 __syncwarp();
-                st_cands += (unsigned)m;
-                st_pairs += 32ull * (unsigned)m;
+                ST(st_cands += (unsigned)m);
+                ST(st_pairs += 32ull * (unsigned)m);
 #pragma unroll 1
                 for (int c = 0; c <= m; ++c) {
                     bool cand = false;
@@ -379,7 +388,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                                 hit = e.hit && (e.t1 > 0.0);
                                 q = (float)e.q;
                                 t1 = (float)e.t1;
-                                st_f64 += 1;
+                                ST(st_f64 += 1);
                             }
                             if (hit) {
                                 const float alpha = ax.x * __expf(-q);   // opacity * exp(-q)  (gaussian.py:197-198)
@@ -405,7 +414,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                             }
                             pend = false;
                         }
-                        st_ins += 1;
+                        ST(st_ins += 1);
                     }
                     if (cand) {
                         pend = true;
@@ -447,7 +456,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                             const float tj_ = ws.kb_t[j][lane];
                             if (fabsf(tj_ - ti_) <= band) {
                                 rank += exact_less(P.raw, cam, ws.kb_i[j][lane], id, pi, pj);
-                                st_f64 += 2;
+                                ST(st_f64 += 2);
                             } else {
                                 rank += tj_ < ti_;
                             }
@@ -529,14 +538,14 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             const int64_t idx = P.full_pitch ? ((int64_t)pi * cam.H + pj)
                                              : ((int64_t)(pi - P.x0) * P.h + (pj - P.y0));
             if (P.out_T) P.out_T[idx] = T;
-            st_rays += 1;
-            st_hit += nl > 0;
-            st_layers += (unsigned)nl;
+            ST(st_rays += 1);
+            ST(st_hit += nl > 0);
+            ST(st_layers += (unsigned)nl);
         }
-        if (lane == 0) st_tiles += 1;
+        ST(if (lane == 0) st_tiles += 1);
     }
 
-    if (P.stats) {
+    if (STATS && P.stats) {
         unsigned long long v[10] = {st_rays, st_hit, st_layers, 0, 0, 0, st_f64, st_tiles, 0, 0};
         // warp-uniform counters are taken from lane 0 only
         if (lane == 0) {
@@ -555,6 +564,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         }
     }
 }
+
+#undef ST
 
 // ---- Camera.generate_ray_field (camera.py:57-71): (W,H,8) = origin, direction, start, end -----
 __global__ void k_generate_rays(const CamD cam, float* __restrict__ rays) {
@@ -692,16 +703,16 @@ CamD make_camd(const rtgs_camera* cam) {
     return c;
 }
 
-template <int K>
+template <int K, bool STATS>
 int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     static int blocks_per_sm[16] = {0};
     const size_t smem = sizeof(WarpShared<K>) * WARPS_PER_CTA;
     int dev = s->device;
     if (dev < 0 || dev >= 16) dev = 0;
     if (blocks_per_sm[dev] == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_render<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(k_render<K, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render<K>, WARPS_PER_CTA * 32, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render<K, STATS>, WARPS_PER_CTA * 32, smem));
         if (nb < 1) {
             rtgs_set_error("render kernel does not fit on an SM (smem %zu)", smem);
             return RTGS_ERR_CUDA;
@@ -712,7 +723,7 @@ int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     const int need = (P.ntiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_render<K><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+    k_render<K, STATS><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return RTGS_OK;
 }
@@ -744,8 +755,8 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.stats = want_stats ? s->stats_dev : nullptr;
     CUDA_TRY(cudaMemsetAsync(s->tile_counter, 0, sizeof(unsigned int), stream));
     if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, 12 * sizeof(unsigned long long), stream));
-    if (depth <= 16) return launch_render_k<16>(s, P, stream);
-    return launch_render_k<32>(s, P, stream);
+    if (depth <= 16) return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
+    return want_stats ? launch_render_k<32, true>(s, P, stream) : launch_render_k<32, false>(s, P, stream);
 }
 
 int rtgs_launch_generate_rays(const rtgs_camera* cam, float* rays, cudaStream_t stream) {
