@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIBDIR = HERE / "lib"
 LIB = LIBDIR / os.environ.get("RTGS_LIB_NAME", "librtgs_b200.so")
-SOURCES = ["abi.cu", "lbvh.cu", "render.cu"]
+SOURCES = ["abi.cu", "lbvh.cu", "render.cu", "tile_lists.cu", "shade.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

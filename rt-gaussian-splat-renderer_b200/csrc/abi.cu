@@ -47,8 +47,9 @@ void free_scene(rtgs_scene* s) {
     DeviceGuard g(s->device);
     cudaFree(s->pos); cudaFree(s->rot); cudaFree(s->scale); cudaFree(s->color); cudaFree(s->opacity);
     cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
-    cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes);
-    cudaFree(s->tile_counter); cudaFree(s->stats_dev); cudaFree(s->stage_rgb); cudaFree(s->stage_T);
+    cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox);
+    cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
+    cudaFree(s->counters); cudaFree(s->stats_dev); cudaFree(s->stage_rgb); cudaFree(s->stage_T);
     if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
     if (s->pinned_T) cudaFreeHost(s->pinned_T);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -91,7 +92,8 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     if (has_sh) TRY(dev_alloc(&s->shp, n * 12));
     TRY(dev_alloc(&s->raw, n * 3));
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
-    TRY(dev_alloc(&s->tile_counter, 1));
+    TRY(dev_alloc(&s->leafbox, n * 2));
+    TRY(dev_alloc(&s->counters, 8));
     TRY(dev_alloc(&s->stats_dev, 12));
     return RTGS_OK;
 }
@@ -298,7 +300,7 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
         CUDA_TRY(cudaStreamSynchronize(st));
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
         stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
-        stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->reserved[0] = stats->reserved[1] = 0;
+        stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->fallback_tiles = hs[10]; stats->reserved = 0;
     }
     return RTGS_OK;
 }

@@ -46,6 +46,7 @@ void rtgs_set_error(const char* fmt, ...);
 //      [k*4 + 2] = { rc.z, rh.x, rh.y, rh.z }
 //      [k*4 + 3] = { left, right (int bits), 0, 0 }   child >= 0: internal node id;
 //                                                      child <  0: leaf, sorted position = ~child
+// leafbox [s*2] = { c.xyz, h.x } { h.yz, 0, 0 }    leaf boxes by sorted position
 struct rtgs_scene {
     int device = 0;
     int64_t n = 0;
@@ -74,11 +75,17 @@ struct rtgs_scene {
     float4* shp = nullptr;
     float4* raw = nullptr;
     float4* nodes = nullptr;
+    float4* leafbox = nullptr;   // n*2: leaf box (centre, half extent) by sorted position
     int64_t num_nodes = 0;  // max(n-1, 1)
 
     // render scratch
-    unsigned int* tile_counter = nullptr;
-    unsigned long long* stats_dev = nullptr;  // 8 counters
+    unsigned int* counters = nullptr;         // 8: work counters, pool cursor, fallback count
+    unsigned long long* stats_dev = nullptr;  // 12 counters
+    void* tile_desc = nullptr;                // candidate lists (render_common.cuh), sized on first render
+    int* list_pool = nullptr;
+    int* fallback_tiles = nullptr;
+    int list_tiles = 0;
+    int pool_chunks = 0;
     float* stage_rgb = nullptr;               // device staging for rtgs_render_host
     float* stage_T = nullptr;
     size_t stage_pixels = 0;

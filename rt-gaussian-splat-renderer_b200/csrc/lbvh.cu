@@ -336,6 +336,16 @@ __global__ void k_pack_nodes(int64_t n, const int32_t* __restrict__ child, const
     nodes[i * 4 + 3] = make_float4(__int_as_float(le), __int_as_float(re), 0.0f, 0.0f);
 }
 
+// leaf boxes as (centre, half extent) by sorted position, for the per-tile filter of group candidates
+__global__ void k_pack_leafboxes(int64_t n, const float* __restrict__ aabb, float4* __restrict__ leafbox) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (s >= n) return;
+    float c[3], h[3];
+    box_ch(aabb + (int64_t)((n - 1) + s) * 6, c, h);
+    leafbox[s * 2 + 0] = make_float4(c[0], c[1], c[2], h[0]);
+    leafbox[s * 2 + 1] = make_float4(h[1], h[2], 0.0f, 0.0f);
+}
+
 __global__ void k_init_bounds(unsigned int* b) {
     if (threadIdx.x < 3) b[threadIdx.x] = 0xFFFFFFFFu;
     else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
@@ -398,6 +408,7 @@ int rtgs_lbvh_build(rtgs_scene* s) {
         k_refit<<<nb, TB, 0, st>>>(n, s->child, s->parent, s->aabb, visit.p);
     }
     k_pack_nodes<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->child, s->aabb, s->nodes);
+    k_pack_leafboxes<<<nb, TB, 0, st>>>(n, s->aabb, s->leafbox);
     CUDA_TRY(cudaGetLastError());
     unsigned int hb[6];
     CUDA_TRY(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, st));

@@ -27,50 +27,27 @@
 // centre ray), which keeps all magnitudes O(tile size / sigma); a hit/miss decision within a
 // small band of the sqrt(3)-sigma surface, an entry distance within a band of 0, and adjacent
 // k-buffer entries closer than a few ulp are re-evaluated in float64 from the raw parameters.
-#include "common.cuh"
-#include "gsmath.cuh"
+#include <stdlib.h>
+
+#include "render_common.cuh"
+
+using namespace rtgs_dev;
 
 namespace {
 
-constexpr int TILE_I = 4, TILE_J = 8;    // pixels per warp tile; lane = li * TILE_J + lj
-constexpr int MACRO_I = 8, MACRO_J = 4;  // tiles per 32x32-pixel macro tile (scheduling locality)
-constexpr int WARPS_PER_CTA = 8;
 #ifndef RTGS_STACK_CAP
 #define RTGS_STACK_CAP 512
 #endif
-#ifndef RTGS_BATCH
-#define RTGS_BATCH 32
-#endif
 constexpr int STACK_CAP = RTGS_STACK_CAP;
-constexpr int STACK_SINGLE = STACK_CAP - 100;   // growth/step <= 32, then DFS depth <= 62  // above this, pop one node at a time (DFS bound)
+constexpr int STACK_SINGLE = STACK_CAP - 100;   // above this pop one node at a time: growth/step <= 32, then DFS depth <= 62
 constexpr int CQ_CAP = 96;
-constexpr int BATCH = RTGS_BATCH;
+constexpr int BATCH = 32;
 constexpr int REC_Q = 5;                 // quads per staged record (80-byte stride: conflict-free gathers)
-constexpr unsigned FULL = 0xffffffffu;
-
-struct RenderParams {
-    const float4* nodes;
-    const float4* geo;
-    const float4* shp;
-    const float4* raw;
-    CamD cam;
-    int x0, y0, w, h;
-    int macro_cols;  // macro tiles along j
-    int ntiles;
-    int depth;
-    float t_cut;
-    int accumulate, full_pitch, has_sh;
-    float* out_rgb;
-    float* out_T;
-    unsigned int* tile_counter;
-    unsigned long long* stats;
-};
 
 struct __align__(16) TraversalScratch {
-    // precise record: {W00 W01 W02 W10} {W11 W12 W20 W21} {W22 e0.xyz} {g0.xyz t_c} {opacity, s, band, -}
-    float4 rec[BATCH][REC_Q];
-    // coarse test: S(a,b) = c0 + a (c1 + a c3 + b c4) + b (c2 + b c5) < 0  <=>  possibly q < 3 + band
-    float4 poly[BATCH][2];
+    float4 rec[BATCH][REC_Q];   // precise records (render_common.cuh: stage_candidate)
+    float4 polyA[BATCH];        // coarse quadratics {c0 c1 c2 c3}
+    float2 polyB[BATCH];        //                   {c4 c5}
     int stack[STACK_CAP];
     int cq[CQ_CAP];
 };
@@ -89,88 +66,8 @@ struct __align__(16) WarpShared {
     float kb_a[K][32];
 };
 
-enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS, ST_COUNT = 12 };
-
-// ---- float64 exact evaluation from raw parameters (rare path) ---------------------------------
-__device__ __noinline__ ExactHit exact_eval(const float4* __restrict__ raw, const CamD& cam, int s,
-                                            int pi, int pj) {
-    float4 a = __ldg(raw + (int64_t)s * 3 + 0), b = __ldg(raw + (int64_t)s * 3 + 1),
-           c = __ldg(raw + (int64_t)s * 3 + 2);
-    double p[3] = {a.x, a.y, a.z};
-    double q[4] = {a.w, b.x, b.y, b.z};
-    double sc[3] = {b.w, c.x, c.y};
-    d3 d = cam_dir(cam, (double)pi + 0.5, (double)pj + 0.5);
-    return exact_intersect(p, q, sc, cam.o, d);
-}
-
-// Exact ordering of two hits of one ray whose float32 entry distances are within rounding of each
-// other: float64 t1 from the raw parameters, ties broken by sorted position (rare path).
-__device__ __noinline__ bool exact_less(const float4* __restrict__ raw, const CamD& cam, int sa, int sb, int pi,
-                                        int pj) {
-    const ExactHit a = exact_eval(raw, cam, sa, pi, pj);
-    const ExactHit b = exact_eval(raw, cam, sb, pi, pj);
-    return a.t1 < b.t1 || (a.t1 == b.t1 && sa < sb);
-}
-
-// ---- SH basis, gaussian.py:149-163 (incl. the `5z^2 - 3z` term at :160 exactly as coded) ------
-__device__ __forceinline__ void sh_basis(float x, float y, float z, float (&Y)[15]) {
-    const float c0 = 0.9772050238058398f;   // sqrt(3/pi)
-    const float c1 = 2.1850968611841584f;   // sqrt(15/pi)
-    const float c2 = 1.2615662610100802f;   // sqrt(5/pi)
-    const float c3 = 2.360174359706574f;   // sqrt(35/(2pi))
-    const float c4 = 5.781222885281108f;   // sqrt(105/pi)
-    const float c5 = 1.828183197857863f;   // sqrt(21/(2pi))
-    const float c6 = 1.4927053303604616f;   // sqrt(7/pi)
-    const float xx = x * x, yy = y * y, zz = z * z;
-    Y[0] = 0.5f * c0 * y;
-    Y[1] = 0.5f * c0 * z;
-    Y[2] = 0.5f * c0 * x;
-    Y[3] = 0.5f * c1 * x * y;
-    Y[4] = 0.5f * c1 * y * z;
-    Y[5] = 0.25f * c2 * (3.0f * zz - 1.0f);
-    Y[6] = 0.5f * c1 * x * z;
-    Y[7] = 0.25f * c1 * (xx - yy);
-    Y[8] = 0.25f * c3 * y * (3.0f * xx - yy);
-    Y[9] = 0.5f * c4 * x * y * z;
-    Y[10] = 0.25f * c5 * y * (5.0f * zz - 1.0f);
-    Y[11] = 0.25f * c6 * (5.0f * zz - 3.0f * z);
-    Y[12] = 0.25f * c5 * x * (5.0f * zz - 1.0f);
-    Y[13] = 0.25f * c4 * (xx - yy) * z;
-    Y[14] = 0.25f * c3 * x * (xx - 3.0f * yy);
-}
-
-struct Frustum {
-    // 4 planes through the camera origin o, inward normals n[k]; a box (centre c, half size h) is
-    // outside plane k iff n.c + |n|.h - n.o < 0.
-    float nx[4], ny[4], nz[4];
-    float ax[4], ay[4], az[4];
-    float d[4];   // n.o
-};
-
-__device__ __forceinline__ bool box_in_frustum(const Frustum& f, float cx, float cy, float cz, float hx,
-                                               float hy, float hz) {
-    bool in = true;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        float v = f.nx[k] * cx + f.ny[k] * cy + f.nz[k] * cz + f.ax[k] * hx + f.ay[k] * hy + f.az[k] * hz;
-        in = in && (v >= f.d[k]);  // NaN / -inf (empty box) -> false
-    }
-    return in;
-}
-
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
-    float r;
-    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-
 // STATS = true compiles the per-render counters in (rtgs_render with a stats pointer); the timed path
-// uses STATS = false so that the ten 64-bit counters do not occupy registers.
+// uses STATS = false so that the 64-bit counters do not occupy registers.
 template <int K, bool STATS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_render(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -179,7 +76,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     const int lane = threadIdx.x & 31;
     const unsigned lt_mask = (1u << lane) - 1u;
     const CamD& cam = P.cam;
-    const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+    // work items: every tile id, or (fallback mode) the tiles k_tile_lists could not store a list for
+    const int nwork = P.use_fallback_list ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : P.ntiles;
 
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
@@ -188,64 +87,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
 #pragma unroll 1
     for (;;) {
         int tile = 0;
-        if (lane == 0) tile = (int)atomicAdd(P.tile_counter, 1u);
+        if (lane == 0) {
+            tile = (int)atomicAdd(P.counters + CTR_WORK3, 1u);
+            if (P.use_fallback_list && tile < nwork) tile = P.fallback_tiles[tile];
+            else if (P.use_fallback_list) tile = P.ntiles;
+        }
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
-        const int macro = tile / (MACRO_I * MACRO_J), local = tile % (MACRO_I * MACRO_J);
-        const int mi = macro / P.macro_cols, mj = macro % P.macro_cols;
-        const int ti = mi * MACRO_I + local / MACRO_J, tj = mj * MACRO_J + local % MACRO_J;
-        const int i0 = P.x0 + ti * TILE_I, j0 = P.y0 + tj * TILE_J;
-        if (i0 >= P.x0 + P.w || j0 >= P.y0 + P.h) continue;
+        int i0, j0;
+        tile_origin(P, tile, i0, j0);
+        if (i0 >= xe || j0 >= ye) continue;
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
-        const bool active = pi < P.x0 + P.w && pj < P.y0 + P.h;
+        const bool active = pi < xe && pj < ye;
 
-        // ---- rays (float64 setup, camera.py:46-52) ---------------------------------------------
-        // Image-plane coordinates: px = (i + 0.5 - W/2)/fx.  Tile centre (px0, py0); own offset
-        // (a, b) = (px - px0, py - py0).  UNNORMALISED directions are linear in (a, b):
-        //   D(a,b) = R (px0 + a, py0 + b, -1) = D0 + a Rx + b Ry,
-        // the reference's direction is d = D / sqrt(px^2 + py^2 + 1); d0 likewise, d = d0 + delta.
-        const double px0 = ((double)i0 + 0.5 * TILE_I - 0.5 * cam.W) * cam.ifx;
-        const double py0 = ((double)j0 + 0.5 * TILE_J - 0.5 * cam.H) * cam.ify;
-        const d3 D0 = cam_rot(cam, px0, py0, -1.0);
-        const double n0 = rsqrt(px0 * px0 + py0 * py0 + 1.0);
-        const d3 d0 = d3make(D0.x * n0, D0.y * n0, D0.z * n0);
-        const double inv_d0d0 = 1.0 / d3dot(d0, d0);
-        const double ad = active ? ((double)(pi - i0) + 0.5 - 0.5 * TILE_I) * cam.ifx : 0.0;
-        const double bd = active ? ((double)(pj - j0) + 0.5 - 0.5 * TILE_J) * cam.ify : 0.0;
-        float dlx, dly, dlz;          // delta = d - d0
-        float dnx, dny, dnz;          // normalize(d) for the SH basis (gaussian.py:200)
-        {
-            const double px = px0 + ad, py = py0 + bd;
-            const double nn = rsqrt(px * px + py * py + 1.0);
-            const d3 dw = d3make((D0.x + ad * cam.R[0] + bd * cam.R[1]) * nn, (D0.y + ad * cam.R[3] + bd * cam.R[4]) * nn,
-                                 (D0.z + ad * cam.R[6] + bd * cam.R[7]) * nn);
-            dlx = (float)(dw.x - d0.x); dly = (float)(dw.y - d0.y); dlz = (float)(dw.z - d0.z);
-            const double il = rsqrt(d3dot(dw, dw));
-            dnx = (float)(dw.x * il); dny = (float)(dw.y * il); dnz = (float)(dw.z * il);
-        }
-        const float pa = (float)ad, pb = (float)bd;
-        const float a_max = (float)(0.5 * TILE_I * fabs(cam.ifx)), b_max = (float)(0.5 * TILE_J * fabs(cam.ify));
-        float dl_max = sqrtf(dlx * dlx + dly * dly + dlz * dlz);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) dl_max = fmaxf(dl_max, __shfl_xor_sync(FULL, dl_max, o));
-
-        // ---- tile frustum: planes through the origin along the tile's pixel EDGES -------------
+        TileRays ry;
+        make_tile_rays(cam, i0, j0, pi, pj, active, ry);
         Frustum fr;
-        {
-            const double pxl = ((double)i0 - 0.5 * cam.W) * cam.ifx, pxh = ((double)(i0 + TILE_I) - 0.5 * cam.W) * cam.ifx;
-            const double pyl = ((double)j0 - 0.5 * cam.H) * cam.ify, pyh = ((double)(j0 + TILE_J) - 0.5 * cam.H) * cam.ify;
-            d3 n[4];
-            n[0] = cam_rot(cam, 1.0, 0.0, pxl);     // px >= pxl
-            n[1] = cam_rot(cam, -1.0, 0.0, -pxh);   // px <= pxh
-            n[2] = cam_rot(cam, 0.0, 1.0, pyl);     // py >= pyl
-            n[3] = cam_rot(cam, 0.0, -1.0, -pyh);   // py <= pyh
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                fr.nx[k] = (float)n[k].x; fr.ny[k] = (float)n[k].y; fr.nz[k] = (float)n[k].z;
-                fr.ax[k] = fabsf(fr.nx[k]); fr.ay[k] = fabsf(fr.ny[k]); fr.az[k] = fabsf(fr.nz[k]);
-                fr.d[k] = fr.nx[k] * ox + fr.ny[k] * oy + fr.nz[k] * oz;
-            }
-        }
+        make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
 
         // ---- per-lane hit buffer (shared memory, unsorted; replace-max once K entries are held) --
         int cnt = 0;
@@ -302,49 +160,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 const int m = min(BATCH, ncq);
                 ncq -= m;
                 if (lane < m) {
-                    const int s = tr.cq[ncq + lane];
-                    const float4 g0 = __ldg(P.geo + (int64_t)s * 4 + 0), g1 = __ldg(P.geo + (int64_t)s * 4 + 1),
-                                 g2 = __ldg(P.geo + (int64_t)s * 4 + 2), g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
-                    const double W00 = g1.x, W01 = g1.y, W02 = g1.z, W10 = g1.w, W11 = g2.x, W12 = g2.y,
-                                 W20 = g2.z, W21 = g2.w, W22 = g3.x;
-                    auto Wmul = [&](const d3& v) {
-                        return d3make(W00 * v.x + W01 * v.y + W02 * v.z, W10 * v.x + W11 * v.y + W12 * v.z,
-                                      W20 * v.x + W21 * v.y + W22 * v.z);
-                    };
-                    const d3 v = d3make((double)g0.x - cam.o[0], (double)g0.y - cam.o[1], (double)g0.z - cam.o[2]);
-                    // precise record: origin shifted to the closest point of the tile-centre ray
-                    const double tc = d3dot(v, d0) * inv_d0d0;
-                    const d3 e0 = Wmul(d3make(tc * d0.x - v.x, tc * d0.y - v.y, tc * d0.z - v.z));
-                    const d3 gd = Wmul(d0);
-                    const float wn = sqrtf(g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w + g2.x * g2.x +
-                                           g2.y * g2.y + g2.z * g2.z + g2.w * g2.w + g3.x * g3.x);
-                    const float eb = (float)sqrt(d3dot(e0, e0)) + fabsf((float)tc) * dl_max * wn;
-                    const float band = 4e-6f * (3.0f + eb * eb);
-                    tr.rec[lane][0] = g1;
-                    tr.rec[lane][1] = g2;
-                    tr.rec[lane][2] = make_float4(g3.x, (float)e0.x, (float)e0.y, (float)e0.z);
-                    tr.rec[lane][3] = make_float4((float)gd.x, (float)gd.y, (float)gd.z, (float)tc);
-                    tr.rec[lane][4] = make_float4(g0.w, __int_as_float(s), band, 0.0f);
-                    // coarse quadratic: with o' = W (o - p) = -W v and G(a,b) = W D(a,b) = G0 + a Gx + b Gy,
-                    //   q(a,b) = |o' x G|^2 / |G|^2 = N/Dn,  m = o' x G = M0 + a Mx + b My.
-                    // S = N - (3 + band) Dn - margin, margin bounding the float32 evaluation error.
-                    const d3 op = Wmul(d3make(-v.x, -v.y, -v.z));
-                    const d3 G0 = Wmul(D0);
-                    const d3 Gx = Wmul(d3make(cam.R[0], cam.R[3], cam.R[6]));
-                    const d3 Gy = Wmul(d3make(cam.R[1], cam.R[4], cam.R[7]));
-                    const d3 M0 = d3cross(op, G0), Mx = d3cross(op, Gx), My = d3cross(op, Gy);
-                    const double lim = 3.0 + (double)band;
-                    const double m00 = d3dot(M0, M0), m0x = d3dot(M0, Mx), m0y = d3dot(M0, My), mxx = d3dot(Mx, Mx),
-                                 mxy = d3dot(Mx, My), myy = d3dot(My, My);
-                    const double g00 = lim * d3dot(G0, G0), g0x = lim * d3dot(G0, Gx), g0y = lim * d3dot(G0, Gy),
-                                 gxx = lim * d3dot(Gx, Gx), gxy = lim * d3dot(Gx, Gy), gyy = lim * d3dot(Gy, Gy);
-                    const double am = a_max, bm = b_max;
-                    // magnitude of the terms BEFORE cancellation (N and Dn parts separately)
-                    const double E = m00 + g00 + 2.0 * am * (fabs(m0x) + fabs(g0x)) + 2.0 * bm * (fabs(m0y) + fabs(g0y)) +
-                                     am * am * (mxx + gxx) + 2.0 * am * bm * (fabs(mxy) + fabs(gxy)) + bm * bm * (myy + gyy);
-                    tr.poly[lane][0] = make_float4((float)(m00 - g00 - 2e-6 * E), (float)(2.0 * (m0x - g0x)),
-                                                   (float)(2.0 * (m0y - g0y)), (float)(mxx - gxx));
-                    tr.poly[lane][1] = make_float4((float)(2.0 * (mxy - gxy)), (float)(myy - gyy), 0.0f, 0.0f);
+                    float4 rec[5];
+                    float poly[6];
+                    stage_candidate(P, ry, tr.cq[ncq + lane], rec, poly);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) tr.rec[lane][k] = rec[k];
+                    tr.polyA[lane] = make_float4(poly[0], poly[1], poly[2], poly[3]);
+                    tr.polyB[lane] = make_float2(poly[4], poly[5]);
                 }
                 __syncwarp();
                 ST(st_cands += (unsigned)m);
@@ -353,52 +175,27 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 for (int c = 0; c <= m; ++c) {
                     bool cand = false;
                     if (c < m) {
-                        const float4 p0 = tr.poly[c][0];
-                        const float2 p1 = *reinterpret_cast<const float2*>(&tr.poly[c][1]);
-                        const float ta = fmaf(pa, p0.w, fmaf(pb, p1.x, p0.y));   // c1 + a c3 + b c4
-                        const float tb = fmaf(pb, p1.y, p0.z);                   // c2 + b c5
-                        const float S = fmaf(pa, ta, fmaf(pb, tb, p0.x));
+                        const float4 pA = tr.polyA[c];
+                        const float2 pB = tr.polyB[c];
+                        const float ta = fmaf(ry.pa, pA.w, fmaf(ry.pb, pB.x, pA.y));   // c1 + a c3 + b c4
+                        const float tb = fmaf(ry.pb, pB.y, pA.z);                      // c2 + b c5
+                        const float S = fmaf(ry.pa, ta, fmaf(ry.pb, tb, pA.x));
                         cand = active && (S < 0.0f);
                     }
                     // flush when a lane gets a second candidate, and once at the end of the batch
                     // (the staged records are about to be overwritten)
                     if (__any_sync(FULL, pend && (cand || c == m))) {
                         if (pend) {
-                            const float4* rc = tr.rec[pend_c];
-                            const float4 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3], ax = rc[4];
-                            const float wx = r0.x * dlx + r0.y * dly + r0.z * dlz;
-                            const float wy = r0.w * dlx + r1.x * dly + r1.y * dlz;
-                            const float wz = r1.z * dlx + r1.w * dly + r2.x * dlz;
-                            const float tc = r3.w;
-                            const float dx = r3.x + wx, dy = r3.y + wy, dz = r3.z + wz;        // d' = W d
-                            const float ex = r2.y + tc * wx, ey = r2.z + tc * wy, ez = r2.w + tc * wz;  // W (r(tc) - p)
-                            const float A = dx * dx + dy * dy + dz * dz;
-                            const float Bh = ex * dx + ey * dy + ez * dz;
-                            const float mx = ey * dz - ez * dy, my = ez * dx - ex * dz, mz = ex * dy - ey * dx;
-                            const float iA = rcp_approx(A);
-                            float q = (mx * mx + my * my + mz * mz) * iA;   // min Mahalanobis^2 along the ray
-                            // tau = -Bh/A - sqrt((3 - q)/A)  (near root relative to tc)
-                            const float tau = -Bh * iA - sqrt_approx(fmaxf(3.0f - q, 0.0f) * iA);
-                            float t1 = tc + tau;
-                            bool hit = (q < 3.0f) && (t1 > 0.0f);
-                            const bool near_q = fabsf(q - 3.0f) < ax.z;
-                            const bool near_t = (q < 3.0f + ax.z) && fabsf(t1) <= 2e-6f * (fabsf(tc) + fabsf(tau));
-                            if (near_q || near_t) {
-                                const ExactHit e = exact_eval(P.raw, cam, __float_as_int(ax.y), pi, pj);
-                                hit = e.hit && (e.t1 > 0.0);
-                                q = (float)e.q;
-                                t1 = (float)e.t1;
-                                ST(st_f64 += 1);
-                            }
-                            if (hit) {
-                                const float alpha = ax.x * __expf(-q);   // opacity * exp(-q)  (gaussian.py:197-198)
+                            const PreciseHit h = precise_test(P, tr.rec[pend_c], ry.dlx, ry.dly, ry.dlz, pi, pj);
+                            ST(st_f64 += h.refined);
+                            if (h.hit) {
                                 int slot = -1;
                                 if (cnt < K) slot = cnt++;
-                                else if (t1 < kmax_t) slot = kmax_slot;
+                                else if (h.t1 < kmax_t) slot = kmax_slot;
                                 if (slot >= 0) {
-                                    ws.kb_t[slot][lane] = t1;
-                                    ws.kb_i[slot][lane] = __float_as_int(ax.y);
-                                    ws.kb_a[slot][lane] = alpha;
+                                    ws.kb_t[slot][lane] = h.t1;
+                                    ws.kb_i[slot][lane] = h.s;
+                                    ws.kb_a[slot][lane] = h.alpha;
                                     if (cnt == K) {   // buffer full: track the farthest entry
                                         float mt = -INFINITY;
                                         int ms = 0;
@@ -476,7 +273,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         int nl = 0;
         {
             float Y[15];
-            sh_basis(dnx, dny, dnz, Y);
+            sh_basis(ry.dnx, ry.dny, ry.dnz, Y);
             const int nmine = min(cnt, P.depth);
             const int nloop = min(maxcnt, P.depth);
 #pragma unroll 1
@@ -484,23 +281,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 if (k < nmine && T >= P.t_cut) {
                     const int s = ws.c.so_i[k][lane];
                     const float alpha = ws.c.so_a[k][lane];
-                    const float4 g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
-                    float r = g3.y, g = g3.z, b = g3.w;
-                    if (P.has_sh) {
-                        const float4* sp = P.shp + (int64_t)s * 12;
-                        float v[48];
-#pragma unroll
-                        for (int f = 0; f < 12; ++f) {
-                            const float4 x = __ldg(sp + f);
-                            v[4 * f] = x.x; v[4 * f + 1] = x.y; v[4 * f + 2] = x.z; v[4 * f + 3] = x.w;
-                        }
-#pragma unroll
-                        for (int j = 0; j < 15; ++j) {
-                            r = fmaf(Y[j], v[3 * j + 0], r);
-                            g = fmaf(Y[j], v[3 * j + 1], g);
-                            b = fmaf(Y[j], v[3 * j + 2], b);
-                        }
-                    }
+                    float r, g, b;
+                    eval_colour(P, s, Y, r, g, b);
                     const float wgt = T * alpha;
                     cr = fmaf(wgt, r, cr);
                     cg = fmaf(wgt, g, cg);
@@ -510,34 +292,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 }
             }
         }
-        // ---- framebuffer write: stage the tile in shared memory so that every store instruction
-        // covers whole 32-byte sectors (each tile column is 8 pixels = 96 contiguous bytes) --------
-        {
-            float* ob = reinterpret_cast<float*>(&ws.kb_t[0][0]);
-            __syncwarp();
-            ob[lane * 3 + 0] = cr;
-            ob[lane * 3 + 1] = cg;
-            ob[lane * 3 + 2] = cb;
-            __syncwarp();
-            const int pitch = P.full_pitch ? cam.H : P.h;
-            const int bi = P.full_pitch ? 0 : P.x0, bj = P.full_pitch ? 0 : P.y0;
-#pragma unroll
-            for (int r = 0; r < 3; ++r) {
-                const int f = r * 32 + lane;
-                const int row = f / (3 * TILE_J), col = f % (3 * TILE_J);
-                const int qi = i0 + row, qj = j0 + col / 3;
-                if (qi < P.x0 + P.w && qj < P.y0 + P.h) {
-                    float* o = P.out_rgb + ((int64_t)(qi - bi) * pitch + (j0 - bj)) * 3 + col;
-                    if (P.accumulate) *o += ob[f];
-                    else *o = ob[f];
-                }
-            }
-            __syncwarp();
-        }
+        store_tile(P, reinterpret_cast<float*>(&ws.kb_t[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
         if (active) {
-            const int64_t idx = P.full_pitch ? ((int64_t)pi * cam.H + pj)
-                                             : ((int64_t)(pi - P.x0) * P.h + (pj - P.y0));
-            if (P.out_T) P.out_T[idx] = T;
             ST(st_rays += 1);
             ST(st_hit += nl > 0);
             ST(st_layers += (unsigned)nl);
@@ -546,17 +302,20 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     }
 
     if (STATS && P.stats) {
-        unsigned long long v[10] = {st_rays, st_hit, st_layers, 0, 0, 0, st_f64, st_tiles, 0, 0};
+        unsigned long long v[ST_COUNT] = {0};
+        v[ST_RAYS] = st_rays; v[ST_RAYS_HIT] = st_hit; v[ST_LAYERS] = st_layers; v[ST_F64] = st_f64;
         // warp-uniform counters are taken from lane 0 only
         if (lane == 0) {
             v[ST_NODES] = st_nodes;
             v[ST_CANDS] = st_cands;
             v[ST_PAIRS] = st_pairs;
+            v[ST_TILES] = st_tiles;
             v[ST_STEPS] = st_steps;
             v[ST_INSERTS] = st_ins;
+            v[ST_FALLBACK] = P.use_fallback_list ? st_tiles : 0;
         }
 #pragma unroll
-        for (int k = 0; k < 10; ++k) {
+        for (int k = 0; k < ST_COUNT; ++k) {
             unsigned long long x = v[k];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
@@ -564,7 +323,6 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         }
     }
 }
-
 #undef ST
 
 // ---- Camera.generate_ray_field (camera.py:57-71): (W,H,8) = origin, direction, start, end -----
@@ -728,6 +486,36 @@ int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     return RTGS_OK;
 }
 
+// Which kernels render a frame: 0 = k_tile_lists + k_shade_tiles (+ k_render on the fallback list),
+// 1 = the fused k_render alone.  depth > 16 always takes the fused kernel (its k-buffer has 32 entries).
+int render_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("RTGS_RENDER_MODE");
+        mode = e ? atoi(e) : 0;
+    }
+    return mode;
+}
+
+// Candidate-list scratch of a scene, sized for the tile count of the largest region rendered so far.
+// The pool holds 16 chunks (496 candidates) per tile on average; tiles may take any share of it.
+int ensure_lists(rtgs_scene* s, int ntiles) {
+    if (s->list_tiles >= ntiles) return RTGS_OK;
+    cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
+    s->tile_desc = nullptr; s->list_pool = nullptr; s->fallback_tiles = nullptr;
+    s->list_tiles = 0;
+    int64_t chunks = (int64_t)ntiles * 16;
+    if (const char* e = getenv("RTGS_POOL_CHUNKS")) chunks = atoll(e);   // tests: force the fallback path
+    if (chunks < 0) chunks = 0;
+    if (chunks > (1ll << 26)) chunks = 1ll << 26;
+    CUDA_TRY(cudaMalloc((void**)&s->tile_desc, (size_t)ntiles * sizeof(TileDesc)));
+    CUDA_TRY(cudaMalloc((void**)&s->list_pool, (size_t)(chunks > 0 ? chunks : 1) * CHUNK_INTS * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&s->fallback_tiles, (size_t)ntiles * sizeof(int)));
+    s->list_tiles = ntiles;
+    s->pool_chunks = (int)chunks;
+    return RTGS_OK;
+}
+
 }  // namespace
 
 int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
@@ -738,12 +526,13 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.geo = s->geo;
     P.shp = s->shp;
     P.raw = s->raw;
+    P.leafbox = s->leafbox;
     P.cam = make_camd(cam);
     P.x0 = x0; P.y0 = y0; P.w = w; P.h = h;
-    const int mrows = (w + TILE_I * MACRO_I - 1) / (TILE_I * MACRO_I);
-    const int mcols = (h + TILE_J * MACRO_J - 1) / (TILE_J * MACRO_J);
+    const int mrows = (w + MACRO_PX_I - 1) / MACRO_PX_I;
+    const int mcols = (h + MACRO_PX_J - 1) / MACRO_PX_J;
     P.macro_cols = mcols;
-    P.ntiles = mrows * mcols * MACRO_I * MACRO_J;
+    P.ntiles = mrows * mcols * TILES_PER_MACRO;
     P.depth = depth;
     P.t_cut = t_cut;
     P.accumulate = accumulate;
@@ -751,12 +540,35 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.has_sh = s->has_sh ? 1 : 0;
     P.out_rgb = out_rgb;
     P.out_T = out_T;
-    P.tile_counter = s->tile_counter;
+    P.counters = s->counters;
     P.stats = want_stats ? s->stats_dev : nullptr;
-    CUDA_TRY(cudaMemsetAsync(s->tile_counter, 0, sizeof(unsigned int), stream));
-    if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, 12 * sizeof(unsigned long long), stream));
-    if (depth <= 16) return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
-    return want_stats ? launch_render_k<32, true>(s, P, stream) : launch_render_k<32, false>(s, P, stream);
+    P.desc = nullptr;
+    P.pool = nullptr;
+    P.pool_chunks = 0;
+    P.fallback_tiles = nullptr;
+    P.use_fallback_list = 0;
+    CUDA_TRY(cudaMemsetAsync(s->counters, 0, CTR_COUNT * sizeof(unsigned int), stream));
+    if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), stream));
+    if (depth > 16)
+        return want_stats ? launch_render_k<32, true>(s, P, stream) : launch_render_k<32, false>(s, P, stream);
+    if (render_mode() == 1)
+        return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
+    // traversal -> per-tile candidate lists -> shading; tiles whose list did not fit the pool are
+    // rendered by the fused kernel afterwards (it returns at once when there are none)
+    {
+        const int r = ensure_lists(s, P.ntiles);
+        if (r != RTGS_OK) return r;
+    }
+    P.desc = reinterpret_cast<TileDesc*>(s->tile_desc);
+    P.pool = s->list_pool;
+    P.pool_chunks = s->pool_chunks;
+    P.fallback_tiles = s->fallback_tiles;
+    int r = rtgs_launch_tile_lists(s, P, stream, want_stats);
+    if (r != RTGS_OK) return r;
+    r = rtgs_launch_shade_tiles(s, P, stream, want_stats);
+    if (r != RTGS_OK) return r;
+    P.use_fallback_list = 1;
+    return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
 }
 
 int rtgs_launch_generate_rays(const rtgs_camera* cam, float* rays, cudaStream_t stream) {

@@ -1,0 +1,374 @@
+// render_common.cuh — declarations shared by the render kernels (sm_100a):
+//   tile_lists.cu  k_tile_lists   LBVH traversal, one candidate list per 4x8-pixel tile   (scene.py:406-450)
+//   shade.cu       k_shade_tiles  intersection + k-buffer + SH compositing per tile       (gaussian.py:140-230,
+//                                                                                          ray_tracer.py:79-104)
+//   render.cu      k_render       the same path fused in one kernel (depth > 16, and tiles whose list did
+//                                 not fit the list pool)
+#pragma once
+#include "common.cuh"
+#include "gsmath.cuh"
+
+namespace rtgs_dev {
+
+constexpr int TILE_I = 4, TILE_J = 8;      // pixels per warp tile; lane = li * TILE_J + lj
+constexpr int GROUP_TI = 2, GROUP_TJ = 2;  // tiles per traversal group: 8 x 16 pixels
+constexpr int GPX_I = TILE_I * GROUP_TI, GPX_J = TILE_J * GROUP_TJ;
+constexpr int MACRO_GI = 4, MACRO_GJ = 2;  // groups per 32x32-pixel macro tile (scheduling locality)
+constexpr int TILES_PER_GROUP = GROUP_TI * GROUP_TJ;
+constexpr int GROUPS_PER_MACRO = MACRO_GI * MACRO_GJ;
+constexpr int TILES_PER_MACRO = TILES_PER_GROUP * GROUPS_PER_MACRO;
+constexpr int MACRO_PX_I = GPX_I * MACRO_GI, MACRO_PX_J = GPX_J * MACRO_GJ;
+constexpr int WARPS_PER_CTA = 8;
+constexpr unsigned FULL = 0xffffffffu;
+
+// Candidate lists (k_tile_lists -> k_shade_tiles): chunks of 32 ints in a global pool.  A chunk holds up
+// to 31 sorted positions in [0..30] and the index of the NEXT chunk of the same tile in [31] (-1 = end).
+// A tile's chunks are linked newest first: the head chunk holds the remainder ((count-1) % 31 + 1
+// entries), every other chunk is full.
+constexpr int CHUNK_IDS = 31;
+constexpr int CHUNK_INTS = 32;
+constexpr int SLAB_CHUNKS = 16;   // chunks a warp takes from the pool per atomic
+
+struct TileDesc {
+    int head;    // first chunk, -1 if the list is empty
+    int count;   // candidates; -1: the list did not fit the pool, the tile is in the fallback list
+};
+
+struct RenderParams {
+    const float4* nodes;
+    const float4* geo;
+    const float4* shp;
+    const float4* raw;
+    const float4* leafbox;
+    CamD cam;
+    int x0, y0, w, h;
+    int macro_cols;  // macro tiles along j
+    int ntiles;      // macro_rows * macro_cols * TILES_PER_MACRO (tile ids, some outside the region)
+    int depth;
+    float t_cut;
+    int accumulate, full_pitch, has_sh;
+    float* out_rgb;
+    float* out_T;
+    unsigned int* counters;   // CTR_*: work counters of the three kernels, pool chunks taken, fallback tiles
+    unsigned long long* stats;
+    // candidate lists
+    TileDesc* desc;           // ntiles
+    int* pool;                // pool_chunks * CHUNK_INTS
+    int pool_chunks;
+    int* fallback_tiles;      // ntiles
+    int use_fallback_list;    // k_render: take tile ids from fallback_tiles[0 .. counters[2])
+};
+
+enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_COUNT = 8 };
+enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
+       ST_FALLBACK, ST_COUNT = 12 };
+
+// tile id -> pixel origin.  id = (macro * GROUPS_PER_MACRO + group) * TILES_PER_GROUP + sub, so that the
+// four tiles of a traversal group are consecutive and consecutive groups share a 32x32-pixel macro tile.
+__device__ __forceinline__ void group_origin(const RenderParams& P, int group, int& gi0, int& gj0) {
+    const int macro = group / GROUPS_PER_MACRO, lg = group % GROUPS_PER_MACRO;
+    const int mi = macro / P.macro_cols, mj = macro % P.macro_cols;
+    gi0 = P.x0 + (mi * MACRO_GI + lg / MACRO_GJ) * GPX_I;
+    gj0 = P.y0 + (mj * MACRO_GJ + lg % MACRO_GJ) * GPX_J;
+}
+__device__ __forceinline__ void tile_origin(const RenderParams& P, int tile, int& i0, int& j0) {
+    int gi0, gj0;
+    group_origin(P, tile / TILES_PER_GROUP, gi0, gj0);
+    const int sub = tile % TILES_PER_GROUP;
+    i0 = gi0 + (sub / GROUP_TJ) * TILE_I;
+    j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
+}
+
+// ---- frustum of a pixel rectangle: 4 planes through the camera origin o, inward normals n[k]; a box
+// (centre c, half size h) is outside plane k iff n.c + |n|.h - n.o < 0 ---------------------------------
+struct Frustum {
+    float nx[4], ny[4], nz[4];
+    float ax[4], ay[4], az[4];   // |n|
+    float d[4];                  // n.o
+};
+
+__device__ __forceinline__ void make_frustum(const CamD& cam, int il, int ih, int jl, int jh, Frustum& fr) {
+    const double pxl = ((double)il - 0.5 * cam.W) * cam.ifx, pxh = ((double)ih - 0.5 * cam.W) * cam.ifx;
+    const double pyl = ((double)jl - 0.5 * cam.H) * cam.ify, pyh = ((double)jh - 0.5 * cam.H) * cam.ify;
+    d3 n[4];
+    n[0] = cam_rot(cam, 1.0, 0.0, pxl);     // px >= pxl
+    n[1] = cam_rot(cam, -1.0, 0.0, -pxh);   // px <= pxh
+    n[2] = cam_rot(cam, 0.0, 1.0, pyl);     // py >= pyl
+    n[3] = cam_rot(cam, 0.0, -1.0, -pyh);   // py <= pyh
+    const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        fr.nx[k] = (float)n[k].x; fr.ny[k] = (float)n[k].y; fr.nz[k] = (float)n[k].z;
+        fr.ax[k] = fabsf(fr.nx[k]); fr.ay[k] = fabsf(fr.ny[k]); fr.az[k] = fabsf(fr.nz[k]);
+        fr.d[k] = fr.nx[k] * ox + fr.ny[k] * oy + fr.nz[k] * oz;
+    }
+}
+
+__device__ __forceinline__ bool box_in_frustum(const Frustum& f, float cx, float cy, float cz, float hx,
+                                               float hy, float hz) {
+    bool in = true;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        float v = f.nx[k] * cx + f.ny[k] * cy + f.nz[k] * cz + f.ax[k] * hx + f.ay[k] * hy + f.az[k] * hz;
+        in = in && (v >= f.d[k]);  // NaN / -inf (empty box) -> false
+    }
+    return in;
+}
+
+// ---- float64 exact evaluation from raw parameters (rare path) ---------------------------------
+__device__ __noinline__ static ExactHit exact_eval(const float4* __restrict__ raw, const CamD& cam, int s, int pi,
+                                                   int pj) {
+    float4 a = __ldg(raw + (int64_t)s * 3 + 0), b = __ldg(raw + (int64_t)s * 3 + 1),
+           c = __ldg(raw + (int64_t)s * 3 + 2);
+    double p[3] = {a.x, a.y, a.z};
+    double q[4] = {a.w, b.x, b.y, b.z};
+    double sc[3] = {b.w, c.x, c.y};
+    d3 d = cam_dir(cam, (double)pi + 0.5, (double)pj + 0.5);
+    return exact_intersect(p, q, sc, cam.o, d);
+}
+
+// Exact ordering of two hits of one ray whose float32 entry distances are within rounding of each
+// other: float64 t1 from the raw parameters, ties broken by sorted position (rare path).
+__device__ __noinline__ static bool exact_less(const float4* __restrict__ raw, const CamD& cam, int sa, int sb,
+                                               int pi, int pj) {
+    const ExactHit a = exact_eval(raw, cam, sa, pi, pj);
+    const ExactHit b = exact_eval(raw, cam, sb, pi, pj);
+    return a.t1 < b.t1 || (a.t1 == b.t1 && sa < sb);
+}
+
+// ---- SH basis, gaussian.py:149-163 (incl. the `5z^2 - 3z` term at :160 exactly as coded) ------
+__device__ __forceinline__ void sh_basis(float x, float y, float z, float (&Y)[15]) {
+    const float c0 = 0.9772050238058398f;   // sqrt(3/pi)
+    const float c1 = 2.1850968611841584f;   // sqrt(15/pi)
+    const float c2 = 1.2615662610100802f;   // sqrt(5/pi)
+    const float c3 = 2.360174359706574f;    // sqrt(35/(2pi))
+    const float c4 = 5.781222885281108f;    // sqrt(105/pi)
+    const float c5 = 1.828183197857863f;    // sqrt(21/(2pi))
+    const float c6 = 1.4927053303604616f;   // sqrt(7/pi)
+    const float xx = x * x, yy = y * y, zz = z * z;
+    Y[0] = 0.5f * c0 * y;
+    Y[1] = 0.5f * c0 * z;
+    Y[2] = 0.5f * c0 * x;
+    Y[3] = 0.5f * c1 * x * y;
+    Y[4] = 0.5f * c1 * y * z;
+    Y[5] = 0.25f * c2 * (3.0f * zz - 1.0f);
+    Y[6] = 0.5f * c1 * x * z;
+    Y[7] = 0.25f * c1 * (xx - yy);
+    Y[8] = 0.25f * c3 * y * (3.0f * xx - yy);
+    Y[9] = 0.5f * c4 * x * y * z;
+    Y[10] = 0.25f * c5 * y * (5.0f * zz - 1.0f);
+    Y[11] = 0.25f * c6 * (5.0f * zz - 3.0f * z);
+    Y[12] = 0.25f * c5 * x * (5.0f * zz - 1.0f);
+    Y[13] = 0.25f * c4 * (xx - yy) * z;
+    Y[14] = 0.25f * c3 * x * (xx - 3.0f * yy);
+}
+
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Rays of one tile (float64 setup, camera.py:46-52).  Image-plane coordinates: px = (i + 0.5 - W/2)/fx.
+// Tile centre (px0, py0); own offset (a, b) = (px - px0, py - py0).  UNNORMALISED directions are linear
+// in (a, b):  D(a,b) = R (px0 + a, py0 + b, -1) = D0 + a Rx + b Ry;  the reference's direction is
+// d = D / sqrt(px^2 + py^2 + 1); d0 likewise for the tile centre, d = d0 + delta.
+struct TileRays {
+    d3 D0, d0;
+    double inv_d0d0;
+    float dlx, dly, dlz;   // delta = d - d0
+    float dnx, dny, dnz;   // normalize(d) for the SH basis (gaussian.py:200)
+    float pa, pb;          // (a, b)
+    float a_max, b_max, dl_max;
+};
+
+__device__ __forceinline__ void make_tile_rays(const CamD& cam, int i0, int j0, int pi, int pj, bool active,
+                                               TileRays& r) {
+    const double px0 = ((double)i0 + 0.5 * TILE_I - 0.5 * cam.W) * cam.ifx;
+    const double py0 = ((double)j0 + 0.5 * TILE_J - 0.5 * cam.H) * cam.ify;
+    r.D0 = cam_rot(cam, px0, py0, -1.0);
+    const double n0 = rsqrt(px0 * px0 + py0 * py0 + 1.0);
+    r.d0 = d3make(r.D0.x * n0, r.D0.y * n0, r.D0.z * n0);
+    r.inv_d0d0 = 1.0 / d3dot(r.d0, r.d0);
+    const double ad = active ? ((double)(pi - i0) + 0.5 - 0.5 * TILE_I) * cam.ifx : 0.0;
+    const double bd = active ? ((double)(pj - j0) + 0.5 - 0.5 * TILE_J) * cam.ify : 0.0;
+    {
+        const double px = px0 + ad, py = py0 + bd;
+        const double nn = rsqrt(px * px + py * py + 1.0);
+        const d3 dw = d3make((r.D0.x + ad * cam.R[0] + bd * cam.R[1]) * nn, (r.D0.y + ad * cam.R[3] + bd * cam.R[4]) * nn,
+                             (r.D0.z + ad * cam.R[6] + bd * cam.R[7]) * nn);
+        r.dlx = (float)(dw.x - r.d0.x); r.dly = (float)(dw.y - r.d0.y); r.dlz = (float)(dw.z - r.d0.z);
+        const double il = rsqrt(d3dot(dw, dw));
+        r.dnx = (float)(dw.x * il); r.dny = (float)(dw.y * il); r.dnz = (float)(dw.z * il);
+    }
+    r.pa = (float)ad;
+    r.pb = (float)bd;
+    r.a_max = (float)(0.5 * TILE_I * fabs(cam.ifx));
+    r.b_max = (float)(0.5 * TILE_J * fabs(cam.ify));
+    float m = sqrtf(r.dlx * r.dlx + r.dly * r.dly + r.dlz * r.dlz);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(FULL, m, o));
+    r.dl_max = m;
+}
+
+// Per-(tile, candidate) staging in float64 by one lane: the precise record (origin shifted to the
+// closest point of the tile-centre ray) and the coarse quadratic.
+//   rec: {W00 W01 W02 W10} {W11 W12 W20 W21} {W22 e0.xyz} {g0.xyz t_c} {opacity, s, band, -}
+//   poly: S(a,b) = c0 + a (c1 + a c3 + b c4) + b (c2 + b c5) < 0  <=>  possibly q < 3 + band
+// With o' = W (o - p) = -W v and G(a,b) = W D(a,b) = G0 + a Gx + b Gy:
+//   q(a,b) = |o' x G|^2 / |G|^2 = N/Dn,  m = o' x G = M0 + a Mx + b My,
+//   S = N - (3 + band) Dn - margin, margin bounding the float32 evaluation error.
+__device__ __forceinline__ void stage_candidate(const RenderParams& P, const TileRays& tr, int s, float4 (&rec)[5],
+                                                float (&poly)[6]) {
+    const CamD& cam = P.cam;
+    const float4 g0 = __ldg(P.geo + (int64_t)s * 4 + 0), g1 = __ldg(P.geo + (int64_t)s * 4 + 1),
+                 g2 = __ldg(P.geo + (int64_t)s * 4 + 2), g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
+    const double W00 = g1.x, W01 = g1.y, W02 = g1.z, W10 = g1.w, W11 = g2.x, W12 = g2.y, W20 = g2.z, W21 = g2.w,
+                 W22 = g3.x;
+    auto Wmul = [&](const d3& v) {
+        return d3make(W00 * v.x + W01 * v.y + W02 * v.z, W10 * v.x + W11 * v.y + W12 * v.z,
+                      W20 * v.x + W21 * v.y + W22 * v.z);
+    };
+    const d3 v = d3make((double)g0.x - cam.o[0], (double)g0.y - cam.o[1], (double)g0.z - cam.o[2]);
+    const double tc = d3dot(v, tr.d0) * tr.inv_d0d0;
+    const d3 e0 = Wmul(d3make(tc * tr.d0.x - v.x, tc * tr.d0.y - v.y, tc * tr.d0.z - v.z));
+    const d3 gd = Wmul(tr.d0);
+    const float wn = sqrtf(g1.x * g1.x + g1.y * g1.y + g1.z * g1.z + g1.w * g1.w + g2.x * g2.x + g2.y * g2.y +
+                           g2.z * g2.z + g2.w * g2.w + g3.x * g3.x);
+    const float eb = (float)sqrt(d3dot(e0, e0)) + fabsf((float)tc) * tr.dl_max * wn;
+    const float band = 4e-6f * (3.0f + eb * eb);
+    rec[0] = g1;
+    rec[1] = g2;
+    rec[2] = make_float4(g3.x, (float)e0.x, (float)e0.y, (float)e0.z);
+    rec[3] = make_float4((float)gd.x, (float)gd.y, (float)gd.z, (float)tc);
+    rec[4] = make_float4(g0.w, __int_as_float(s), band, 0.0f);
+    const d3 op = Wmul(d3make(-v.x, -v.y, -v.z));
+    const d3 G0 = Wmul(tr.D0);
+    const d3 Gx = Wmul(d3make(cam.R[0], cam.R[3], cam.R[6]));
+    const d3 Gy = Wmul(d3make(cam.R[1], cam.R[4], cam.R[7]));
+    const d3 M0 = d3cross(op, G0), Mx = d3cross(op, Gx), My = d3cross(op, Gy);
+    const double lim = 3.0 + (double)band;
+    const double m00 = d3dot(M0, M0), m0x = d3dot(M0, Mx), m0y = d3dot(M0, My), mxx = d3dot(Mx, Mx),
+                 mxy = d3dot(Mx, My), myy = d3dot(My, My);
+    const double g00 = lim * d3dot(G0, G0), g0x = lim * d3dot(G0, Gx), g0y = lim * d3dot(G0, Gy),
+                 gxx = lim * d3dot(Gx, Gx), gxy = lim * d3dot(Gx, Gy), gyy = lim * d3dot(Gy, Gy);
+    const double am = tr.a_max, bm = tr.b_max;
+    // magnitude of the terms BEFORE cancellation (N and Dn parts separately)
+    const double E = m00 + g00 + 2.0 * am * (fabs(m0x) + fabs(g0x)) + 2.0 * bm * (fabs(m0y) + fabs(g0y)) +
+                     am * am * (mxx + gxx) + 2.0 * am * bm * (fabs(mxy) + fabs(gxy)) + bm * bm * (myy + gyy);
+    poly[0] = (float)(m00 - g00 - 2e-6 * E);
+    poly[1] = (float)(2.0 * (m0x - g0x));
+    poly[2] = (float)(2.0 * (m0y - g0y));
+    poly[3] = (float)(mxx - gxx);
+    poly[4] = (float)(2.0 * (mxy - gxy));
+    poly[5] = (float)(myy - gyy);
+}
+
+__device__ __forceinline__ bool coarse_test(const float (&p)[6], float pa, float pb) {
+    const float ta = fmaf(pa, p[3], fmaf(pb, p[4], p[1]));   // c1 + a c3 + b c4
+    const float tb = fmaf(pb, p[5], p[2]);                   // c2 + b c5
+    return fmaf(pa, ta, fmaf(pb, tb, p[0])) < 0.0f;
+}
+
+// The precise per-ray test of one staged candidate (float32 relative to the tile-centre ray, decisions
+// within the band re-evaluated in float64): hit?, entry distance t1, alpha = opacity * exp(-q).
+struct PreciseHit {
+    bool hit;
+    float t1, alpha;
+    int s;
+    bool refined;
+};
+
+__device__ __forceinline__ PreciseHit precise_test(const RenderParams& P, const float4* rc, float dlx, float dly,
+                                                   float dlz, int pi, int pj) {
+    const float4 r0 = rc[0], r1 = rc[1], r2 = rc[2], r3 = rc[3], ax = rc[4];
+    const float wx = r0.x * dlx + r0.y * dly + r0.z * dlz;
+    const float wy = r0.w * dlx + r1.x * dly + r1.y * dlz;
+    const float wz = r1.z * dlx + r1.w * dly + r2.x * dlz;
+    const float tc = r3.w;
+    const float dx = r3.x + wx, dy = r3.y + wy, dz = r3.z + wz;                 // d' = W d
+    const float ex = r2.y + tc * wx, ey = r2.z + tc * wy, ez = r2.w + tc * wz;  // W (r(tc) - p)
+    const float A = dx * dx + dy * dy + dz * dz;
+    const float Bh = ex * dx + ey * dy + ez * dz;
+    const float mx = ey * dz - ez * dy, my = ez * dx - ex * dz, mz = ex * dy - ey * dx;
+    const float iA = rcp_approx(A);
+    float q = (mx * mx + my * my + mz * mz) * iA;   // min Mahalanobis^2 along the ray
+    // tau = -Bh/A - sqrt((3 - q)/A)  (near root relative to tc)
+    const float tau = -Bh * iA - sqrt_approx(fmaxf(3.0f - q, 0.0f) * iA);
+    PreciseHit h;
+    h.t1 = tc + tau;
+    h.s = __float_as_int(ax.y);
+    h.hit = (q < 3.0f) && (h.t1 > 0.0f);
+    h.refined = false;
+    const bool near_q = fabsf(q - 3.0f) < ax.z;
+    const bool near_t = (q < 3.0f + ax.z) && fabsf(h.t1) <= 2e-6f * (fabsf(tc) + fabsf(tau));
+    if (near_q || near_t) {
+        const ExactHit e = exact_eval(P.raw, P.cam, h.s, pi, pj);
+        h.hit = e.hit && (e.t1 > 0.0);
+        q = (float)e.q;
+        h.t1 = (float)e.t1;
+        h.refined = true;
+    }
+    h.alpha = ax.x * __expf(-q);   // opacity * exp(-q)  (gaussian.py:197-198)
+    return h;
+}
+
+// rgb = color + eval_sh(normalize(dir))  (gaussian.py:199-200) of the Gaussian at sorted position s
+__device__ __forceinline__ void eval_colour(const RenderParams& P, int s, const float (&Y)[15], float& r, float& g,
+                                            float& b) {
+    const float4 g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
+    r = g3.y; g = g3.z; b = g3.w;
+    if (P.has_sh) {
+        const float4* sp = P.shp + (int64_t)s * 12;
+        float v[48];
+#pragma unroll
+        for (int f = 0; f < 12; ++f) {
+            const float4 x = __ldg(sp + f);
+            v[4 * f] = x.x; v[4 * f + 1] = x.y; v[4 * f + 2] = x.z; v[4 * f + 3] = x.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 15; ++j) {
+            r = fmaf(Y[j], v[3 * j + 0], r);
+            g = fmaf(Y[j], v[3 * j + 1], g);
+            b = fmaf(Y[j], v[3 * j + 2], b);
+        }
+    }
+}
+
+// Framebuffer write of one tile: staged through `ob` (>= 96 floats of shared memory) so that every store
+// instruction covers whole 32-byte sectors (each tile column is 8 pixels = 96 contiguous bytes).
+__device__ __forceinline__ void store_tile(const RenderParams& P, float* ob, int lane, int i0, int j0, int pi, int pj,
+                                           bool active, float cr, float cg, float cb, float T) {
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+    __syncwarp();
+    ob[lane * 3 + 0] = cr;
+    ob[lane * 3 + 1] = cg;
+    ob[lane * 3 + 2] = cb;
+    __syncwarp();
+    const int pitch = P.full_pitch ? P.cam.H : P.h;
+    const int bi = P.full_pitch ? 0 : P.x0, bj = P.full_pitch ? 0 : P.y0;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const int f = r * 32 + lane;
+        const int row = f / (3 * TILE_J), col = f % (3 * TILE_J);
+        const int qi = i0 + row, qj = j0 + col / 3;
+        if (qi < xe && qj < ye) {
+            float* o = P.out_rgb + ((int64_t)(qi - bi) * pitch + (j0 - bj)) * 3 + col;
+            if (P.accumulate) *o += ob[f];
+            else *o = ob[f];
+        }
+    }
+    __syncwarp();
+    if (active && P.out_T) P.out_T[(int64_t)(pi - bi) * pitch + (pj - bj)] = T;
+}
+
+}  // namespace rtgs_dev
+
+// launchers of the two-kernel path (tile_lists.cu, shade.cu); P.counters/desc/pool must be set up
+int rtgs_launch_tile_lists(rtgs_scene* s, const rtgs_dev::RenderParams& P, cudaStream_t stream, bool want_stats);
+int rtgs_launch_shade_tiles(rtgs_scene* s, const rtgs_dev::RenderParams& P, cudaStream_t stream, bool want_stats);

@@ -1,0 +1,287 @@
+// shade.cu — k_shade_tiles: everything of the render path after the traversal, per 4x8-pixel tile:
+//   camera ray generation        camera.py:31-71              (registers; rays never stored)
+//   ray-Gaussian intersection    gaussian.py:203-230          (local-frame quadratic)
+//   response + SH colour         gaussian.py:140-201
+//   front-to-back compositing    ray_tracer.py:79-104         (k-buffer of the `depth` nearest entries)
+//
+// A warp owns one tile at a time (lane = pixel; persistent threads, tiles pulled from an atomic counter
+// in the order k_tile_lists produced them) and walks the tile's candidate list, 31 candidates (one
+// 128-byte chunk) per batch:
+//   stage    one lane per candidate, float64: origin shifted to the closest point of the tile's centre
+//            ray -> a 80-byte float32 record + a 6-coefficient quadratic in shared memory;
+//   coarse   every lane evaluates every staged quadratic (broadcast shared-memory reads, 5 FMA) and
+//            keeps a 32-bit mask of the candidates its ray may hit;
+//   precise  warp-wide rounds, each lane takes the next set bit of its mask: exact decision (float32
+//            in the tile-centred frame, float64 from the raw parameters inside the error band), entry
+//            distance, alpha; the hit goes to the lane's K-entry buffer in shared memory (replace-max
+//            once K are held).
+// After the list: rank sort of the lane's entries (keys in registers, near ties ordered by their float64
+// entry distances), compositing in that order with the SH basis evaluated once per ray, and a
+// sector-aligned framebuffer store.
+//
+// Numerics: identical to the fused kernel (render.cu) - parity is defined against the float64
+// evaluation of the reference's maths, see DESIGN.md §2.
+//
+// Occupancy is the point of this kernel's layout: 9.25 KB of shared memory per warp and <= 80 registers
+// give 24 warps per SM (the fused kernel: 12 KB, 128 registers, 16 warps), which is what hides the
+// scattered Gaussian-record and SH fetches.
+#include "render_common.cuh"
+
+using namespace rtgs_dev;
+
+namespace {
+
+constexpr int K = 16;          // k-buffer entries (depth <= 16)
+constexpr int BATCH = 32;      // staged candidates per batch (a chunk fills 31)
+constexpr int REC_Q = 5;       // quads per staged record (80-byte stride: conflict-free gathers)
+
+struct __align__(16) WarpShared {
+    float4 rec[BATCH][REC_Q];  // precise records
+    float4 polyA[BATCH];       // coarse quadratics {c0 c1 c2 c3}
+    float2 polyB[BATCH];       //                   {c4 c5}
+    float kb_t[K][32];         // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
+    int kb_i[K][32];
+    float kb_a[K][32];
+};
+static_assert(sizeof(WarpShared) == 9472, "shared-memory budget of 24 warps per SM");
+
+template <bool STATS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const CamD& cam = P.cam;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+
+    unsigned long long st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
+#define ST(expr) do { if (STATS) { expr; } } while (0)
+
+#pragma unroll 1
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(P.counters + CTR_WORK2, 1u);
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= P.ntiles) break;
+        int i0, j0;
+        tile_origin(P, tile, i0, j0);
+        if (i0 >= xe || j0 >= ye) continue;
+        const TileDesc desc = P.desc[tile];
+        if (desc.count < 0) continue;   // list did not fit the pool: the fused kernel renders this tile
+        const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
+        const bool active = pi < xe && pj < ye;
+
+        int cnt = 0;
+        TileRays tr;
+        if (desc.count > 0) {
+            make_tile_rays(cam, i0, j0, pi, pj, active, tr);
+            float kmax_t = INFINITY;
+            int kmax_slot = 0;
+            int left = desc.count;
+            // one coalesced 128-byte read per chunk: lanes 0..30 candidates, lane 31 the next chunk
+            int cur = __ldg(P.pool + (int64_t)desc.head * CHUNK_INTS + lane);
+#pragma unroll 1
+            while (left > 0) {
+                const int m = (left - 1) % CHUNK_IDS + 1;
+                left -= m;
+                const int s = cur;
+                const int next = __shfl_sync(FULL, cur, CHUNK_INTS - 1);
+                if (left > 0) cur = __ldg(P.pool + (int64_t)next * CHUNK_INTS + lane);   // prefetch
+                // ---- stage ---------------------------------------------------------------------
+                const int m4 = (m + 3) & ~3;
+                if (lane < m) {
+                    float4 rec[5];
+                    float poly[6];
+                    stage_candidate(P, tr, s, rec, poly);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) ws.rec[lane][k] = rec[k];
+                    ws.polyA[lane] = make_float4(poly[0], poly[1], poly[2], poly[3]);
+                    ws.polyB[lane] = make_float2(poly[4], poly[5]);
+                } else if (lane < m4) {   // pad to a multiple of 4: never a candidate
+                    ws.polyA[lane] = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+                    ws.polyB[lane] = make_float2(0.0f, 0.0f);
+                }
+                __syncwarp();
+                ST(st_pairs += (unsigned)m);
+                // ---- coarse: mask of the staged candidates this ray may hit ---------------------
+                unsigned mask = 0;
+#pragma unroll 1
+                for (int c = 0; c < m4; c += 4) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 pA = ws.polyA[c + u];
+                        const float2 pB = ws.polyB[c + u];
+                        const float ta = fmaf(tr.pa, pA.w, fmaf(tr.pb, pB.x, pA.y));   // c1 + a c3 + b c4
+                        const float tb = fmaf(tr.pb, pB.y, pA.z);                      // c2 + b c5
+                        const float S = fmaf(tr.pa, ta, fmaf(tr.pb, tb, pA.x));
+                        if (S < 0.0f) mask |= 1u << (c + u);
+                    }
+                }
+                if (!active) mask = 0;
+                // ---- precise: warp-wide rounds, one candidate per lane and round -----------------
+#pragma unroll 1
+                while (__any_sync(FULL, mask != 0)) {
+                    if (mask != 0) {
+                        const int c = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const PreciseHit h = precise_test(P, ws.rec[c], tr.dlx, tr.dly, tr.dlz, pi, pj);
+                        ST(st_f64 += h.refined);
+                        if (h.hit) {
+                            int slot = -1;
+                            if (cnt < K) slot = cnt++;
+                            else if (h.t1 < kmax_t) slot = kmax_slot;
+                            if (slot >= 0) {
+                                ws.kb_t[slot][lane] = h.t1;
+                                ws.kb_i[slot][lane] = h.s;
+                                ws.kb_a[slot][lane] = h.alpha;
+                                if (cnt == K) {   // buffer full: track the farthest entry
+                                    // entry distances are positive: their bit patterns order like the
+                                    // floats; the slot rides in the 4 low bits
+                                    unsigned best = 0;
+#pragma unroll
+                                    for (int k = 0; k < K; ++k)
+                                        best = max(best, (__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k);
+                                    kmax_slot = (int)(best & 15u);
+                                    kmax_t = ws.kb_t[kmax_slot][lane];
+                                }
+                            }
+                        }
+                    }
+                    ST(st_ins += 1);
+                }
+                __syncwarp();
+            }
+        }
+
+        // ---- order the hits by ascending entry distance -------------------------------------------
+        // Keys = entry-distance bits with the slot in the 4 low bits (unique, so the ranks are a
+        // permutation); rank_i = #{j : key_j < key_i}.  perm holds the slot of every rank, 4 bits each.
+        unsigned long long perm = 0;
+        int maxcnt = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
+        if (maxcnt > 0) {
+            unsigned key[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
+#pragma unroll 1
+            for (int i = 0; i < maxcnt; ++i) {
+                if (i < cnt) {
+                    const unsigned ki = (__float_as_uint(ws.kb_t[i][lane]) & ~15u) | (unsigned)i;
+                    int rank = 0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) rank += key[j] < ki;
+                    perm |= (unsigned long long)i << (4 * rank);
+                }
+            }
+            // neighbours within float32 rounding (and the 4 truncated bits) of each other are ordered
+            // by their float64 entry distances (rare)
+            if (cnt > 1) {
+                float tp = ws.kb_t[(int)(perm & 15u)][lane];
+#pragma unroll 1
+                for (int k = 1; k < cnt; ++k) {
+                    const int sk = (int)((perm >> (4 * k)) & 15u);
+                    const float tk = ws.kb_t[sk][lane];
+                    if (fabsf(tk - tp) <= 4e-6f * fabsf(tk)) {
+                        // insertion among the near-tied predecessors
+                        int j = k;
+                        while (j > 0) {
+                            const int sa = (int)((perm >> (4 * (j - 1))) & 15u), sb = (int)((perm >> (4 * j)) & 15u);
+                            const float ta = ws.kb_t[sa][lane], tb = ws.kb_t[sb][lane];
+                            if (fabsf(tb - ta) > 4e-6f * fabsf(tb)) break;
+                            ST(st_f64 += 2);
+                            if (!exact_less(P.raw, cam, ws.kb_i[sb][lane], ws.kb_i[sa][lane], pi, pj)) break;
+                            const unsigned long long ma = 15ull << (4 * (j - 1)), mb = 15ull << (4 * j);
+                            perm = (perm & ~(ma | mb)) | ((unsigned long long)sb << (4 * (j - 1))) |
+                                   ((unsigned long long)sa << (4 * j));
+                            --j;
+                        }
+                    }
+                    tp = ws.kb_t[(int)((perm >> (4 * k)) & 15u)][lane];
+                }
+            }
+        }
+
+        // ---- compositing: accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98) ---------
+        float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+        int nl = 0;
+        if (maxcnt > 0) {
+            float Y[15];
+            sh_basis(tr.dnx, tr.dny, tr.dnz, Y);
+            const int nmine = min(cnt, P.depth);
+            const int nloop = min(maxcnt, P.depth);
+#pragma unroll 1
+            for (int k = 0; k < nloop; ++k) {
+                if (k < nmine && T >= P.t_cut) {
+                    const int slot = (int)((perm >> (4 * k)) & 15u);
+                    const int s = ws.kb_i[slot][lane];
+                    const float alpha = ws.kb_a[slot][lane];
+                    float r, g, b;
+                    eval_colour(P, s, Y, r, g, b);
+                    const float wgt = T * alpha;
+                    cr = fmaf(wgt, r, cr);
+                    cg = fmaf(wgt, g, cg);
+                    cb = fmaf(wgt, b, cb);
+                    T *= 1.0f - alpha;
+                    ++nl;
+                }
+            }
+        }
+        store_tile(P, reinterpret_cast<float*>(&ws.rec[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
+        if (active) {
+            ST(st_rays += 1);
+            ST(st_hit += nl > 0);
+            ST(st_layers += (unsigned)nl);
+        }
+        ST(if (lane == 0) st_tiles += 1);
+    }
+
+    if (STATS && P.stats) {
+        unsigned long long v[ST_COUNT] = {0};
+        v[ST_RAYS] = st_rays; v[ST_RAYS_HIT] = st_hit; v[ST_LAYERS] = st_layers; v[ST_F64] = st_f64;
+        if (lane == 0) {   // warp-uniform counters are taken from lane 0 only
+            v[ST_PAIRS] = 32ull * st_pairs;
+            v[ST_TILES] = st_tiles;
+            v[ST_INSERTS] = st_ins;
+        }
+#pragma unroll
+        for (int k = 0; k < ST_COUNT; ++k) {
+            unsigned long long x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+            if (lane == 0 && x) atomicAdd(P.stats + k, x);
+        }
+    }
+#undef ST
+}
+
+template <bool STATS>
+int launch(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
+    static int blocks_per_sm[16] = {0};
+    const size_t smem = sizeof(WarpShared) * WARPS_PER_CTA;
+    int dev = s->device;
+    if (dev < 0 || dev >= 16) dev = 0;
+    if (blocks_per_sm[dev] == 0) {
+        CUDA_TRY(cudaFuncSetAttribute(k_shade_tiles<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade_tiles<STATS>, WARPS_PER_CTA * 32, smem));
+        if (nb < 1) {
+            rtgs_set_error("k_shade_tiles does not fit on an SM (smem %zu)", smem);
+            return RTGS_ERR_CUDA;
+        }
+        blocks_per_sm[dev] = nb;
+    }
+    int grid = s->sm_count * blocks_per_sm[dev];
+    const int need = (P.ntiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_shade_tiles<STATS><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+}  // namespace
+
+int rtgs_launch_shade_tiles(rtgs_scene* s, const RenderParams& P, cudaStream_t stream, bool want_stats) {
+    return want_stats ? launch<true>(s, P, stream) : launch<false>(s, P, stream);
+}

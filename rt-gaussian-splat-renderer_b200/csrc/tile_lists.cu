@@ -1,0 +1,231 @@
+// tile_lists.cu — k_tile_lists: the BVH traversal of the render path (scene.py:406-450), done once per
+// frame for whole pixel tiles instead of once per ray and per compositing step.
+//
+// All primary rays share the camera origin, so a rectangle of pixels is a thin pyramid bounded by 4
+// planes through the origin, and "every Gaussian whose bound some ray of the rectangle hits" is a
+// frustum query on the LBVH.  A warp owns one 8x16-pixel GROUP at a time (persistent threads, groups
+// pulled from an atomic counter in 32x32-pixel macro-tile order):
+//   1. group traversal - up to 32 nodes are popped from a shared-memory stack per step, each lane tests
+//      the two child boxes of its node against the 4 planes, survivors are compacted with ballot/popc
+//      (internal children -> stack, leaves -> the group's candidate list in shared memory);
+//   2. for each of the group's four 4x8-pixel tiles the list is filtered with the tile's own frustum
+//      (one leaf box per lane, coalesced because the list is in Morton order) and streamed to the
+//      global list pool in 128-byte chunks (render_common.cuh), where k_shade_tiles picks it up.
+// A group whose list would overflow shared memory traverses the LBVH per tile instead (same code,
+// leaves stream straight to the pool).  A tile whose list does not fit the pool is handed to the fused
+// kernel (render.cu) through the fallback list; nothing is ever dropped.
+//
+// The kernel holds no per-ray state: ~50 registers and 3.5 KB of shared memory per warp, so 40+ warps
+// per SM hide the dependent node fetches (the fused kernel ran this phase at 16 warps per SM).
+#include "render_common.cuh"
+
+using namespace rtgs_dev;
+
+namespace {
+
+constexpr int STACK_CAP = 256;
+constexpr int STACK_SINGLE = STACK_CAP - 100;   // above this pop one node at a time: growth/step <= 32, then DFS depth <= 62
+constexpr int GLIST_CAP = 512;
+constexpr int CQ_CAP = 128;
+static_assert(GLIST_CAP >= STACK_CAP, "per-tile traversal keeps its stack in the group list");
+
+struct __align__(16) WarpShared {
+    int stack[STACK_CAP];
+    int glist[GLIST_CAP];
+    int cq[CQ_CAP];
+};
+
+template <bool STATS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_tile_lists(const __grid_constant__ RenderParams P) {
+    __shared__ WarpShared smem[WARPS_PER_CTA];
+    WarpShared& ws = smem[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const CamD& cam = P.cam;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+
+    unsigned long long st_nodes = 0, st_steps = 0, st_cands = 0;
+#define ST(expr) do { if (STATS) { expr; } } while (0)
+
+    int slab_next = 0, slab_end = 0;   // chunks this warp owns in the pool
+
+    // one traversal step: pop <= 32 nodes from `stk`, test both child boxes of each against `fr`,
+    // compact the survivors: internal children back onto `stk`, leaves into `dst`
+    auto traverse_step = [&](int* stk, int& top, int* dst, int& nd, const Frustum& fr) {
+        const int take = top > STACK_SINGLE ? 1 : min(32, top);
+        int node = -1;
+        if (lane < take) node = stk[top - 1 - lane];
+        top -= take;
+        __syncwarp();
+        bool h0 = false, h1 = false;
+        int c0 = 0, c1 = 0;
+        if (node >= 0) {
+            const float4 a = __ldg(P.nodes + (int64_t)node * 4 + 0);
+            const float4 b = __ldg(P.nodes + (int64_t)node * 4 + 1);
+            const float4 c = __ldg(P.nodes + (int64_t)node * 4 + 2);
+            const float4 d = __ldg(P.nodes + (int64_t)node * 4 + 3);
+            c0 = __float_as_int(d.x);
+            c1 = __float_as_int(d.y);
+            h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
+            h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
+        }
+        ST(st_nodes += 2ull * (unsigned)take);
+        ST(st_steps += 1);
+        const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
+        const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
+        if (h0 && c0 >= 0) stk[top + __popc(mI0 & lt_mask)] = c0;
+        const int topa = top + __popc(mI0);
+        if (h1 && c1 >= 0) stk[topa + __popc(mI1 & lt_mask)] = c1;
+        top = topa + __popc(mI1);
+        if (h0 && c0 < 0) dst[nd + __popc(mL0 & lt_mask)] = ~c0;
+        const int nda = nd + __popc(mL0);
+        if (h1 && c1 < 0) dst[nda + __popc(mL1 & lt_mask)] = ~c1;
+        nd = nda + __popc(mL1);
+        __syncwarp();
+    };
+
+    // take one chunk from the pool (-1: exhausted)
+    auto alloc_chunk = [&]() -> int {
+        if (slab_next == slab_end) {
+            unsigned base = 0;
+            if (lane == 0) base = atomicAdd(P.counters + CTR_POOL, (unsigned)SLAB_CHUNKS);
+            base = __shfl_sync(FULL, base, 0);
+            if (base + (unsigned)SLAB_CHUNKS > (unsigned)P.pool_chunks) return -1;
+            slab_next = (int)base;
+            slab_end = slab_next + SLAB_CHUNKS;
+        }
+        return slab_next++;
+    };
+
+    // write the last `m` entries of cq as one chunk linked in front of `head`
+    auto write_chunk = [&](int m, int& ncq, int& head, int& count) -> bool {
+        const int chunk = alloc_chunk();
+        if (chunk < 0) return false;
+        int v = head;
+        if (lane < m) v = ws.cq[ncq - m + lane];
+        if (lane < m || lane == CHUNK_INTS - 1) P.pool[(int64_t)chunk * CHUNK_INTS + lane] = v;
+        head = chunk;
+        ncq -= m;
+        count += m;
+        __syncwarp();
+        return true;
+    };
+
+#pragma unroll 1
+    for (;;) {
+        int group = 0;
+        if (lane == 0) group = (int)atomicAdd(P.counters + CTR_WORK, 1u);
+        group = __shfl_sync(FULL, group, 0);
+        if (group * TILES_PER_GROUP >= P.ntiles) break;
+        int gi0, gj0;
+        group_origin(P, group, gi0, gj0);
+        if (gi0 >= xe || gj0 >= ye) continue;
+
+        // ---- group traversal: the LBVH once for the 8x16-pixel frustum ---------------------------
+        int ng = 0;
+        bool per_tile = false;
+        {
+            Frustum fg;
+            make_frustum(cam, gi0, min(gi0 + GPX_I, xe), gj0, min(gj0 + GPX_J, ye), fg);
+            int top = 1;
+            if (lane == 0) ws.stack[0] = 0;
+            __syncwarp();
+#pragma unroll 1
+            while (top > 0) {
+                if (ng > GLIST_CAP - 64) {   // too many candidates for the shared list
+                    per_tile = true;
+                    break;
+                }
+                traverse_step(ws.stack, top, ws.glist, ng, fg);
+            }
+        }
+
+#pragma unroll 1
+        for (int sub = 0; sub < TILES_PER_GROUP; ++sub) {
+            const int i0 = gi0 + (sub / GROUP_TJ) * TILE_I, j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
+            if (i0 >= xe || j0 >= ye) continue;
+            const int tile = group * TILES_PER_GROUP + sub;
+            Frustum fr;
+            make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
+            int head = -1, count = 0, ncq = 0;
+            bool ok = true;
+            if (!per_tile) {
+                // filter the group's candidates: leaf box vs tile frustum, 32 per step
+#pragma unroll 1
+                for (int gpos = 0; gpos < ng && ok; gpos += 32) {
+                    const int idx = gpos + lane;
+                    bool h = false;
+                    int s = 0;
+                    if (idx < ng) {
+                        s = ws.glist[idx];
+                        const float4 a = __ldg(P.leafbox + (int64_t)s * 2 + 0), b = __ldg(P.leafbox + (int64_t)s * 2 + 1);
+                        h = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
+                    }
+                    ST(st_nodes += (unsigned)min(32, ng - gpos));
+                    ST(st_steps += 1);
+                    const unsigned mh = __ballot_sync(FULL, h);
+                    if (h) ws.cq[ncq + __popc(mh & lt_mask)] = s;
+                    ncq += __popc(mh);
+                    __syncwarp();
+                    if (ncq >= CHUNK_IDS) ok = write_chunk(CHUNK_IDS, ncq, head, count);
+                }
+            } else {
+                int top = 1;
+                if (lane == 0) ws.glist[0] = 0;
+                __syncwarp();
+#pragma unroll 1
+                while (top > 0 && ok) {
+                    traverse_step(ws.glist, top, ws.cq, ncq, fr);
+#pragma unroll 1
+                    while (ncq >= CHUNK_IDS && ok) ok = write_chunk(CHUNK_IDS, ncq, head, count);
+                }
+            }
+            if (ok && ncq > 0) ok = write_chunk(ncq, ncq, head, count);
+            if (lane == 0) {
+                TileDesc d;
+                d.head = head;
+                d.count = ok ? count : -1;
+                P.desc[tile] = d;
+                if (!ok) P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
+            }
+            ST(st_cands += ok ? (unsigned)count : 0u);
+            __syncwarp();
+        }
+    }
+
+    if (STATS && P.stats && lane == 0) {
+        if (st_nodes) atomicAdd(P.stats + ST_NODES, st_nodes);
+        if (st_steps) atomicAdd(P.stats + ST_STEPS, st_steps);
+        if (st_cands) atomicAdd(P.stats + ST_CANDS, st_cands);
+    }
+#undef ST
+}
+
+template <bool STATS>
+int launch(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
+    static int blocks_per_sm[16] = {0};
+    int dev = s->device;
+    if (dev < 0 || dev >= 16) dev = 0;
+    if (blocks_per_sm[dev] == 0) {
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_tile_lists<STATS>, WARPS_PER_CTA * 32, 0));
+        if (nb < 1) {
+            rtgs_set_error("k_tile_lists does not fit on an SM");
+            return RTGS_ERR_CUDA;
+        }
+        blocks_per_sm[dev] = nb;
+    }
+    int grid = s->sm_count * blocks_per_sm[dev];
+    const int need = (P.ntiles / TILES_PER_GROUP + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_tile_lists<STATS><<<grid, WARPS_PER_CTA * 32, 0, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+}  // namespace
+
+int rtgs_launch_tile_lists(rtgs_scene* s, const RenderParams& P, cudaStream_t stream, bool want_stats) {
+    return want_stats ? launch<true>(s, P, stream) : launch<false>(s, P, stream);
+}

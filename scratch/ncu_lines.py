@@ -19,6 +19,7 @@ for r in rows:
             pass
 tot_i = sum(l[3] for l in lines); tot_s = sum(l[4] for l in lines)
 print(f"total instr {tot_i:,}  samples {tot_s:,}")
-lines.sort(key=lambda l: -l[3])
+key = 4 if len(sys.argv) > 4 and sys.argv[4] == "smp" else 3
+lines.sort(key=lambda l: -l[key])
 for f, n, src, ins, smp, thr in lines[:top]:
     print(f"{f}:{n:4d} {100*ins/tot_i:5.1f}% ins {100*smp/max(tot_s,1):5.1f}% smp thr={thr:>4} | {src[:110]}")
