@@ -38,7 +38,7 @@ void rtgs_set_error(const char* fmt, ...);
 //      [s*4 + 1] = { W00, W01, W02, W10 }        W = S^-1 R^T / |q|^4  (local-frame matrix:
 //      [s*4 + 2] = { W11, W12, W20, W21 }        x' = W (x - p);  Sigma^-1 = W^T W)
 //      [s*4 + 3] = { W22, dc.r, dc.g, dc.b }     dc = post-sigmoid colour (scene.py:113)
-// shp  [s*12 .. s*12+11] = 45 SH floats (sh_10.rgb, sh_11.rgb, ... sh_36.rgb) + 3 pad
+// shp  [s*12 .. s*12+11] = 45 SH floats (sh_10.rgb, sh_11.rgb, ... sh_36.rgb) + dc.rgb
 // raw  [s*3 .. s*3+2]    = { p.xyz, q.x } { q.yzw, s.x } { s.yz, original index (int bits), 0 }
 //                          (inputs of the float64 exact-decision path)
 // node [k*4 + 0] = { lc.x, lc.y, lc.z, lh.x }      child boxes as (centre c, half extent h), h rounded up

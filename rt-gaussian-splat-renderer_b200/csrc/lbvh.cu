@@ -258,7 +258,7 @@ __global__ void k_pack(int64_t n, const uint64_t* __restrict__ keys, const float
         float v[48];
 #pragma unroll
         for (int k = 0; k < 45; ++k) v[k] = src[k];
-        v[45] = v[46] = v[47] = 0.0f;
+        v[45] = color[g * 3 + 0]; v[46] = color[g * 3 + 1]; v[47] = color[g * 3 + 2];   // DC colour rides in the pad
 #pragma unroll
         for (int k = 0; k < 12; ++k)
             shp[s * 12 + k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);

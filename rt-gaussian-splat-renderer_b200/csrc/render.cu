@@ -131,10 +131,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 bool h0 = false, h1 = false;
                 int c0 = 0, c1 = 0;
                 if (node >= 0) {
-                    const float4 a = __ldg(P.nodes + (int64_t)node * 4 + 0);
-                    const float4 b = __ldg(P.nodes + (int64_t)node * 4 + 1);
-                    const float4 c = __ldg(P.nodes + (int64_t)node * 4 + 2);
-                    const float4 d = __ldg(P.nodes + (int64_t)node * 4 + 3);
+                    float4 a, b, c, d;
+                    ldg256(P.nodes + (int64_t)node * 4 + 0, a, b);
+                    ldg256(P.nodes + (int64_t)node * 4 + 2, c, d);
                     c0 = __float_as_int(d.x);
                     c1 = __float_as_int(d.y);
                     h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);

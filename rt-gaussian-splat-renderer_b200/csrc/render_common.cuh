@@ -63,6 +63,14 @@ enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 
 enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
        ST_FALLBACK, ST_COUNT = 12 };
 
+// 256-bit read-only global load (sm_100 LDG.E.256): the L1 data pipe is charged per 128-byte line and
+// instruction, so a gather of 32-byte pieces costs half of what two 16-byte gathers do.  p is 32-byte aligned.
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(p));
+}
+
 // tile id -> pixel origin.  id = (macro * GROUPS_PER_MACRO + group) * TILES_PER_GROUP + sub, so that the
 // four tiles of a traversal group are consecutive and consecutive groups share a 32x32-pixel macro tile.
 __device__ __forceinline__ void group_origin(const RenderParams& P, int group, int& gi0, int& gj0) {
@@ -226,8 +234,9 @@ __device__ __forceinline__ void make_tile_rays(const CamD& cam, int i0, int j0, 
 __device__ __forceinline__ void stage_candidate(const RenderParams& P, const TileRays& tr, int s, float4 (&rec)[5],
                                                 float (&poly)[6]) {
     const CamD& cam = P.cam;
-    const float4 g0 = __ldg(P.geo + (int64_t)s * 4 + 0), g1 = __ldg(P.geo + (int64_t)s * 4 + 1),
-                 g2 = __ldg(P.geo + (int64_t)s * 4 + 2), g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
+    float4 g0, g1, g2, g3;
+    ldg256(P.geo + (int64_t)s * 4 + 0, g0, g1);
+    ldg256(P.geo + (int64_t)s * 4 + 2, g2, g3);
     const double W00 = g1.x, W01 = g1.y, W02 = g1.z, W10 = g1.w, W11 = g2.x, W12 = g2.y, W20 = g2.z, W21 = g2.w,
                  W22 = g3.x;
     auto Wmul = [&](const d3& v) {
@@ -318,25 +327,30 @@ __device__ __forceinline__ PreciseHit precise_test(const RenderParams& P, const 
     return h;
 }
 
-// rgb = color + eval_sh(normalize(dir))  (gaussian.py:199-200) of the Gaussian at sorted position s
+// rgb = color + eval_sh(normalize(dir))  (gaussian.py:199-200) of the Gaussian at sorted position s.
+// With SH the 192-byte record holds the 45 coefficients followed by the DC colour.
 __device__ __forceinline__ void eval_colour(const RenderParams& P, int s, const float (&Y)[15], float& r, float& g,
                                             float& b) {
-    const float4 g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
-    r = g3.y; g = g3.z; b = g3.w;
     if (P.has_sh) {
         const float4* sp = P.shp + (int64_t)s * 12;
         float v[48];
 #pragma unroll
-        for (int f = 0; f < 12; ++f) {
-            const float4 x = __ldg(sp + f);
-            v[4 * f] = x.x; v[4 * f + 1] = x.y; v[4 * f + 2] = x.z; v[4 * f + 3] = x.w;
+        for (int f = 0; f < 6; ++f) {
+            float4 x, y;
+            ldg256(sp + 2 * f, x, y);
+            v[8 * f] = x.x; v[8 * f + 1] = x.y; v[8 * f + 2] = x.z; v[8 * f + 3] = x.w;
+            v[8 * f + 4] = y.x; v[8 * f + 5] = y.y; v[8 * f + 6] = y.z; v[8 * f + 7] = y.w;
         }
+        r = v[45]; g = v[46]; b = v[47];
 #pragma unroll
         for (int j = 0; j < 15; ++j) {
             r = fmaf(Y[j], v[3 * j + 0], r);
             g = fmaf(Y[j], v[3 * j + 1], g);
             b = fmaf(Y[j], v[3 * j + 2], b);
         }
+    } else {
+        const float4 g3 = __ldg(P.geo + (int64_t)s * 4 + 3);
+        r = g3.y; g = g3.z; b = g3.w;
     }
 }
 
