@@ -14,8 +14,11 @@ per-GPU work is fixed as N grows ("scaling": "weak").  One ray = one finished pi
 value  = whole-job Mrays/s with everything resident in HBM (device-timed, CUDA events, max over ranks)
 e2e    = the same through the public API call with HOST buffers (RayTracer.render: camera struct
          in, image copied back to host memory inside the timed region)
-roofline = algorithmic bytes per ray (16 + kbar*(64 + 192[sh])) x rays per launch /
-         mean kernel time, against the measured HBM copy bandwidth in MEASURED_PEAKS.json
+roofline = the dominant kernel, k_shade_tiles (intersection + k-buffer + SH compositing): algorithmic bytes per
+         ray (16 + kbar*(64 + 192[sh]), all of them consumed by this kernel) x rays per launch /
+         its mean duration, measured with CUDA events the library records around each kernel on the render
+         stream during the timed region, against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
+         "kernels" lists every kernel of the step with its mean time and share
 cpu_baseline = oracle/ref_cpu.cpp (reference-shaped C++/OpenMP port, float32) on a pixel subsample
 """
 from __future__ import annotations
@@ -122,12 +125,12 @@ def load_peak():
     return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def load_traffic():
-    """dram bytes per launch of the render kernel from the committed ncu summary, if any."""
+def load_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu summary (profiles/), if any."""
     p = ROOT / "profiles" / "render_kernel_traffic.json"
     if p.exists():
         try:
-            return json.loads(p.read_text()).get("dram_bytes_per_launch")
+            return json.loads(p.read_text())[kernel]["dram_bytes_per_launch"]
         except Exception:
             return None
     return None
@@ -242,6 +245,8 @@ def main():
         set_view(s)
         rt.render_device(DEPTH, out=out)
     barrier()
+    timed_frames = min(args.steps, 4096)
+    scene.set_option("kernel_timing", timed_frames)   # events around every kernel of the timed steps
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -255,12 +260,14 @@ def main():
         ev[s][0].record()
         rt.render_device(DEPTH, out=out)
         ev[s][1].record()
-        launches += 1
+        launches += 3     # k_tile_lists, k_shade_tiles, k_render (fallback list; returns at once when empty)
     e_end.record()
     barrier()
     total_ms = e_beg.elapsed_time(e_end)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     clocks = sampler.stop() if rank == 0 else None
+    per_kernel = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)   # ms: lists, shade, fused
+    scene.set_option("kernel_timing", 0)
 
     # end-to-end: public API call with host buffers (camera in, image out on the host)
     for s in range(min(args.warmup, 2)):
@@ -275,9 +282,11 @@ def main():
     e2e_s = time.perf_counter() - t0
 
     if dist is not None:
-        t = torch.tensor([total_ms, e2e_s, float(np.mean(kern_ms))], dtype=torch.float64, device="cuda")
+        t = torch.tensor([total_ms, e2e_s, float(np.mean(kern_ms)), *per_kernel.tolist()], dtype=torch.float64,
+                         device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kern_mean = t.tolist()
+        total_ms, e2e_s, kern_mean, *pk = t.tolist()
+        per_kernel = np.asarray(pk)
     else:
         kern_mean = float(np.mean(kern_ms))
 
@@ -286,7 +295,13 @@ def main():
         value = rays_step * args.steps / (total_ms * 1e-3) / 1e6
         e2e_val = rays_step * args.steps / e2e_s / 1e6
         peak, peak_src = load_peak()
-        achieved = W * H * bytes_ray / (kern_mean * 1e-3) / 1e9
+        from rtgs._native import KERNEL_NAMES
+        dom = int(np.argmax(per_kernel))
+        dom_ms = float(per_kernel[dom])
+        achieved = W * H * bytes_ray / (dom_ms * 1e-3) / 1e9
+        step_ms = float(per_kernel.sum())
+        kernels = [{"kernel": KERNEL_NAMES[k], "ms": float(per_kernel[k]), "share": float(per_kernel[k] / step_ms)}
+                   for k in range(len(KERNEL_NAMES))]
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -295,8 +310,12 @@ def main():
                     "d2h_bytes_per_step": W * H * 3 * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(), "peak_source": peak_src, "kernel": "k_render<16>",
-                         "kernel_ms": kern_mean, "bytes_per_ray": bytes_ray, "kbar": kbar},
+                         "traffic": load_traffic(KERNEL_NAMES[dom]), "peak_source": peak_src,
+                         "kernel": KERNEL_NAMES[dom], "kernel_ms": dom_ms, "step_ms": kern_mean,
+                         "bytes_per_ray": bytes_ray, "kbar": kbar,
+                         "note": "algorithmic bytes assume zero reuse between rays; neighbouring rays share "
+                                 "Gaussians through L1/L2, so achieved may exceed what DRAM moved (see traffic)"},
+            "kernels": kernels,
             "clocks": clocks,
             "scene_stats": {"hit_fraction": agg["rays_hit"] / agg["rays"], "kbar": kbar,
                             "child_boxes_tested_per_ray": agg["nodes_tested"] / agg["rays"],
@@ -304,7 +323,8 @@ def main():
                             "pair_tests_per_ray": agg["pair_tests"] / agg["rays"],
                             "f64_refinements_per_Mray": 1e6 * agg["f64_refinements"] / agg["rays"],
                             "traversal_steps_per_tile": agg["traversal_steps"] / max(agg["tiles"], 1),
-                            "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1)},
+                            "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1),
+                            "fallback_tiles": agg["fallback_tiles"]},
             "bvh_build_ms": build_ms,
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RTGS_ABI_VERSION 1
+#define RTGS_ABI_VERSION 2
 #define RTGS_MAX_DEPTH 32        /* largest `depth` rtgs_render composites in one pass */
 
 typedef enum rtgs_status {
@@ -126,6 +126,30 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
                 int32_t x0, int32_t y0, int32_t w, int32_t h,
                 int32_t depth, float t_cut, int32_t accumulate, int32_t full_image_pitch,
                 float* out_rgb, float* out_T, void* stream, rtgs_render_stats* stats);
+
+/* Tuning knobs of one scene's render path (no reference counterpart; defaults need no call).
+ *  RTGS_OPT_RENDER_MODE      0 (default): k_tile_lists + k_shade_tiles, the fused kernel only for tiles whose
+ *                            candidate list did not fit the pool; 1: the fused kernel alone.  depth > 16 always
+ *                            uses the fused kernel.
+ *  RTGS_OPT_LIST_POOL_CHUNKS capacity of the candidate-list pool in 128-byte chunks (31 candidates each);
+ *                            -1 (default) = 16 chunks per 4x8-pixel tile of the rendered region.  A small pool is
+ *                            legal (it only moves tiles to the fused kernel) and is what the tests use to
+ *                            exercise that path.
+ *  RTGS_OPT_KERNEL_TIMING    see rtgs_scene_read_kernel_times. */
+typedef enum rtgs_option {
+    RTGS_OPT_RENDER_MODE = 0,
+    RTGS_OPT_LIST_POOL_CHUNKS = 1,
+    RTGS_OPT_KERNEL_TIMING = 2
+} rtgs_option;
+int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value);
+
+/* Per-kernel device times (measurement only).  RTGS_OPT_KERNEL_TIMING = n > 0 makes every following render
+ * bracket its kernels with CUDA events on the render stream (a ring of n frames; 0 switches it off).
+ * rtgs_scene_read_kernel_times synchronises the device and returns, for the last `frames` renders (oldest
+ * first), RTGS_NUM_KERNELS floats each: milliseconds of k_tile_lists, k_shade_tiles and the fused k_render
+ * (0 for a kernel that did not run).  Fails with RTGS_ERR_STATE if fewer frames were timed. */
+#define RTGS_NUM_KERNELS 3
+int rtgs_scene_read_kernel_times(rtgs_scene* s, int32_t frames, float* ms /* frames * RTGS_NUM_KERNELS */);
 
 /* Pinned (page-locked, device-mapped) host memory for image outputs.  rtgs_render_host is
  * fastest when its output buffers come from here (the kernel then writes the framebuffer

@@ -53,6 +53,7 @@ void free_scene(rtgs_scene* s) {
     if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
     if (s->pinned_T) cudaFreeHost(s->pinned_T);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    for (cudaEvent_t e : s->timing_events) cudaEventDestroy(e);
     delete s;
 }
 
@@ -301,6 +302,67 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
         stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
         stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->fallback_tiles = hs[10]; stats->reserved = 0;
+    }
+    return RTGS_OK;
+}
+
+int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
+    RTGS_CHECK_ARG(s != nullptr);
+    switch (option) {
+        case RTGS_OPT_RENDER_MODE:
+            RTGS_CHECK_ARG(value == 0 || value == 1);
+            s->opt_render_mode = (int)value;
+            return RTGS_OK;
+        case RTGS_OPT_LIST_POOL_CHUNKS: {
+            RTGS_CHECK_ARG(value >= -1 && value <= (1ll << 26));
+            DeviceGuard g(s->device);
+            s->opt_pool_chunks = value;
+            // dropped here, re-created with the new capacity by the next render
+            cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
+            s->tile_desc = nullptr; s->list_pool = nullptr; s->fallback_tiles = nullptr;
+            s->list_tiles = 0;
+            s->pool_chunks = 0;
+            return RTGS_OK;
+        }
+        case RTGS_OPT_KERNEL_TIMING: {
+            RTGS_CHECK_ARG(value >= 0 && value <= 4096);
+            DeviceGuard g(s->device);
+            CUDA_TRY(cudaDeviceSynchronize());
+            for (cudaEvent_t e : s->timing_events) cudaEventDestroy(e);
+            s->timing_events.clear();
+            s->timing_ran.assign((size_t)value, 0);
+            s->timing_frames = 0;
+            for (int64_t k = 0; k < value * 4; ++k) {
+                cudaEvent_t e;
+                CUDA_TRY(cudaEventCreate(&e));
+                s->timing_events.push_back(e);
+            }
+            return RTGS_OK;
+        }
+        default:
+            rtgs_set_error("unknown option %d", (int)option);
+            return RTGS_ERR_INVALID;
+    }
+}
+
+int rtgs_scene_read_kernel_times(rtgs_scene* s, int32_t frames, float* ms) {
+    RTGS_CHECK_ARG(s != nullptr && ms != nullptr && frames >= 1);
+    const int64_t ring = (int64_t)s->timing_ran.size();
+    if (ring == 0 || frames > ring || frames > s->timing_frames) {
+        rtgs_set_error("rtgs_scene_read_kernel_times: %d frames requested, %lld timed (ring %lld)", (int)frames,
+                       (long long)s->timing_frames, (long long)ring);
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaDeviceSynchronize());
+    for (int32_t f = 0; f < frames; ++f) {
+        const int64_t slot = (s->timing_frames - frames + f) % ring;
+        for (int k = 0; k < RTGS_NUM_KERNELS; ++k) {
+            float t = 0.0f;
+            if (s->timing_ran[slot] & (1u << k))
+                CUDA_TRY(cudaEventElapsedTime(&t, s->timing_events[slot * 4 + k], s->timing_events[slot * 4 + k + 1]));
+            ms[f * RTGS_NUM_KERNELS + k] = t;
+        }
     }
     return RTGS_OK;
 }

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <vector>
 
 #include "../../include/rtgs_b200.h"
 
@@ -86,6 +87,8 @@ struct rtgs_scene {
     int* fallback_tiles = nullptr;
     int list_tiles = 0;
     int pool_chunks = 0;
+    int64_t opt_pool_chunks = -1;             // RTGS_OPT_LIST_POOL_CHUNKS (-1 = default sizing)
+    int opt_render_mode = -1;                 // RTGS_OPT_RENDER_MODE (-1 = RTGS_RENDER_MODE env or 0)
     float* stage_rgb = nullptr;               // device staging for rtgs_render_host
     float* stage_T = nullptr;
     size_t stage_pixels = 0;
@@ -93,6 +96,11 @@ struct rtgs_scene {
     float* pinned_T = nullptr;
     size_t pinned_pixels = 0;
     cudaStream_t own_stream = nullptr;
+
+    // per-kernel timing ring (RTGS_OPT_KERNEL_TIMING): 4 events per frame slot
+    std::vector<cudaEvent_t> timing_events;
+    std::vector<unsigned char> timing_ran;   // per slot: bit k = kernel k was launched
+    int64_t timing_frames = 0;               // renders recorded since timing was switched on
 };
 
 // ---- launchers implemented in the kernel translation units ------------------------------------

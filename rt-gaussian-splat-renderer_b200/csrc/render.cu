@@ -487,7 +487,8 @@ int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
 
 // Which kernels render a frame: 0 = k_tile_lists + k_shade_tiles (+ k_render on the fallback list),
 // 1 = the fused k_render alone.  depth > 16 always takes the fused kernel (its k-buffer has 32 entries).
-int render_mode() {
+int render_mode(const rtgs_scene* s) {
+    if (s->opt_render_mode >= 0) return s->opt_render_mode;
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("RTGS_RENDER_MODE");
@@ -503,9 +504,7 @@ int ensure_lists(rtgs_scene* s, int ntiles) {
     cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
     s->tile_desc = nullptr; s->list_pool = nullptr; s->fallback_tiles = nullptr;
     s->list_tiles = 0;
-    int64_t chunks = (int64_t)ntiles * 16;
-    if (const char* e = getenv("RTGS_POOL_CHUNKS")) chunks = atoll(e);   // tests: force the fallback path
-    if (chunks < 0) chunks = 0;
+    int64_t chunks = s->opt_pool_chunks >= 0 ? s->opt_pool_chunks : (int64_t)ntiles * 16;
     if (chunks > (1ll << 26)) chunks = 1ll << 26;
     CUDA_TRY(cudaMalloc((void**)&s->tile_desc, (size_t)ntiles * sizeof(TileDesc)));
     CUDA_TRY(cudaMalloc((void**)&s->list_pool, (size_t)(chunks > 0 ? chunks : 1) * CHUNK_INTS * sizeof(int)));
@@ -548,26 +547,48 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.use_fallback_list = 0;
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, CTR_COUNT * sizeof(unsigned int), stream));
     if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), stream));
-    if (depth > 16)
-        return want_stats ? launch_render_k<32, true>(s, P, stream) : launch_render_k<32, false>(s, P, stream);
-    if (render_mode() == 1)
+
+    // optional per-kernel timing: events e[0..3] of this frame's ring slot bracket the three kernels
+    cudaEvent_t* ev = nullptr;
+    unsigned char* ran = nullptr;
+    if (!s->timing_ran.empty()) {
+        const int64_t slot = s->timing_frames % (int64_t)s->timing_ran.size();
+        ev = &s->timing_events[slot * 4];
+        ran = &s->timing_ran[slot];
+        *ran = 0;
+        ++s->timing_frames;
+    }
+    auto mark = [&](int k) -> int {
+        if (ev) CUDA_TRY(cudaEventRecord(ev[k], stream));
+        return RTGS_OK;
+    };
+    auto fused = [&](int K) -> int {
+        if (K > 16) return want_stats ? launch_render_k<32, true>(s, P, stream) : launch_render_k<32, false>(s, P, stream);
         return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
+    };
+    int r;
+    if (depth > 16 || render_mode(s) == 1) {
+        if ((r = mark(0)) != RTGS_OK || (r = mark(1)) != RTGS_OK || (r = mark(2)) != RTGS_OK) return r;
+        if ((r = fused(depth > 16 ? 32 : 16)) != RTGS_OK) return r;
+        if (ran) *ran = 4;
+        return mark(3);
+    }
     // traversal -> per-tile candidate lists -> shading; tiles whose list did not fit the pool are
     // rendered by the fused kernel afterwards (it returns at once when there are none)
-    {
-        const int r = ensure_lists(s, P.ntiles);
-        if (r != RTGS_OK) return r;
-    }
+    if ((r = ensure_lists(s, P.ntiles)) != RTGS_OK) return r;
     P.desc = reinterpret_cast<TileDesc*>(s->tile_desc);
     P.pool = s->list_pool;
     P.pool_chunks = s->pool_chunks;
     P.fallback_tiles = s->fallback_tiles;
-    int r = rtgs_launch_tile_lists(s, P, stream, want_stats);
-    if (r != RTGS_OK) return r;
-    r = rtgs_launch_shade_tiles(s, P, stream, want_stats);
-    if (r != RTGS_OK) return r;
+    if ((r = mark(0)) != RTGS_OK) return r;
+    if ((r = rtgs_launch_tile_lists(s, P, stream, want_stats)) != RTGS_OK) return r;
+    if ((r = mark(1)) != RTGS_OK) return r;
+    if ((r = rtgs_launch_shade_tiles(s, P, stream, want_stats)) != RTGS_OK) return r;
+    if ((r = mark(2)) != RTGS_OK) return r;
     P.use_fallback_list = 1;
-    return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
+    if ((r = fused(16)) != RTGS_OK) return r;
+    if (ran) *ran = 7;
+    return mark(3);
 }
 
 int rtgs_launch_generate_rays(const rtgs_camera* cam, float* rays, cudaStream_t stream) {

@@ -23,6 +23,9 @@ using namespace rtgs_dev;
 
 namespace {
 
+#ifndef K1_CTAS
+#define K1_CTAS 4
+#endif
 constexpr int STACK_CAP = 256;
 constexpr int STACK_SINGLE = STACK_CAP - 100;   // above this pop one node at a time: growth/step <= 32, then DFS depth <= 62
 constexpr int GLIST_CAP = 512;
@@ -36,7 +39,7 @@ struct __align__(16) WarpShared {
 };
 
 template <bool STATS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 5) k_tile_lists(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(const __grid_constant__ RenderParams P) {
     __shared__ WarpShared smem[WARPS_PER_CTA];
     WarpShared& ws = smem[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;

@@ -52,6 +52,8 @@ SIGNATURES = {
     "rtgs_render": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                               C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp,
                               C.POINTER(rtgs_render_stats)]),
+    "rtgs_scene_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
+    "rtgs_scene_read_kernel_times": (C.c_int, [_vp, C.c_int32, _vp]),
     "rtgs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rtgs_host_free": (C.c_int, [_vp]),
     "rtgs_render_host": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
@@ -60,6 +62,9 @@ SIGNATURES = {
     "rtgs_trace_closest": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "rtgs_scene_destroy": (C.c_int, [_vp]),
 }
+
+OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING = 0, 1, 2
+KERNEL_NAMES = ("k_tile_lists", "k_shade_tiles", "k_render")
 
 _lib = None
 

@@ -181,6 +181,21 @@ class Scene:
     def num_gaussians(self) -> int:
         return self._n
 
+    def set_option(self, name: str, value: int) -> "Scene":
+        """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 0 = tile lists + shading kernels (default),
+        1 = the fused kernel alone; ``list_pool_chunks`` = capacity of the candidate-list pool (-1 = default)."""
+        opt = {"render_mode": _native.OPT_RENDER_MODE, "list_pool_chunks": _native.OPT_LIST_POOL_CHUNKS,
+               "kernel_timing": _native.OPT_KERNEL_TIMING}[name]
+        _native.check(_native.load().rtgs_scene_set_option(self.handle, opt, int(value)))
+        return self
+
+    def read_kernel_times(self, frames: int):
+        """(frames, 3) float32 milliseconds of k_tile_lists, k_shade_tiles, k_render for the last `frames` renders
+        (needs ``set_option("kernel_timing", n)`` with n >= frames beforehand).  Synchronises the device."""
+        out = np.zeros((int(frames), len(_native.KERNEL_NAMES)), np.float32)
+        _native.check(_native.load().rtgs_scene_read_kernel_times(self.handle, int(frames), out.ctypes.data))
+        return out
+
     def read_gaussians(self) -> dict:
         """Stored parameters in original order as float32 arrays."""
         n = self._n

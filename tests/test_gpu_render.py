@@ -107,6 +107,39 @@ def test_tile_sharding_is_bit_identical():
     assert np.array_equal(again, full), "render is not deterministic"
 
 
+def test_render_paths_agree_and_pool_overflow_falls_back():
+    """The same frame through (a) tile lists + shading kernels, (b) the fused kernel alone, (c) a list pool that
+    is far too small, so that most tiles take the fused kernel through the fallback list: all within tolerance
+    of the oracle, and (c) reports the fallback tiles."""
+    from rtgs.ray_tracer import RayTracer
+    gs = random_set(6000, seed=41, mean_scale=0.03)
+    scene = make_scene(gs)
+    cam, ocam = make_camera(0.7, 1.2, 2.4, 200, 136)
+    ref = O.render(gs, ocam, depth=16)["rgb"]
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    a = rt.render(16)
+    rt.render_device(16, collect_stats=True)
+    assert rt.last_stats["fallback_tiles"] == 0
+    scene.set_option("render_mode", 1)
+    b = rt.render(16)
+    scene.set_option("render_mode", 0)
+    scene.set_option("list_pool_chunks", 48)       # 3 slabs of 16 chunks for ~850 tiles
+    c = rt.render(16)
+    rt.render_device(16, collect_stats=True)
+    st = rt.last_stats
+    assert 0 < st["fallback_tiles"] <= st["tiles"]
+    assert st["rays"] == 200 * 136
+    scene.set_option("list_pool_chunks", 0)        # no pool at all: every non-empty tile falls back
+    d = rt.render(16)
+    scene.set_option("list_pool_chunks", -1)
+    e = rt.render(16)
+    for name, img in (("lists", a), ("fused", b), ("small pool", c), ("no pool", d)):
+        mx, ps, _ = compare(img, ref, TOL)
+        print(f"{name}: max-abs={mx:.2e} psnr={ps:.1f}")
+        assert mx <= TOL and ps >= 60.0, name
+    assert np.array_equal(a, e)
+
+
 def test_early_termination_bound():
     gs = random_set(3000, seed=21, mean_scale=0.06)
     scene = make_scene(gs)
