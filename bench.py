@@ -324,6 +324,7 @@ def main():
                             "f64_refinements_per_Mray": 1e6 * agg["f64_refinements"] / agg["rays"],
                             "traversal_steps_per_tile": agg["traversal_steps"] / max(agg["tiles"], 1),
                             "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1),
+                            "useful_candidates_per_tile": agg["useful_candidates"] / max(agg["tiles"], 1),
                             "fallback_tiles": agg["fallback_tiles"]},
             "bvh_build_ms": build_ms,
         }

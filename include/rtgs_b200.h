@@ -63,7 +63,7 @@ typedef struct rtgs_render_stats {
     uint64_t traversal_steps;    /* warp-wide traversal iterations (each pops <= 32 nodes) */
     uint64_t insert_rounds;      /* warp-wide k-buffer insertion rounds */
     uint64_t fallback_tiles;     /* tiles rendered by the fused kernel because their list did not fit the pool */
-    uint64_t reserved;
+    uint64_t useful_candidates;  /* staged candidates that passed the coarse test for at least one ray */
 } rtgs_render_stats;
 
 const char* rtgs_last_error(void);

@@ -301,7 +301,7 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
         CUDA_TRY(cudaStreamSynchronize(st));
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
         stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
-        stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->fallback_tiles = hs[10]; stats->reserved = 0;
+        stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->fallback_tiles = hs[10]; stats->useful_candidates = hs[11];
     }
     return RTGS_OK;
 }

@@ -53,7 +53,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __g
     const CamD& cam = P.cam;
     const int xe = P.x0 + P.w, ye = P.y0 + P.h;
 
-    unsigned long long st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
+    unsigned long long st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
 #define ST(expr) do { if (STATS) { expr; } } while (0)
 
 #pragma unroll 1
@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __g
                     }
                 }
                 if (!active) mask = 0;
+                ST(st_useful += (unsigned)__popc(__reduce_or_sync(FULL, mask)));
                 // ---- precise: warp-wide rounds, one candidate per lane and round -----------------
 #pragma unroll 1
                 while (__any_sync(FULL, mask != 0)) {
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __g
             v[ST_PAIRS] = 32ull * st_pairs;
             v[ST_TILES] = st_tiles;
             v[ST_INSERTS] = st_ins;
+            v[11] = st_useful;
         }
 #pragma unroll
         for (int k = 0; k < ST_COUNT; ++k) {

@@ -16,6 +16,7 @@ CONFIGS = {
     # name: (N, seed, sh_degree, (W, H))
     "100k_deg0_1080p": (100_000, 1001, 0, (1920, 1080)),
     "1m_deg3_1080p": (1_000_000, 1002, 3, (1920, 1080)),
+    "1m_deg0_1080p": (1_000_000, 1002, 0, (1920, 1080)),   # same geometry without SH (diagnostic)
     "3m_deg3_2160p": (3_000_000, 1003, 3, (3840, 2160)),
 }
 ORBIT_R = 2.2
