@@ -45,6 +45,34 @@ struct __align__(16) WarpShared {
 };
 static_assert(sizeof(WarpShared) == 9472, "shared-memory budget of 24 warps per SM");
 
+// Bitonic sorting network over the first N (8 or 16) of 16 register-resident keys, ascending.
+template <int N>
+__device__ __forceinline__ void sort_keys(unsigned (&key)[16]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned a = key[i], b = key[l];
+                    const bool up = (i & k) == 0;
+                    key[i] = up ? min(a, b) : max(a, b);
+                    key[l] = up ? max(a, b) : min(a, b);
+                }
+            }
+        }
+    }
+}
+
+// Could the entry distances behind two sorted keys be within 4e-6 relative of each other?  (The keys
+// carry the distances with 4 truncated bits, hence the wider 6e-6 screen; unused keys are 0xffffffff.)
+__device__ __forceinline__ bool keys_near(unsigned ka, unsigned kb) {
+    const float ta = __uint_as_float(ka & ~15u), tb = __uint_as_float(kb & ~15u);
+    return kb != 0xffffffffu && (tb - ta) <= 6e-6f * tb;
+}
+
 template <bool STATS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,30 +182,44 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __g
         }
 
         // ---- order the hits by ascending entry distance -------------------------------------------
-        // Keys = entry-distance bits with the slot in the 4 low bits (unique, so the ranks are a
-        // permutation); rank_i = #{j : key_j < key_i}.  perm holds the slot of every rank, 4 bits each.
+        // Keys = entry-distance bits (positive floats order like their bit patterns) with the slot in the
+        // 4 low bits, sorted in registers by a bitonic network; perm holds the slot of every rank, 4 bits
+        // each.  Neighbours within float32 rounding (and the 4 truncated bits) of each other are then
+        // ordered by their float64 entry distances (rare).
         unsigned long long perm = 0;
         int maxcnt = cnt;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
         if (maxcnt > 0) {
             unsigned key[K];
+            bool near = false;
+            if (maxcnt <= 8) {
 #pragma unroll
-            for (int k = 0; k < K; ++k)
-                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
-#pragma unroll 1
-            for (int i = 0; i < maxcnt; ++i) {
-                if (i < cnt) {
-                    const unsigned ki = (__float_as_uint(ws.kb_t[i][lane]) & ~15u) | (unsigned)i;
-                    int rank = 0;
+                for (int k = 0; k < 8; ++k)
+                    key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
+                sort_keys<8>(key);
+                unsigned lo = 0;
 #pragma unroll
-                    for (int j = 0; j < K; ++j) rank += key[j] < ki;
-                    perm |= (unsigned long long)i << (4 * rank);
+                for (int r = 0; r < 8; ++r) lo |= (key[r] & 15u) << (4 * r);
+                perm = lo;
+#pragma unroll
+                for (int r = 0; r + 1 < 8; ++r) near = near || keys_near(key[r], key[r + 1]);
+            } else {
+#pragma unroll
+                for (int k = 0; k < K; ++k)
+                    key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
+                sort_keys<16>(key);
+                unsigned lo = 0, hi = 0;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) {
+                    lo |= (key[r] & 15u) << (4 * r);
+                    hi |= (key[r + 8] & 15u) << (4 * r);
                 }
+                perm = ((unsigned long long)hi << 32) | lo;
+#pragma unroll
+                for (int r = 0; r + 1 < K; ++r) near = near || keys_near(key[r], key[r + 1]);
             }
-            // neighbours within float32 rounding (and the 4 truncated bits) of each other are ordered
-            // by their float64 entry distances (rare)
-            if (cnt > 1) {
+            if (near) {
                 float tp = ws.kb_t[(int)(perm & 15u)][lane];
 #pragma unroll 1
                 for (int k = 1; k < cnt; ++k) {
