@@ -52,6 +52,9 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="1m_deg3_1080p")
+    ap.add_argument("--sharding", default="views", choices=["views", "tiles"],
+                    help="multi-GPU partition: camera views (weak scaling, default) or 32-column stripes of every "
+                         "frame gathered on rank 0 (strong scaling)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-stride", type=int, default=0, help="pixel subsample stride of the CPU legs (0 = auto)")
     return ap.parse_args()
@@ -173,7 +176,9 @@ def main():
     config = {"workload": f"synthetic {n_g} random Gaussians, SH degree {sh_deg}, seed {seed}, {W}x{H}, fov 60, "
                           f"orbit r=2.2, depth {DEPTH}, t_cut {T_CUT}; 64-view orbit, view (step*N+rank)%64",
               "gaussians": n_g, "sh_degree": sh_deg, "resolution": [W, H], "depth": DEPTH,
-              "sharding": "camera views (scene replicated, no collective)",
+              "sharding": "camera views (scene replicated, no collective)" if args.sharding == "views" else
+                          "32-column stripes of every frame, dealt round-robin (scene replicated; the finished "
+                          "stripes are gathered on rank 0 after the render)",
               "l2": "inputs larger than L2 (packed scene 360 MB > 126 MB) and a new view every step"}
 
     # ------------------------------------------------------------------ reference arm (CPU port)
@@ -221,29 +226,44 @@ def main():
     rt = RayTracer((W, H), scene, cam, t_cut=T_CUT)
     out = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
 
+    tiles = args.sharding == "tiles"
+    gather = None
+    if tiles:
+        from rtgs.sharding import StripeGather
+        scene.set_stripe(world, rank)
+        gather = StripeGather(W, H, rank, world, torch.device("cuda", local_rank))
+
     def set_view(step):
-        v = (step * world + rank) % N_VIEWS
+        v = step % N_VIEWS if tiles else (step * world + rank) % N_VIEWS
         cam.position, cam.rotation = views[v]
         return v
+
+    def render_step():
+        rt.render_device(DEPTH, out=out)
+        if tiles and dist is not None:
+            gather(out, dist)
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views
+    # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views (whole frames)
+    scene.set_stripe()
     agg = {}
     for s in range(min(args.steps, N_VIEWS)):
         set_view(s)
         rt.render_device(DEPTH, out=out, collect_stats=True)
         for k, v in rt.last_stats.items():
             agg[k] = agg.get(k, 0) + v
+    if tiles:
+        scene.set_stripe(world, rank)
     kbar = agg["layers"] / agg["rays"]
     bytes_ray = 16 + kbar * (64 + (192 if sh_deg > 0 else 0))
 
     for s in range(args.warmup):
         set_view(s)
-        rt.render_device(DEPTH, out=out)
+        render_step()
     barrier()
     timed_frames = min(args.steps, 4096)
     scene.set_option("kernel_timing", timed_frames)   # events around every kernel of the timed steps
@@ -258,7 +278,7 @@ def main():
     for s in range(args.steps):
         set_view(s)
         ev[s][0].record()
-        rt.render_device(DEPTH, out=out)
+        render_step()
         ev[s][1].record()
         launches += 3     # k_tile_lists, k_shade_tiles, k_render (fallback list; returns at once when empty)
     e_end.record()
@@ -270,14 +290,25 @@ def main():
     scene.set_option("kernel_timing", 0)
 
     # end-to-end: public API call with host buffers (camera in, image out on the host)
+    if tiles:
+        host = torch.empty((W, H, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+
+        def e2e_step():
+            render_step()
+            if rank == 0:
+                host.copy_(out, non_blocking=True)
+                torch.cuda.synchronize()
+    else:
+        def e2e_step():
+            return rt.render(DEPTH)
     for s in range(min(args.warmup, 2)):
         set_view(s)
-        rt.render(DEPTH)
+        e2e_step()
     barrier()
     t0 = time.perf_counter()
     for s in range(args.steps):
         set_view(s)
-        img = rt.render(DEPTH)
+        e2e_step()
     barrier()
     e2e_s = time.perf_counter() - t0
 
@@ -291,23 +322,26 @@ def main():
         kern_mean = float(np.mean(kern_ms))
 
     if rank == 0:
-        rays_step = W * H * world
+        rays_step = W * H * (1 if tiles else world)
         value = rays_step * args.steps / (total_ms * 1e-3) / 1e6
         e2e_val = rays_step * args.steps / e2e_s / 1e6
         peak, peak_src = load_peak()
         from rtgs._native import KERNEL_NAMES
         dom = int(np.argmax(per_kernel))
         dom_ms = float(per_kernel[dom])
-        achieved = W * H * bytes_ray / (dom_ms * 1e-3) / 1e9
+        rays_launch = W * H / (world if tiles else 1)      # rays one launch of the kernel processes
+        achieved = rays_launch * bytes_ray / (dom_ms * 1e-3) / 1e9
         step_ms = float(per_kernel.sum())
         kernels = [{"kernel": KERNEL_NAMES[k], "ms": float(per_kernel[k]), "share": float(per_kernel[k] / step_ms)}
                    for k in range(len(KERNEL_NAMES))]
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+            "scaling": "strong" if tiles else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 44,
-                    "d2h_bytes_per_step": W * H * 3 * 4, "ms_per_step": 1e3 * e2e_s / args.steps},
+            "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 44 * world,
+                    "d2h_bytes_per_step": W * H * 3 * 4 * (1 if tiles else world),
+                    "ms_per_step": 1e3 * e2e_s / args.steps},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(KERNEL_NAMES[dom]), "peak_source": peak_src,

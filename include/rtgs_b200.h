@@ -135,11 +135,16 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
  *                            -1 (default) = 16 chunks per 4x8-pixel tile of the rendered region.  A small pool is
  *                            legal (it only moves tiles to the fused kernel) and is what the tests use to
  *                            exercise that path.
- *  RTGS_OPT_KERNEL_TIMING    see rtgs_scene_read_kernel_times. */
+ *  RTGS_OPT_KERNEL_TIMING    see rtgs_scene_read_kernel_times.
+ *  RTGS_OPT_STRIPE           value = (mod << 32) | rem: following renders touch only the 32-pixel-wide column
+ *                            stripes mi = (i - x0) / 32 with mi % mod == rem and leave every other pixel of the
+ *                            output untouched (tile sharding of one frame over `mod` GPUs; a
+ *                            stripe is 32*H*3 contiguous floats of the (W,H,3) image).  (1 << 32) = all (default). */
 typedef enum rtgs_option {
     RTGS_OPT_RENDER_MODE = 0,
     RTGS_OPT_LIST_POOL_CHUNKS = 1,
-    RTGS_OPT_KERNEL_TIMING = 2
+    RTGS_OPT_KERNEL_TIMING = 2,
+    RTGS_OPT_STRIPE = 3
 } rtgs_option;
 int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value);
 

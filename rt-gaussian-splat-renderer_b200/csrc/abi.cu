@@ -324,6 +324,13 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             s->pool_chunks = 0;
             return RTGS_OK;
         }
+        case RTGS_OPT_STRIPE: {
+            const int64_t mod = value >> 32, rem = value & 0xffffffffll;
+            RTGS_CHECK_ARG(mod >= 1 && mod <= 1024 && rem >= 0 && rem < mod);
+            s->opt_stripe_mod = (int)mod;
+            s->opt_stripe_rem = (int)rem;
+            return RTGS_OK;
+        }
         case RTGS_OPT_KERNEL_TIMING: {
             RTGS_CHECK_ARG(value >= 0 && value <= 4096);
             DeviceGuard g(s->device);

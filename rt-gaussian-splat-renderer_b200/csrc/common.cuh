@@ -88,6 +88,7 @@ struct rtgs_scene {
     int list_tiles = 0;
     int pool_chunks = 0;
     int64_t opt_pool_chunks = -1;             // RTGS_OPT_LIST_POOL_CHUNKS (-1 = default sizing)
+    int opt_stripe_mod = 1, opt_stripe_rem = 0;   // RTGS_OPT_STRIPE
     int opt_render_mode = -1;                 // RTGS_OPT_RENDER_MODE (-1 = RTGS_RENDER_MODE env or 0)
     float* stage_rgb = nullptr;               // device staging for rtgs_render_host
     float* stage_T = nullptr;

@@ -95,8 +95,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
         int i0, j0;
-        tile_origin(P, tile, i0, j0);
-        if (i0 >= xe || j0 >= ye) continue;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) continue;
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
         const bool active = pi < xe && pj < ye;
 
@@ -530,6 +529,8 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     const int mrows = (w + MACRO_PX_I - 1) / MACRO_PX_I;
     const int mcols = (h + MACRO_PX_J - 1) / MACRO_PX_J;
     P.macro_cols = mcols;
+    P.stripe_mod = s->opt_stripe_mod;
+    P.stripe_rem = s->opt_stripe_rem;
     P.ntiles = mrows * mcols * TILES_PER_MACRO;
     P.depth = depth;
     P.t_cut = t_cut;

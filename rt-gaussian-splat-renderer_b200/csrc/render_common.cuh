@@ -43,6 +43,7 @@ struct RenderParams {
     CamD cam;
     int x0, y0, w, h;
     int macro_cols;  // macro tiles along j
+    int stripe_mod, stripe_rem;   // render only macro-tile columns mi with mi % stripe_mod == stripe_rem (multi-GPU)
     int ntiles;      // macro_rows * macro_cols * TILES_PER_MACRO (tile ids, some outside the region)
     int depth;
     float t_cut;
@@ -73,18 +74,21 @@ __device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
 
 // tile id -> pixel origin.  id = (macro * GROUPS_PER_MACRO + group) * TILES_PER_GROUP + sub, so that the
 // four tiles of a traversal group are consecutive and consecutive groups share a 32x32-pixel macro tile.
-__device__ __forceinline__ void group_origin(const RenderParams& P, int group, int& gi0, int& gj0) {
+// Returns false for a group outside this launch's stripe (its macro-tile column belongs to another GPU).
+__device__ __forceinline__ bool group_origin(const RenderParams& P, int group, int& gi0, int& gj0) {
     const int macro = group / GROUPS_PER_MACRO, lg = group % GROUPS_PER_MACRO;
     const int mi = macro / P.macro_cols, mj = macro % P.macro_cols;
     gi0 = P.x0 + (mi * MACRO_GI + lg / MACRO_GJ) * GPX_I;
     gj0 = P.y0 + (mj * MACRO_GJ + lg % MACRO_GJ) * GPX_J;
+    return P.stripe_mod <= 1 || mi % P.stripe_mod == P.stripe_rem;
 }
-__device__ __forceinline__ void tile_origin(const RenderParams& P, int tile, int& i0, int& j0) {
+__device__ __forceinline__ bool tile_origin(const RenderParams& P, int tile, int& i0, int& j0) {
     int gi0, gj0;
-    group_origin(P, tile / TILES_PER_GROUP, gi0, gj0);
+    const bool mine = group_origin(P, tile / TILES_PER_GROUP, gi0, gj0);
     const int sub = tile % TILES_PER_GROUP;
     i0 = gi0 + (sub / GROUP_TJ) * TILE_I;
     j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
+    return mine;
 }
 
 // ---- frustum of a pixel rectangle: 4 planes through the camera origin o, inward normals n[k]; a box

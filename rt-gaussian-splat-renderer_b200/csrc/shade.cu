@@ -91,8 +91,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __g
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
         int i0, j0;
-        tile_origin(P, tile, i0, j0);
-        if (i0 >= xe || j0 >= ye) continue;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) continue;
         const TileDesc desc = P.desc[tile];
         if (desc.count < 0) continue;   // list did not fit the pool: the fused kernel renders this tile
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;

@@ -120,8 +120,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
         group = __shfl_sync(FULL, group, 0);
         if (group * TILES_PER_GROUP >= P.ntiles) break;
         int gi0, gj0;
-        group_origin(P, group, gi0, gj0);
-        if (gi0 >= xe || gj0 >= ye) continue;
+        if (!group_origin(P, group, gi0, gj0) || gi0 >= xe || gj0 >= ye) continue;
 
         // ---- group traversal: the LBVH once for the 8x16-pixel frustum ---------------------------
         int ng = 0;

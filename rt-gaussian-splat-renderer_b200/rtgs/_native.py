@@ -63,7 +63,7 @@ SIGNATURES = {
     "rtgs_scene_destroy": (C.c_int, [_vp]),
 }
 
-OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING = 0, 1, 2
+OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING, OPT_STRIPE = 0, 1, 2, 3
 KERNEL_NAMES = ("k_tile_lists", "k_shade_tiles", "k_render")
 
 _lib = None

@@ -185,9 +185,14 @@ class Scene:
         """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 0 = tile lists + shading kernels (default),
         1 = the fused kernel alone; ``list_pool_chunks`` = capacity of the candidate-list pool (-1 = default)."""
         opt = {"render_mode": _native.OPT_RENDER_MODE, "list_pool_chunks": _native.OPT_LIST_POOL_CHUNKS,
-               "kernel_timing": _native.OPT_KERNEL_TIMING}[name]
+               "kernel_timing": _native.OPT_KERNEL_TIMING, "stripe": _native.OPT_STRIPE}[name]
         _native.check(_native.load().rtgs_scene_set_option(self.handle, opt, int(value)))
         return self
+
+    def set_stripe(self, world: int = 1, rank: int = 0) -> "Scene":
+        """Tile sharding of one frame: following renders touch only the 32-column stripes k with k % world == rank
+        (rtgs.sharding.STRIPE_COLUMNS); ``set_stripe()`` restores full frames."""
+        return self.set_option("stripe", (int(world) << 32) | int(rank))
 
     def read_kernel_times(self, frames: int):
         """(frames, 3) float32 milliseconds of k_tile_lists, k_shade_tiles, k_render for the last `frames` renders

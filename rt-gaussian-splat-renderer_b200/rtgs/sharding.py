@@ -6,6 +6,7 @@ from __future__ import annotations
 import numpy as np
 
 TILE_COLUMNS = 32   # tile = 32 pixel columns x full height: contiguous in the (W,H,3) i-major image
+STRIPE_COLUMNS = TILE_COLUMNS   # = the kernels' macro-tile width (RTGS_OPT_STRIPE)
 
 
 def views_for_rank(n_views: int, rank: int, world: int) -> list[int]:
@@ -30,3 +31,35 @@ def assemble_tiles(W: int, H: int, world: int, payloads) -> np.ndarray:
             frame[x0:x0 + w, y0:y0 + h] = np.asarray(buf[off:off + n]).reshape(w, h, 3)
             off += n
     return frame
+
+
+def stripe_columns(W: int, rank: int, world: int):
+    """Pixel columns of the stripes owned by `rank` (what ``Scene.set_stripe(world, rank)`` renders)."""
+    return np.concatenate([np.arange(x0, x0 + w) for (x0, _, w, _) in tiles_for_rank(W, 1, rank, world)] or
+                          [np.zeros(0, np.int64)]).astype(np.int64)
+
+
+class StripeGather:
+    """Gathers a tile-sharded frame on rank 0 with one collective (torch.distributed gather of the packed
+    stripes; NCCL on GPUs, gloo in the CPU tests).  Only finished pixels move - nothing on the render path."""
+
+    def __init__(self, W: int, H: int, rank: int, world: int, device):
+        import torch
+        self.W, self.H, self.rank, self.world = W, H, rank, world
+        self.cols = [torch.from_numpy(stripe_columns(W, r, world)).to(device) for r in range(world)]
+        self.max_cols = max(int(c.numel()) for c in self.cols)
+        self.send = torch.zeros((self.max_cols, H, 3), dtype=torch.float32, device=device)
+        self.recv = [torch.zeros_like(self.send) for _ in range(world)] if rank == 0 else None
+
+    def __call__(self, frame, dist):
+        """frame: (W,H,3) tensor holding this rank's stripes; on rank 0 the other ranks' stripes are filled in."""
+        import torch
+        mine = self.cols[self.rank]
+        if self.world == 1:
+            return frame
+        torch.index_select(frame, 0, mine, out=self.send[:mine.numel()])
+        dist.gather(self.send, self.recv, dst=0)
+        if self.rank == 0:
+            for r in range(1, self.world):
+                frame.index_copy_(0, self.cols[r], self.recv[r][:self.cols[r].numel()])
+        return frame

@@ -31,7 +31,7 @@ def _setup(name, view=0):
 
 
 @pytest.mark.parametrize("name,stride,view", [("100k_deg0_1080p", 12, 0), ("1m_deg3_1080p", 16, 0),
-                                               ("1m_deg3_1080p", 24, 37)])
+                                               ("1m_deg3_1080p", 24, 37), ("3m_deg3_2160p", 48, 5)])
 def test_full_size_frame_matches_float64_oracle(name, stride, view):
     rt, cs, ocam, (W, H) = _setup(name, view)
     img = rt.render(16).copy()

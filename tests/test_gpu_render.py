@@ -107,6 +107,35 @@ def test_tile_sharding_is_bit_identical():
     assert np.array_equal(again, full), "render is not deterministic"
 
 
+def test_stripe_sharding_is_bit_identical():
+    """One frame rendered as the 32-column stripes of 3 ranks (Scene.set_stripe, the --sharding tiles partition)
+    into one buffer equals the single launch bit for bit; a stripe launch leaves foreign pixels untouched."""
+    import torch
+    from rtgs.ray_tracer import RayTracer
+    from rtgs.sharding import stripe_columns
+    gs = random_set(4000, seed=12, mean_scale=0.03)
+    scene = make_scene(gs)
+    cam, _ = make_camera(0.9, 1.2, 2.4, 200, 72)
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    full = rt.render_device(16).clone()
+    buf = torch.full_like(full, -7.0)
+    for depth in (16, 20):                       # tile lists + shading kernels, and the fused kernel (depth > 16)
+        ref = rt.render_device(depth).clone()
+        buf.fill_(-7.0)
+        for r in range(3):
+            scene.set_stripe(3, r)
+            rt.render_device(depth, out=buf)
+            cols = torch.from_numpy(stripe_columns(200, r, 3)).cuda()
+            done = torch.cat([torch.from_numpy(stripe_columns(200, q, 3)) for q in range(r + 1)]).cuda()
+            assert torch.equal(buf[cols], ref[cols])
+            mask = torch.ones(200, dtype=torch.bool, device="cuda")
+            mask[done] = False
+            assert (buf[mask] == -7.0).all()
+        scene.set_stripe()
+        assert torch.equal(buf, ref)
+    assert torch.equal(rt.render_device(16), full)
+
+
 def test_render_paths_agree_and_pool_overflow_falls_back():
     """The same frame through (a) tile lists + shading kernels, (b) the fused kernel alone, (c) a list pool that
     is far too small, so that most tiles take the fused kernel through the fallback list: all within tolerance
