@@ -31,6 +31,13 @@ using namespace rtgs_dev;
 
 namespace {
 
+#ifndef K2_WARPS
+#define K2_WARPS 10
+#endif
+#ifndef K2_CTAS
+#define K2_CTAS 2
+#endif
+constexpr int SHADE_WARPS = K2_WARPS;   // warps per CTA
 constexpr int K = 16;          // k-buffer entries (depth <= 16)
 constexpr int BATCH = 32;      // staged candidates per batch (a chunk fills 31)
 constexpr int REC_Q = 5;       // quads per staged record (80-byte stride: conflict-free gathers)
@@ -43,7 +50,7 @@ struct __align__(16) WarpShared {
     int kb_i[K][32];
     float kb_a[K][32];
 };
-static_assert(sizeof(WarpShared) == 9472, "shared-memory budget of 24 warps per SM");
+static_assert(sizeof(WarpShared) * K2_WARPS * K2_CTAS <= 227 * 1024, "shared-memory budget per SM");
 
 // Bitonic sorting network over the first N (8 or 16) of 16 register-resident keys, ascending.
 template <int N>
@@ -74,7 +81,7 @@ __device__ __forceinline__ bool keys_near(unsigned ka, unsigned kb) {
 }
 
 template <bool STATS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __grid_constant__ RenderParams P) {
+__global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const __grid_constant__ RenderParams P) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpShared& ws = reinterpret_cast<WarpShared*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
@@ -301,13 +308,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, 3) k_shade_tiles(const __g
 template <bool STATS>
 int launch(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     static int blocks_per_sm[16] = {0};
-    const size_t smem = sizeof(WarpShared) * WARPS_PER_CTA;
+    const size_t smem = sizeof(WarpShared) * SHADE_WARPS;
     int dev = s->device;
     if (dev < 0 || dev >= 16) dev = 0;
     if (blocks_per_sm[dev] == 0) {
         CUDA_TRY(cudaFuncSetAttribute(k_shade_tiles<STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade_tiles<STATS>, WARPS_PER_CTA * 32, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_shade_tiles<STATS>, SHADE_WARPS * 32, smem));
         if (nb < 1) {
             rtgs_set_error("k_shade_tiles does not fit on an SM (smem %zu)", smem);
             return RTGS_ERR_CUDA;
@@ -315,10 +322,10 @@ int launch(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
         blocks_per_sm[dev] = nb;
     }
     int grid = s->sm_count * blocks_per_sm[dev];
-    const int need = (P.ntiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int need = (P.ntiles + SHADE_WARPS - 1) / SHADE_WARPS;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
-    k_shade_tiles<STATS><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+    k_shade_tiles<STATS><<<grid, SHADE_WARPS * 32, smem, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
     return RTGS_OK;
 }
