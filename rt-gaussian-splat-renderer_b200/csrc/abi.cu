@@ -2,10 +2,11 @@
 #include <stdarg.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include <new>
 
-#include "common.cuh"
+#include "render_common.cuh"
 
 static thread_local char g_err[512] = "";
 
@@ -53,6 +54,10 @@ void free_scene(rtgs_scene* s) {
     if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
     if (s->pinned_T) cudaFreeHost(s->pinned_T);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
+    if (s->copy_stream2) cudaStreamDestroy(s->copy_stream2);
+    cudaFree(s->band_done);
+    if (s->band_flags) cudaFreeHost(s->band_flags);
     for (cudaEvent_t e : s->timing_events) cudaEventDestroy(e);
     delete s;
 }
@@ -78,6 +83,11 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream2, cudaStreamNonBlocking));
+    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, RTGS_MAX_BANDS * sizeof(int), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostGetDevicePointer((void**)&s->band_flags_dev, s->band_flags, 0));
+    TRY(dev_alloc(&s->band_done, RTGS_MAX_BANDS));
     TRY(dev_alloc(&s->pos, n * 3));
     TRY(dev_alloc(&s->rot, n * 4));
     TRY(dev_alloc(&s->scale, n * 3));
@@ -386,14 +396,17 @@ int rtgs_host_free(void* p) {
     return RTGS_OK;
 }
 
-// How rtgs_render_host delivers the image: 0 = render to device memory, then one DMA (+ a host
-// memcpy for pageable destinations); 1 = the kernel stores straight into pinned host memory
-// (zero-copy; the PCIe writes overlap the rendering).  RTGS_HOST_MODE overrides the default.
+// How rtgs_render_host delivers the image to a pinned destination:
+//   0 = render to device memory, then one DMA;
+//   1 = the kernel stores straight into the mapped host buffer (zero-copy; 32..96-byte PCIe writes);
+//   2 = (default) render to device memory in bands of 32-pixel columns; the kernels raise a host-visible flag
+//       per finished band and this thread queues the band's DMA while the later bands are still rendering.
+// RTGS_HOST_MODE overrides the default.
 static int host_mode() {
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("RTGS_HOST_MODE");
-        mode = e ? atoi(e) : 1;
+        mode = e ? atoi(e) : 2;
     }
     return mode;
 }
@@ -430,6 +443,67 @@ int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t 
         // zero-copy: the render kernel writes the framebuffer into mapped host memory
         TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, d_rgb, d_T, st, false));
         CUDA_TRY(cudaStreamSynchronize(st));
+        return RTGS_OK;
+    }
+    if (pinned && host_mode() == 2) {
+        // banded: region columns are contiguous in the (w,h,3) i-major buffer, so a band of macro-tile columns is
+        // one contiguous block; its DMA starts as soon as the kernels flag it complete
+        TRY(ensure_stage(s, px));
+        const int mrows = (w + 31) / 32;                       // 32-pixel macro-tile columns of the region
+        const int bmc = (mrows + 23) / 24 > 0 ? (mrows + 23) / 24 : 1;
+        const int nb = (mrows + bmc - 1) / bmc;                // <= 24 bands (RTGS_MAX_BANDS 32)
+        for (int b = 0; b < nb; ++b) s->band_flags[b] = 0;
+        s->bands_active = nb;
+        s->band_macro_cols = bmc;
+        static const int sched = getenv("RTGS_BAND_SCHEDULE") ? atoi(getenv("RTGS_BAND_SCHEDULE")) : 2;
+        s->band_schedule = sched;
+        const int r = rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, s->stage_rgb,
+                                         host_T ? s->stage_T : nullptr, st, false);
+        s->bands_active = 0;
+        if (r != RTGS_OK) return r;
+        volatile int* flags = s->band_flags;
+        static const bool dbg = getenv("RTGS_DEBUG_BANDS") != nullptr;
+        static int dbg_frame = 0;
+        struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+        auto now_us = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - ts0.tv_sec) * 1e6 + (t.tv_nsec - ts0.tv_nsec) * 1e-3; };
+        double tflag[RTGS_MAX_BANDS];
+        int qi = 0;
+        for (int b = 0; b < nb; ++b) {
+            long spins = 0;
+            while (flags[b] == 0) {
+                if ((++spins & 0xfff) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;   // done or failed
+            }
+            tflag[b] = now_us();
+            // the band's schedule positions -> macro-tile columns (edges inwards, render_common.cuh): at most two
+            // contiguous runs of columns
+            const int p0 = b * bmc, p1 = (b + 1) * bmc < mrows ? (b + 1) * bmc : mrows;
+            int lo[2] = {mrows, mrows}, hi[2] = {-1, -1};      // two runs: columns left / right of the middle
+            for (int p = p0; p < p1; ++p) {
+                const int col = rtgs_dev::macro_column(mrows, p, sched), k = col * 2 >= mrows ? 1 : 0;
+                lo[k] = col < lo[k] ? col : lo[k];
+                hi[k] = col > hi[k] ? col : hi[k];
+            }
+            for (int k = 0; k < 2; ++k) {
+                if (hi[k] < 0) continue;
+                const size_t c0 = (size_t)lo[k] * 32, c1 = (size_t)(hi[k] + 1) * 32 < (size_t)w ? (size_t)(hi[k] + 1) * 32 : (size_t)w;
+                cudaStream_t cs = (qi++ & 1) ? s->copy_stream2 : s->copy_stream;
+                CUDA_TRY(cudaMemcpyAsync(host_rgb + c0 * h * 3, s->stage_rgb + c0 * h * 3,
+                                         (c1 - c0) * h * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+                if (host_T)
+                    CUDA_TRY(cudaMemcpyAsync(host_T + c0 * h, s->stage_T + c0 * h, (c1 - c0) * h * sizeof(float),
+                                             cudaMemcpyDeviceToHost, cs));
+            }
+        }
+        const double t_enq = now_us();
+        CUDA_TRY(cudaStreamSynchronize(st));
+        const double t_k = now_us();
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+        CUDA_TRY(cudaStreamSynchronize(s->copy_stream2));
+        if (dbg && ++dbg_frame == 20) {
+            fprintf(stderr, "bands %d: enq_done %.0f kernels_done %.0f copies_done %.0f us; flags:", nb, t_enq, t_k, now_us());
+            for (int b = 0; b < nb; ++b) fprintf(stderr, " %.0f", tflag[b]);
+            fprintf(stderr, "\n");
+        }
         return RTGS_OK;
     }
     TRY(ensure_stage(s, px));

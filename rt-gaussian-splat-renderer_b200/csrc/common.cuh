@@ -9,6 +9,7 @@
 #include "../../include/rtgs_b200.h"
 
 #define RTGS_SM_COUNT_FALLBACK 148
+#define RTGS_MAX_BANDS 32
 
 // ---- error plumbing (never abort across the ABI) ---------------------------------------------
 void rtgs_set_error(const char* fmt, ...);
@@ -97,6 +98,14 @@ struct rtgs_scene {
     float* pinned_T = nullptr;
     size_t pinned_pixels = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;       // framebuffer DMA of rtgs_render_host, overlapping the render
+    cudaStream_t copy_stream2 = nullptr;      // second DMA queue (bands alternate, hiding the per-copy set-up)
+    unsigned int* band_done = nullptr;        // device: finished tile ids per band
+    int* band_flags = nullptr;                // mapped pinned host memory: band complete
+    int* band_flags_dev = nullptr;            // device alias of band_flags
+    int bands_active = 0;                     // set by rtgs_render_host around its launch
+    int band_macro_cols = 0;
+    int band_schedule = 0;                    // macro-column order of the banded launch (render_common.cuh)
 
     // per-kernel timing ring (RTGS_OPT_KERNEL_TIMING): 4 events per frame slot
     std::vector<cudaEvent_t> timing_events;

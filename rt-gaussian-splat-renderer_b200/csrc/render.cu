@@ -95,7 +95,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
         int i0, j0;
-        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) continue;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
+            tile_done(P, tile, lane);
+            continue;
+        }
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
         const bool active = pi < xe && pj < ye;
 
@@ -291,6 +294,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             }
         }
         store_tile(P, reinterpret_cast<float*>(&ws.kb_t[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
+        tile_done(P, tile, lane);
         if (active) {
             ST(st_rays += 1);
             ST(st_hit += nl > 0);
@@ -546,6 +550,17 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.pool_chunks = 0;
     P.fallback_tiles = nullptr;
     P.use_fallback_list = 0;
+    P.nbands = 0;
+    P.band_macro_cols = 1;
+    P.macro_rows = mrows;
+    P.schedule = s->bands_active > 0 ? s->band_schedule : 0;
+    P.band_done = s->band_done;
+    P.band_flags = s->band_flags_dev;
+    if (s->bands_active > 0) {
+        P.nbands = s->bands_active;
+        P.band_macro_cols = s->band_macro_cols;
+        CUDA_TRY(cudaMemsetAsync(s->band_done, 0, RTGS_MAX_BANDS * sizeof(unsigned int), stream));
+    }
     CUDA_TRY(cudaMemsetAsync(s->counters, 0, CTR_COUNT * sizeof(unsigned int), stream));
     if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), stream));
 

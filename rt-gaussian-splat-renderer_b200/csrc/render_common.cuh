@@ -58,11 +58,33 @@ struct RenderParams {
     int pool_chunks;
     int* fallback_tiles;      // ntiles
     int use_fallback_list;    // k_render: take tile ids from fallback_tiles[0 .. counters[2])
+    // band completion (host-pipelined framebuffer copy, rtgs_render_host): the frame is cut into nbands bands of
+    // band_macro_cols 32-pixel columns; a band is finished when all its tile ids have been rendered or skipped
+    int nbands, band_macro_cols, macro_rows, schedule;
+    unsigned int* band_done;  // device counters, one per band
+    int* band_flags;          // mapped pinned host memory: set to 1 by the warp that finishes the band
 };
 
 enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_COUNT = 8 };
 enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
        ST_FALLBACK, ST_COUNT = 12 };
+
+// A tile id has been rendered (its framebuffer stores are issued) or skipped: count it for its band and, when
+// the band is complete, raise the host-visible flag.  Call with the whole warp converged, after store_tile.
+__device__ __forceinline__ void tile_done(const RenderParams& P, int tile, int lane) {
+    if (P.nbands == 0) return;
+    if (lane == 0) {
+        const int mi = tile / TILES_PER_MACRO / P.macro_cols;
+        const int band = mi / P.band_macro_cols;
+        const int cols = min(P.macro_rows, (band + 1) * P.band_macro_cols) - band * P.band_macro_cols;
+        const unsigned total = (unsigned)(cols * P.macro_cols * TILES_PER_MACRO);
+        __threadfence();   // cumulative: the warp's framebuffer stores (ordered before by __syncwarp) first
+        if (atomicAdd(P.band_done + band, 1u) + 1u == total) {
+            __threadfence_system();
+            *reinterpret_cast<volatile int*>(P.band_flags + band) = 1;
+        }
+    }
+}
 
 // 256-bit read-only global load (sm_100 LDG.E.256): the L1 data pipe is charged per 128-byte line and
 // instruction, so a gather of 32-byte pieces costs half of what two 16-byte gathers do.  p is 32-byte aligned.
@@ -74,10 +96,27 @@ __device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {
 
 // tile id -> pixel origin.  id = (macro * GROUPS_PER_MACRO + group) * TILES_PER_GROUP + sub, so that the
 // four tiles of a traversal group are consecutive and consecutive groups share a 32x32-pixel macro tile.
+// Order in which the macro-tile columns are scheduled (position -> column).  0: left to right (device renders:
+// best locality and a cheap tail).  The banded framebuffer copy of rtgs_render_host wants bands to finish no
+// faster than the DMA drains them at the END of the frame, so that nothing piles up behind the render:
+// 1: from the image edges inwards (0, last, 1, last-1 ...; for a centred scene cheap columns first, expensive
+// last); 2: rotated, the rightmost fifth first, then left to right.
+__host__ __device__ __forceinline__ int macro_column(int macro_rows, int pos, int schedule) {
+    if (schedule == 1) return (pos & 1) ? macro_rows - 1 - (pos >> 1) : (pos >> 1);
+    if (schedule == 2) {
+        const int head = macro_rows / 5;
+        return pos < head ? macro_rows - head + pos : pos - head;
+    }
+    return pos;
+}
+__device__ __forceinline__ int macro_column(const RenderParams& P, int pos) {
+    return macro_column(P.macro_rows, pos, P.schedule);
+}
+
 // Returns false for a group outside this launch's stripe (its macro-tile column belongs to another GPU).
 __device__ __forceinline__ bool group_origin(const RenderParams& P, int group, int& gi0, int& gj0) {
     const int macro = group / GROUPS_PER_MACRO, lg = group % GROUPS_PER_MACRO;
-    const int mi = macro / P.macro_cols, mj = macro % P.macro_cols;
+    const int mi = macro_column(P, macro / P.macro_cols), mj = macro % P.macro_cols;
     gi0 = P.x0 + (mi * MACRO_GI + lg / MACRO_GJ) * GPX_I;
     gj0 = P.y0 + (mj * MACRO_GJ + lg % MACRO_GJ) * GPX_J;
     return P.stripe_mod <= 1 || mi % P.stripe_mod == P.stripe_rem;

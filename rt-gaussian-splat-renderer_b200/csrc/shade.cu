@@ -98,7 +98,10 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
         int i0, j0;
-        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) continue;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
+            tile_done(P, tile, lane);
+            continue;
+        }
         const TileDesc desc = P.desc[tile];
         if (desc.count < 0) continue;   // list did not fit the pool: the fused kernel renders this tile
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
@@ -277,6 +280,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
             }
         }
         store_tile(P, reinterpret_cast<float*>(&ws.rec[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
+        tile_done(P, tile, lane);
         if (active) {
             ST(st_rays += 1);
             ST(st_hit += nl > 0);
