@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--sharding", default="views", choices=["views", "tiles"],
                     help="multi-GPU partition: camera views (weak scaling, default) or 32-column stripes of every "
                          "frame gathered on rank 0 (strong scaling)")
+    ap.add_argument("--h-target", type=float, default=None,
+                    help="diagnostic: expected ellipsoid crossings per cube-spanning ray of the synthetic scene "
+                         "(default 16, SURVEY.md 8d); larger = bigger Gaussians, denser tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-stride", type=int, default=0, help="pixel subsample stride of the CPU legs (0 = auto)")
     return ap.parse_args()
@@ -215,7 +218,9 @@ def main():
     from rtgs.ray_tracer import RayTracer
     from rtgs.scene import Scene
 
-    arrays = make_scene(n_g, seed, sh_deg)
+    arrays = make_scene(n_g, seed, sh_deg) if args.h_target is None else make_scene(n_g, seed, sh_deg, args.h_target)
+    if args.h_target is not None:
+        config["workload"] += f" [diagnostic: h_target {args.h_target}]"
     focal, views = make_views(W, H)
     t0 = time.perf_counter()
     scene = Scene(device=local_rank).from_arrays(arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"],

@@ -132,7 +132,8 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
  *                            candidate list did not fit the pool; 1: the fused kernel alone.  depth > 16 always
  *                            uses the fused kernel.
  *  RTGS_OPT_LIST_POOL_CHUNKS capacity of the candidate-list pool in 128-byte chunks (31 candidates each);
- *                            -1 (default) = 16 chunks per 4x8-pixel tile of the rendered region.  A small pool is
+ *                            -1 (default) = 16 chunks per 4x8-pixel tile of the rendered region, doubled whenever a
+ *                            finished frame used more than 70 % of it.  A small pool is
  *                            legal (it only moves tiles to the fused kernel) and is what the tests use to
  *                            exercise that path.
  *  RTGS_OPT_KERNEL_TIMING    see rtgs_scene_read_kernel_times.

@@ -80,6 +80,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     // work items: every tile id, or (fallback mode) the tiles k_tile_lists could not store a list for
     const int nwork = P.use_fallback_list ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : P.ntiles;
 
+    if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0)   // pool demand of this frame, for the host's sizing
+        *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
+
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
 #define ST(expr) do { if (STATS) { expr; } } while (0)
@@ -501,19 +504,31 @@ int render_mode(const rtgs_scene* s) {
 }
 
 // Candidate-list scratch of a scene, sized for the tile count of the largest region rendered so far.
-// The pool holds 16 chunks (496 candidates) per tile on average; tiles may take any share of it.
+// The pool starts at 16 chunks (496 candidates) per tile on average - tiles may take any share of it - and
+// doubles whenever the demand reported by the last finished frame (k_tile_lists keeps counting past the end of
+// the pool; the closing k_render launch mirrors the count into mapped host memory) exceeded 70 % of it.  A frame
+// that overflows is still rendered correctly (fallback list), the next one has the larger pool.
 int ensure_lists(rtgs_scene* s, int ntiles) {
-    if (s->list_tiles >= ntiles) return RTGS_OK;
+    int64_t want = s->pool_chunks;
+    if (s->opt_pool_chunks < 0 && s->list_tiles > 0) {
+        const int64_t used = *reinterpret_cast<volatile int*>(s->band_flags + RTGS_MAX_BANDS);
+        while (used * 10 > want * 7 && want < (1ll << 26)) want *= 2;
+    }
+    if (s->list_tiles >= ntiles && want == s->pool_chunks) return RTGS_OK;
+    const bool grow_only = s->list_tiles >= ntiles;
+    const int tiles = grow_only ? s->list_tiles : ntiles;
     cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
     s->tile_desc = nullptr; s->list_pool = nullptr; s->fallback_tiles = nullptr;
     s->list_tiles = 0;
-    int64_t chunks = s->opt_pool_chunks >= 0 ? s->opt_pool_chunks : (int64_t)ntiles * 16;
+    int64_t chunks = s->opt_pool_chunks >= 0 ? s->opt_pool_chunks : (int64_t)tiles * 16;
+    if (grow_only && want > chunks) chunks = want;
     if (chunks > (1ll << 26)) chunks = 1ll << 26;
-    CUDA_TRY(cudaMalloc((void**)&s->tile_desc, (size_t)ntiles * sizeof(TileDesc)));
+    CUDA_TRY(cudaMalloc((void**)&s->tile_desc, (size_t)tiles * sizeof(TileDesc)));
     CUDA_TRY(cudaMalloc((void**)&s->list_pool, (size_t)(chunks > 0 ? chunks : 1) * CHUNK_INTS * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&s->fallback_tiles, (size_t)ntiles * sizeof(int)));
-    s->list_tiles = ntiles;
+    CUDA_TRY(cudaMalloc((void**)&s->fallback_tiles, (size_t)tiles * sizeof(int)));
+    s->list_tiles = tiles;
     s->pool_chunks = (int)chunks;
+    s->band_flags[RTGS_MAX_BANDS] = 0;
     return RTGS_OK;
 }
 

@@ -28,7 +28,7 @@ namespace {
 #endif
 constexpr int STACK_CAP = 256;
 constexpr int STACK_SINGLE = STACK_CAP - 100;   // above this pop one node at a time: growth/step <= 32, then DFS depth <= 62
-constexpr int GLIST_CAP = 512;
+constexpr int GLIST_CAP = 1024;
 constexpr int CQ_CAP = 128;
 static_assert(GLIST_CAP >= STACK_CAP, "per-tile traversal keeps its stack in the group list");
 
