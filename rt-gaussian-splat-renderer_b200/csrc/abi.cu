@@ -48,7 +48,7 @@ void free_scene(rtgs_scene* s) {
     DeviceGuard g(s->device);
     cudaFree(s->pos); cudaFree(s->rot); cudaFree(s->scale); cudaFree(s->color); cudaFree(s->opacity);
     cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
-    cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox);
+    cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
     cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
     cudaFree(s->counters); cudaFree(s->stats_dev); cudaFree(s->stage_rgb); cudaFree(s->stage_T);
     if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
@@ -105,6 +105,7 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->raw, n * 3));
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->leafbox, n * 2));
+    TRY(dev_alloc(&s->nodes4, s->num_nodes * 8));
     TRY(dev_alloc(&s->counters, 8));
     TRY(dev_alloc(&s->stats_dev, 12));
     return RTGS_OK;

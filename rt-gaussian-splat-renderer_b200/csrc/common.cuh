@@ -78,6 +78,7 @@ struct rtgs_scene {
     float4* raw = nullptr;
     float4* nodes = nullptr;
     float4* leafbox = nullptr;   // n*2: leaf box (centre, half extent) by sorted position
+    float4* nodes4 = nullptr;    // num_nodes*8: two-level nodes (records of both children), k_tile_lists
     int64_t num_nodes = 0;  // max(n-1, 1)
 
     // render scratch

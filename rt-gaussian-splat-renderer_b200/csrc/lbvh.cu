@@ -346,6 +346,36 @@ __global__ void k_pack_leafboxes(int64_t n, const float* __restrict__ aabb, floa
     leafbox[s * 2 + 1] = make_float4(h[1], h[2], 0.0f, 0.0f);
 }
 
+// Two-level nodes for k_tile_lists (128 B per internal node): the record of the LEFT child followed by the
+// record of the RIGHT child, each in the 64-byte layout of `nodes` (two boxes + two references), so that one
+// traversal step descends two levels.  A child that is a leaf becomes {its box, empty box, ~position, none}.
+__global__ void k_pack_nodes4(int64_t n, const float4* __restrict__ nodes, const float4* __restrict__ leafbox,
+                              float4* __restrict__ nodes4) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= (n > 1 ? n - 1 : 1)) return;
+    const float4 d = nodes[i * 4 + 3];
+    const int ref[2] = {__float_as_int(d.x), __float_as_int(d.y)};
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        float4* o = nodes4 + i * 8 + k * 4;
+        if (ref[k] >= 0) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) o[q] = nodes[(int64_t)ref[k] * 4 + q];
+        } else if (k == 1 && n == 1) {   // single Gaussian: the synthetic root has no right child
+            o[0] = make_float4(0.0f, 0.0f, 0.0f, -INFINITY);
+            o[1] = make_float4(-INFINITY, -INFINITY, 0.0f, 0.0f);
+            o[2] = make_float4(0.0f, -INFINITY, -INFINITY, -INFINITY);
+            o[3] = make_float4(__int_as_float(~0), __int_as_float(~0), 0.0f, 0.0f);
+        } else {
+            const float4 a = leafbox[(int64_t)(~ref[k]) * 2 + 0], b = leafbox[(int64_t)(~ref[k]) * 2 + 1];
+            o[0] = a;                                               // c.xyz, h.x
+            o[1] = make_float4(b.x, b.y, 0.0f, 0.0f);               // h.yz, empty second box: centre 0,
+            o[2] = make_float4(0.0f, -INFINITY, -INFINITY, -INFINITY);   // half extent -inf (never inside)
+            o[3] = make_float4(__int_as_float(ref[k]), __int_as_float(~0), 0.0f, 0.0f);
+        }
+    }
+}
+
 __global__ void k_init_bounds(unsigned int* b) {
     if (threadIdx.x < 3) b[threadIdx.x] = 0xFFFFFFFFu;
     else if (threadIdx.x < 6) b[threadIdx.x] = 0u;
@@ -409,6 +439,7 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     }
     k_pack_nodes<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->child, s->aabb, s->nodes);
     k_pack_leafboxes<<<nb, TB, 0, st>>>(n, s->aabb, s->leafbox);
+    k_pack_nodes4<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->nodes, s->leafbox, s->nodes4);
     CUDA_TRY(cudaGetLastError());
     unsigned int hb[6];
     CUDA_TRY(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, st));

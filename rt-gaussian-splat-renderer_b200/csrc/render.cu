@@ -539,6 +539,7 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
                        cudaStream_t stream, bool want_stats) {
     RenderParams P;
     P.nodes = s->nodes;
+    P.nodes4 = s->nodes4;
     P.geo = s->geo;
     P.shp = s->shp;
     P.raw = s->raw;

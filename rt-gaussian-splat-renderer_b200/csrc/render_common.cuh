@@ -36,6 +36,7 @@ struct TileDesc {
 
 struct RenderParams {
     const float4* nodes;
+    const float4* nodes4;     // two-level nodes (k_tile_lists)
     const float4* geo;
     const float4* shp;
     const float4* raw;

@@ -27,7 +27,8 @@ namespace {
 #define K1_CTAS 4
 #endif
 constexpr int STACK_CAP = 256;
-constexpr int STACK_SINGLE = STACK_CAP - 100;   // above this pop one node at a time: growth/step <= 32, then DFS depth <= 62
+constexpr int STACK_SINGLE = STACK_CAP - 144;   // above this pop one node at a time: growth/step <= 48, then <= +3 per
+                                                // level over <= 31 two-level steps (tree depth <= 62)
 constexpr int GLIST_CAP = 1024;
 constexpr int CQ_CAP = 128;
 static_assert(GLIST_CAP >= STACK_CAP, "per-tile traversal keeps its stack in the group list");
@@ -52,26 +53,30 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
 
     int slab_next = 0, slab_end = 0;   // chunks this warp owns in the pool
 
-    // one traversal step: pop <= 32 nodes from `stk`, test both child boxes of each against `fr`,
-    // compact the survivors: internal children back onto `stk`, leaves into `dst`
+    // one traversal step, two tree levels deep: pop <= 16 nodes from `stk`; a PAIR of lanes shares a node, lane
+    // parity picks the record of its left or right child in the two-level node (lbvh.cu: k_pack_nodes4), i.e. each
+    // lane tests two GRANDCHILD boxes against `fr`; survivors are compacted with ballot/popc: internal
+    // grandchildren back onto `stk`, leaves into `dst`.  (The step is bound by the dependent node fetch, so
+    // halving the number of levels is what counts; the extra box tests under a culled child are cheap.)
     auto traverse_step = [&](int* stk, int& top, int* dst, int& nd, const Frustum& fr) {
-        const int take = top > STACK_SINGLE ? 1 : min(32, top);
+        const int take = top > STACK_SINGLE ? 1 : min(16, top);
         int node = -1;
-        if (lane < take) node = stk[top - 1 - lane];
+        if ((lane >> 1) < take) node = stk[top - 1 - (lane >> 1)];
         top -= take;
         __syncwarp();
         bool h0 = false, h1 = false;
         int c0 = 0, c1 = 0;
         if (node >= 0) {
+            const float4* rec = P.nodes4 + (int64_t)node * 8 + (lane & 1) * 4;
             float4 a, b, c, d;
-            ldg256(P.nodes + (int64_t)node * 4 + 0, a, b);
-            ldg256(P.nodes + (int64_t)node * 4 + 2, c, d);
+            ldg256(rec + 0, a, b);
+            ldg256(rec + 2, c, d);
             c0 = __float_as_int(d.x);
             c1 = __float_as_int(d.y);
             h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
             h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
         }
-        ST(st_nodes += 2ull * (unsigned)take);
+        ST(st_nodes += 4ull * (unsigned)take);
         ST(st_steps += 1);
         const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
         const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
