@@ -48,7 +48,8 @@ void rtgs_set_error(const char* fmt, ...);
 //      [k*4 + 2] = { rc.z, rh.x, rh.y, rh.z }
 //      [k*4 + 3] = { left, right (int bits), 0, 0 }   child >= 0: internal node id;
 //                                                      child <  0: leaf, sorted position = ~child
-// leafbox [s*2] = { c.xyz, h.x } { h.yz, 0, 0 }    leaf boxes by sorted position
+// leafbox [s*2] = { p.xyz, h.x } { h.yz, fp16 rho_xy rho_xz, fp16 rho_yz 0 }   leaf records by sorted position:
+//                 exact centre, half extents of the sqrt(3)-sigma ellipsoid, correlations of Sigma
 struct rtgs_scene {
     int device = 0;
     int64_t n = 0;

@@ -9,6 +9,7 @@
 // The split key is the Gaussian centre, as in the reference (scene.py:263-266).
 #include "common.cuh"
 #include "gsmath.cuh"
+#include <cuda_fp16.h>
 
 namespace {
 
@@ -233,7 +234,7 @@ __global__ void k_pack(int64_t n, const uint64_t* __restrict__ keys, const float
                        const float* __restrict__ color, const float* __restrict__ opacity,
                        const float* __restrict__ sh, uint32_t* __restrict__ sorted_idx,
                        float4* __restrict__ geo, float4* __restrict__ shp, float4* __restrict__ raw,
-                       float* __restrict__ aabb) {
+                       float* __restrict__ aabb, float4* __restrict__ leafbox) {
     int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (s >= n) return;
     uint32_t g = (uint32_t)(keys[s] & 0xFFFFFFFFull);
@@ -265,14 +266,33 @@ __global__ void k_pack(int64_t n, const uint64_t* __restrict__ keys, const float
     }
     // tight AABB: h_i = sqrt(3 * Sigma_ii), Sigma_ii = sum_k R_ik^2 s_k^2
     float* bb = aabb + (int64_t)((n - 1) + s) * 6;
+    double var[3];
+    float hf[3];
 #pragma unroll
     for (int a = 0; a < 3; ++a) {
-        double v = Rm[a][0] * Rm[a][0] * sc[0] * sc[0] + Rm[a][1] * Rm[a][1] * sc[1] * sc[1] +
-                   Rm[a][2] * Rm[a][2] * sc[2] * sc[2];
-        double h = sqrt(RTGS_BOUNDING_THRESHOLD * v) * (1.0 + 1e-6);
+        var[a] = Rm[a][0] * Rm[a][0] * sc[0] * sc[0] + Rm[a][1] * Rm[a][1] * sc[1] * sc[1] +
+                 Rm[a][2] * Rm[a][2] * sc[2] * sc[2];
+        double h = sqrt(RTGS_BOUNDING_THRESHOLD * var[a]) * (1.0 + 1e-6);
         bb[a] = __double2float_rd((double)p[a] - h);
         bb[3 + a] = __double2float_ru((double)p[a] + h);
+        hf[a] = __double2float_ru(h);
     }
+    // leaf record of the per-tile filter (k_tile_lists): exact centre, half extents (rounded up) and the
+    // correlations rho_ij = Sigma_ij / sqrt(Sigma_ii Sigma_jj) in fp16, from which the support of the sqrt(3)-sigma
+    // ellipsoid along any plane normal n is  s^2 = (n.h)^T C (n.h)  (render_common.cuh: ellipsoid_in_frustum)
+    auto cov = [&](int a, int b) {
+        return Rm[a][0] * Rm[b][0] * sc[0] * sc[0] + Rm[a][1] * Rm[b][1] * sc[1] * sc[1] +
+               Rm[a][2] * Rm[b][2] * sc[2] * sc[2];
+    };
+    auto rho = [&](int a, int b) {
+        const double d = sqrt(var[a] * var[b]);
+        double r = d > 0.0 ? cov(a, b) / d : 0.0;
+        return (float)fmin(1.0, fmax(-1.0, r));
+    };
+    const __half2 r01 = __floats2half2_rn(2.0f * rho(0, 1), 2.0f * rho(0, 2)), r2 = __floats2half2_rn(2.0f * rho(1, 2), 0.0f);   // stored doubled
+    leafbox[s * 2 + 0] = make_float4(p[0], p[1], p[2], hf[0]);
+    leafbox[s * 2 + 1] = make_float4(hf[1], hf[2], __uint_as_float(*reinterpret_cast<const unsigned*>(&r01)),
+                                     __uint_as_float(*reinterpret_cast<const unsigned*>(&r2)));
 }
 
 // ------------------------------------------------------------------ bottom-up refit
@@ -334,16 +354,6 @@ __global__ void k_pack_nodes(int64_t n, const int32_t* __restrict__ child, const
     nodes[i * 4 + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
     nodes[i * 4 + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
     nodes[i * 4 + 3] = make_float4(__int_as_float(le), __int_as_float(re), 0.0f, 0.0f);
-}
-
-// leaf boxes as (centre, half extent) by sorted position, for the per-tile filter of group candidates
-__global__ void k_pack_leafboxes(int64_t n, const float* __restrict__ aabb, float4* __restrict__ leafbox) {
-    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (s >= n) return;
-    float c[3], h[3];
-    box_ch(aabb + (int64_t)((n - 1) + s) * 6, c, h);
-    leafbox[s * 2 + 0] = make_float4(c[0], c[1], c[2], h[0]);
-    leafbox[s * 2 + 1] = make_float4(h[1], h[2], 0.0f, 0.0f);
 }
 
 // Two-level nodes for k_tile_lists (128 B per internal node): the record of the LEFT child followed by the
@@ -431,14 +441,13 @@ int rtgs_lbvh_build(rtgs_scene* s) {
         CUDA_TRY(cudaMemcpyAsync(s->parent, &m1, sizeof(int32_t), cudaMemcpyHostToDevice, st));
     }
     k_pack<<<(int)((n + 127) / 128), 128, 0, st>>>(n, src, s->pos, s->rot, s->scale, s->color, s->opacity, s->sh,
-                               s->sorted_idx, s->geo, s->shp, s->raw, s->aabb);
+                               s->sorted_idx, s->geo, s->shp, s->raw, s->aabb, s->leafbox);
     CUDA_TRY(cudaGetLastError());
     if (n > 1) {
         CUDA_TRY(cudaMemsetAsync(visit.p, 0, (size_t)(n - 1) * sizeof(unsigned int), st));
         k_refit<<<nb, TB, 0, st>>>(n, s->child, s->parent, s->aabb, visit.p);
     }
     k_pack_nodes<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->child, s->aabb, s->nodes);
-    k_pack_leafboxes<<<nb, TB, 0, st>>>(n, s->aabb, s->leafbox);
     k_pack_nodes4<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->nodes, s->leafbox, s->nodes4);
     CUDA_TRY(cudaGetLastError());
     unsigned int hb[6];

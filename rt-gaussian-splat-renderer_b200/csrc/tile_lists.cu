@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
                         s = ws.glist[idx];
                         float4 a, b;
                         ldg256(P.leafbox + (int64_t)s * 2, a, b);
-                        h = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
+                        h = ellipsoid_in_frustum(fr, a, b);
                     }
                     ST(st_nodes += (unsigned)min(32, ng - gpos));
                     ST(st_steps += 1);
