@@ -107,6 +107,39 @@ def test_tile_sharding_is_bit_identical():
     assert np.array_equal(again, full), "render is not deterministic"
 
 
+def test_extreme_shapes_needles_pancakes_and_screen_filling_gaussians():
+    """Shapes the synthetic generator never makes: 100:1 needles and pancakes at random orientations (their boxes
+    are far larger than their ellipsoids: the exact support test of the tile filter must stay conservative with
+    correlations near +-1), a few Gaussians that cover the whole image, and tiny ones below a pixel."""
+    rng = np.random.default_rng(99)
+    n = 1500
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    scale = np.exp(rng.normal(np.log(0.03), 0.4, (n, 3)))
+    kind = rng.integers(0, 4, n)
+    scale[kind == 0, 1:] *= 0.01            # needles
+    scale[kind == 1, 2] *= 0.01             # pancakes
+    scale[kind == 2] *= 0.02                # sub-pixel
+    scale[:6] = rng.uniform(0.8, 2.0, (6, 3))   # screen filling
+    gs = O.GaussianSet(pos=rng.uniform(-1, 1, (n, 3)), rot=q, scale=scale,
+                       color=1 / (1 + np.exp(-rng.normal(0, 1, (n, 3)))),
+                       opacity=np.clip(1 / (1 + np.exp(-rng.normal(0, 1.5, n))), 0.02, 0.6),
+                       sh=rng.normal(0, 0.15, (n, 15, 3)))
+    scene = make_scene(gs)
+    for (theta, phi, r, fov) in ((0.3, 1.2, 2.6, 60.0), (2.1, 0.7, 0.9, 90.0)):
+        cam, ocam = make_camera(theta, phi, r, 144, 104, fov=fov)
+        img, rt = _render(scene, cam)
+        ref = O.render(gs, ocam, depth=16)
+        mx, ps, bad = compare(img, ref["rgb"], TOL)
+        print(f"extreme shapes r={r}: kbar={np.minimum(ref['nhit'], 16).mean():.2f} maxhits={ref['nhit'].max()} "
+              f"max-abs={mx:.2e} psnr={ps:.1f}")
+        assert mx <= TOL and ps >= 60.0
+        scene.set_option("render_mode", 1)
+        fused, _ = _render(scene, cam)
+        scene.set_option("render_mode", 0)
+        assert np.abs(fused - img).max() <= 1e-5
+
+
 def test_stripe_sharding_is_bit_identical():
     """One frame rendered as the 32-column stripes of 3 ranks (Scene.set_stripe, the --sharding tiles partition)
     into one buffer equals the single launch bit for bit; a stripe launch leaves foreign pixels untouched."""
