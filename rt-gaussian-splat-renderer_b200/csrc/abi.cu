@@ -85,10 +85,11 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (RTGS_MAX_BANDS + 1) * sizeof(int), cudaHostAllocMapped));
+    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (RTGS_MAX_BANDS + 2) * sizeof(int), cudaHostAllocMapped));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&s->band_flags_dev, s->band_flags, 0));
     TRY(dev_alloc(&s->band_done, RTGS_MAX_BANDS));
-    s->band_flags[RTGS_MAX_BANDS] = 0;   // pool demand of the last finished frame (render.cu: ensure_lists)
+    s->band_flags[RTGS_MAX_BANDS] = 0;       // pool demand of the last finished frame (render.cu: ensure_lists)
+    s->band_flags[RTGS_MAX_BANDS + 1] = 0;   // some finished frame had fallback tiles (render.cu: launch_render_k)
     TRY(dev_alloc(&s->pos, n * 3));
     TRY(dev_alloc(&s->rot, n * 4));
     TRY(dev_alloc(&s->scale, n * 3));

@@ -80,8 +80,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     // work items: every tile id, or (fallback mode) the tiles k_tile_lists could not store a list for
     const int nwork = P.use_fallback_list ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : P.ntiles;
 
-    if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0)   // pool demand of this frame, for the host's sizing
+    if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0) {
+        // pool demand of this frame (for the host's sizing) and whether any frame so far needed the fallback
         *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
+        if (P.counters[CTR_FALLBACK] != 0) *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS + 1) = 1;
+    }
 
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
@@ -485,6 +488,15 @@ int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     int grid = s->sm_count * blocks_per_sm[dev];
     const int need = (P.ntiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (grid > need) grid = need;
+    if (P.use_fallback_list) {
+        // The fallback launch is empty unless the list pool overflowed.  While no finished frame has reported
+        // fallback tiles it runs on a quarter of the SMs (a cheaper launch); the first frame that does overflow
+        // is still rendered correctly, just with fewer warps on its fallback tiles.
+        const int seen = *reinterpret_cast<volatile int*>(s->band_flags + RTGS_MAX_BANDS + 1);
+        static const char* e = getenv("RTGS_FB_GRID");
+        const int small = e ? atoi(e) : (s->sm_count + 3) / 4;
+        if (!seen && grid > small) grid = small;
+    }
     if (grid < 1) grid = 1;
     k_render<K, STATS><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
     CUDA_TRY(cudaGetLastError());
