@@ -143,6 +143,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                 unsigned mask = 0;
 #pragma unroll 1
                 for (int c = 0; c < m4; c += 4) {
+                    unsigned nib = 0;
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
                         const float4 pA = ws.polyA[c + u];
@@ -150,8 +151,9 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                         const float ta = fmaf(tr.pa, pA.w, fmaf(tr.pb, pB.x, pA.y));   // c1 + a c3 + b c4
                         const float tb = fmaf(tr.pb, pB.y, pA.z);                      // c2 + b c5
                         const float S = fmaf(tr.pa, ta, fmaf(tr.pb, tb, pA.x));
-                        if (S < 0.0f) mask |= 1u << (c + u);
+                        if (S < 0.0f) nib |= 1u << u;
                     }
+                    mask |= nib << c;
                 }
                 if (!active) mask = 0;
                 ST(st_useful += (unsigned)__popc(__reduce_or_sync(FULL, mask)));
