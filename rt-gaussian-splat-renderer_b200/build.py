@@ -55,7 +55,8 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     for src, obj, r in results:
         log.append(f"==== {src}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:
-            sys.stderr.write("\n".join(log))
+            bad = [l for l in (r.stdout + r.stderr).splitlines() if not l.startswith("ptxas info") and l.strip()]
+            sys.stderr.write(f"==== {src}\n" + "\n".join(bad[-60:]) + "\n")
             raise RuntimeError(f"nvcc failed on {src}")
     (objdir / "ptxas.log").write_text("\n".join(log))
     if verbose:
