@@ -105,6 +105,13 @@ def test_tile_sharding_is_bit_identical():
     assert np.array_equal(parts, full)
     again, _ = _render(scene, cam)
     assert np.array_equal(again, full), "render is not deterministic"
+    # a region at an odd offset tiles the pixels differently (other tile-centre frames): same image to rounding
+    x0, y0, w, h = 13, 7, 50, 33
+    odd = rt.render(16, tile=(x0, y0, w, h))
+    assert np.abs(odd - full[x0:x0 + w, y0:y0 + h]).max() <= 1e-5
+    # ... also with the transmittance buffer and from pageable host memory
+    out = np.empty((w, h, 3), np.float32)
+    assert np.array_equal(rt.render(16, tile=(x0, y0, w, h), out=out), odd)
 
 
 def test_extreme_shapes_needles_pancakes_and_screen_filling_gaussians():
