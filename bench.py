@@ -182,7 +182,7 @@ def main():
               "sharding": "camera views (scene replicated, no collective)" if args.sharding == "views" else
                           "32-column stripes of every frame, dealt round-robin (scene replicated; the finished "
                           "stripes are gathered on rank 0 after the render)",
-              "l2": "inputs larger than L2 (packed scene 360 MB > 126 MB) and a new view every step"}
+              "l2": "inputs larger than L2 (packed scene 528 MB > 126 MB) and a new view every step"}
 
     # ------------------------------------------------------------------ reference arm (CPU port)
     if args.impl == "reference":
