@@ -55,6 +55,9 @@ def parse_args():
     ap.add_argument("--sharding", default="views", choices=["views", "tiles"],
                     help="multi-GPU partition: camera views (weak scaling, default) or 32-column stripes of every "
                          "frame gathered on rank 0 (strong scaling)")
+    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
+                    help="--sharding tiles: every rank stores its stripes straight into rank 0's framebuffer over "
+                         "NVLink (CUDA IPC peer mapping, default) or packs them for one NCCL gather")
     ap.add_argument("--h-target", type=float, default=None,
                     help="diagnostic: expected ellipsoid crossings per cube-spanning ray of the synthetic scene "
                          "(default 16, SURVEY.md 8d); larger = bigger Gaussians, denser tiles")
@@ -234,10 +237,16 @@ def main():
 
     tiles = args.sharding == "tiles"
     gather = None
+    peer = None
     if tiles:
-        from rtgs.sharding import StripeGather
+        from rtgs.sharding import PeerFrame, StripeGather
         scene.set_stripe(world, rank)
-        gather = StripeGather(W, H, rank, world, torch.device("cuda", local_rank))
+        if args.gather == "peer":
+            peer = PeerFrame(W, H, rank, world, local_rank, dist)
+            out = peer.tensor            # rank 0's image, peer-mapped on the other ranks
+        else:
+            gather = StripeGather(W, H, rank, world, torch.device("cuda", local_rank))
+        config["sharding"] += f" [{args.gather}]"
 
     def set_view(step):
         v = step % N_VIEWS if tiles else (step * world + rank) % N_VIEWS
@@ -247,7 +256,10 @@ def main():
     def render_step():
         rt.render_device(DEPTH, out=out)
         if tiles and dist is not None:
-            gather(out, dist)
+            if peer is not None:
+                peer.finish(dist)
+            else:
+                gather(out, dist)
 
     def barrier():
         if dist is not None:
@@ -271,6 +283,19 @@ def main():
         set_view(s)
         render_step()
     barrier()
+    tiles_verified = None
+    if tiles:
+        # untimed check: the frame assembled from all ranks' stripes == rank 0's own full-frame render, bit for bit
+        set_view(0)
+        render_step()
+        barrier()
+        if rank == 0:
+            scene.set_stripe()
+            full = rt.render_device(DEPTH)
+            scene.set_stripe(world, rank)
+            torch.cuda.synchronize()
+            tiles_verified = bool(torch.equal(full, out))
+        barrier()
     timed_frames = min(args.steps, 4096)
     scene.set_option("kernel_timing", timed_frames)   # events around every kernel of the timed steps
     sampler = ClockSampler(local_rank)
@@ -368,6 +393,8 @@ def main():
                             "fallback_tiles": agg["fallback_tiles"]},
             "bvh_build_ms": build_ms,
         }
+        if tiles:
+            line["tiles_verified_bit_identical"] = tiles_verified
         if world == 1 and not args.no_cpu_baseline:
             stride = args.cpu_stride or (4 if W * H <= 1920 * 1080 else 8)
             r = cpu_leg(args.config, arrays, W, H, focal, views, min(args.steps, 32), 1, stride)   # ~10-20 s of CPU work

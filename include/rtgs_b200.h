@@ -163,6 +163,18 @@ int rtgs_scene_read_kernel_times(rtgs_scene* s, int32_t frames, float* ms /* fra
 int rtgs_host_alloc(size_t bytes, void** out);
 int rtgs_host_free(void* p);
 
+/* Peer-mapped framebuffer for tile sharding across processes ("peer-mapped stores of each GPU's
+ * tiles into GPU 0's framebuffer over NVLink"; no reference counterpart).  Rank 0 allocates the (W,H,3) image with
+ * rtgs_device_alloc and exports it; every other rank opens the handle on its own device and passes the returned
+ * pointer as `out_rgb` of rtgs_render (full_image_pitch = 1, RTGS_OPT_STRIPE set): its kernels then store their
+ * stripes straight into rank 0's memory.  handle = the 64 bytes of a cudaIpcMemHandle_t. */
+#define RTGS_IPC_HANDLE_BYTES 64
+int rtgs_device_alloc(int device, size_t bytes, void** out);
+int rtgs_device_free(int device, void* p);
+int rtgs_ipc_export(int device, const void* dev_ptr, unsigned char* handle /*[64]*/);
+int rtgs_ipc_open(int device, const unsigned char* handle /*[64]*/, void** out);
+int rtgs_ipc_close(int device, void* p);
+
 /* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
  * RayTracer makes: camera in, image out): `host_rgb` ((w,h,3) float32) and optionally
  * `host_T` ((w,h)).  Synchronous.  Pinned buffers (rtgs_host_alloc, cudaHostAlloc,

@@ -527,6 +527,54 @@ int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t 
     return RTGS_OK;
 }
 
+int rtgs_device_alloc(int device, size_t bytes, void** out) {
+    RTGS_CHECK_ARG(out != nullptr && bytes > 0);
+    *out = nullptr;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    CUDA_TRY(cudaMalloc(out, bytes));
+    return RTGS_OK;
+}
+
+int rtgs_device_free(int device, void* p) {
+    DeviceGuard g(device);
+    if (p) CUDA_TRY(cudaFree(p));
+    return RTGS_OK;
+}
+
+int rtgs_ipc_export(int device, const void* dev_ptr, unsigned char* handle) {
+    RTGS_CHECK_ARG(dev_ptr != nullptr && handle != nullptr);
+    static_assert(sizeof(cudaIpcMemHandle_t) == RTGS_IPC_HANDLE_BYTES, "handle size");
+    DeviceGuard g(device);
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, const_cast<void*>(dev_ptr)));
+    memcpy(handle, &h, sizeof(h));
+    return RTGS_OK;
+}
+
+int rtgs_ipc_open(int device, const unsigned char* handle, void** out) {
+    RTGS_CHECK_ARG(handle != nullptr && out != nullptr);
+    *out = nullptr;
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, sizeof(h));
+    CUDA_TRY(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RTGS_OK;
+}
+
+int rtgs_ipc_close(int device, void* p) {
+    DeviceGuard g(device);
+    if (p) CUDA_TRY(cudaIpcCloseMemHandle(p));
+    return RTGS_OK;
+}
+
 int rtgs_generate_rays(const rtgs_camera* cam, int device, float* rays, void* stream) {
     TRY(check_camera(cam));
     RTGS_CHECK_ARG(rays != nullptr);

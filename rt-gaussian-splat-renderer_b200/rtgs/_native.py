@@ -56,6 +56,11 @@ SIGNATURES = {
     "rtgs_scene_read_kernel_times": (C.c_int, [_vp, C.c_int32, _vp]),
     "rtgs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rtgs_host_free": (C.c_int, [_vp]),
+    "rtgs_device_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(_vp)]),
+    "rtgs_device_free": (C.c_int, [C.c_int, _vp]),
+    "rtgs_ipc_export": (C.c_int, [C.c_int, _vp, _vp]),
+    "rtgs_ipc_open": (C.c_int, [C.c_int, _vp, C.POINTER(_vp)]),
+    "rtgs_ipc_close": (C.c_int, [C.c_int, _vp]),
     "rtgs_render_host": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_float, _vp, _vp]),
     "rtgs_generate_rays": (C.c_int, [C.POINTER(rtgs_camera), C.c_int, _vp, _vp]),

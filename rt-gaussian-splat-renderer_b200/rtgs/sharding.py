@@ -63,3 +63,57 @@ class StripeGather:
             for r in range(1, self.world):
                 frame.index_copy_(0, self.cols[r], self.recv[r][:self.cols[r].numel()])
         return frame
+
+
+class PeerFrame:
+    """One (W,H,3) float32 framebuffer in rank 0's device memory that every rank's render kernels store their
+    stripes into directly over NVLink (CUDA IPC + peer access).  ``tensor`` is a torch view of that
+    memory on the local device: pass it as ``out`` of a full-frame ``RayTracer.render_device`` after
+    ``Scene.set_stripe(world, rank)``.  ``finish(dist)`` is a stream-ordered barrier: once it has completed on
+    rank 0's stream, every rank's stores have landed (a kernel's stores are performed when it completes)."""
+
+    class _Raw:
+        def __init__(self, ptr, shape):
+            self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 3}
+
+    def __init__(self, W: int, H: int, rank: int, world: int, device: int, dist=None):
+        import ctypes as C
+
+        import torch
+
+        from . import _native
+        lib = _native.load()
+        self.rank, self.world, self.device = rank, world, device
+        self._lib, self._owner_ptr, self._peer_ptr = lib, None, None
+        nbytes = W * H * 3 * 4
+        handle = torch.zeros(64, dtype=torch.uint8)
+        p = C.c_void_p()
+        if rank == 0:
+            _native.check(lib.rtgs_device_alloc(device, nbytes, C.byref(p)))
+            self._owner_ptr = p.value
+            buf = (C.c_ubyte * 64)()
+            _native.check(lib.rtgs_ipc_export(device, p, buf))
+            handle = torch.tensor(list(buf), dtype=torch.uint8)
+        if world > 1:
+            h = handle.to(torch.device("cuda", device))
+            dist.broadcast(h, src=0)
+            handle = h.cpu()
+        if rank != 0:
+            buf = (C.c_ubyte * 64)(*handle.tolist())
+            _native.check(lib.rtgs_ipc_open(device, buf, C.byref(p)))
+            self._peer_ptr = p.value
+        self.tensor = torch.as_tensor(PeerFrame._Raw(p.value, (W, H, 3)), device=torch.device("cuda", device))
+        self._token = torch.zeros(1, device=torch.device("cuda", device))
+
+    def finish(self, dist):
+        if self.world > 1:
+            dist.all_reduce(self._token)      # stream-ordered, no host synchronisation
+
+    def close(self):
+        self.tensor = None
+        if self._peer_ptr:
+            self._lib.rtgs_ipc_close(self.device, self._peer_ptr)
+            self._peer_ptr = None
+        if self._owner_ptr:
+            self._lib.rtgs_device_free(self.device, self._owner_ptr)
+            self._owner_ptr = None

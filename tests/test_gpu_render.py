@@ -176,6 +176,30 @@ def test_stripe_sharding_is_bit_identical():
     assert torch.equal(rt.render_device(16), full)
 
 
+def test_peer_frame_owner_side():
+    """PeerFrame on the owning rank: the library-allocated image is exportable (CUDA IPC handle) and a render into
+    its torch view equals the ordinary render.  (Opening the handle needs a second process and GPU: that path is
+    exercised by `bench.py --gpus N --sharding tiles`.)"""
+    import ctypes as C
+    import torch
+    from rtgs import _native
+    from rtgs.ray_tracer import RayTracer
+    from rtgs.sharding import PeerFrame
+    gs = random_set(2000, seed=13, mean_scale=0.03)
+    scene = make_scene(gs)
+    cam, _ = make_camera(0.5, 1.2, 2.4, 96, 64)
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    want = rt.render_device(16).clone()
+    pf = PeerFrame(96, 64, 0, 1, torch.cuda.current_device())
+    buf = (C.c_ubyte * 64)()
+    _native.check(_native.load().rtgs_ipc_export(torch.cuda.current_device(), C.c_void_p(pf.tensor.data_ptr()), buf))
+    assert any(buf)
+    rt.render_device(16, out=pf.tensor)
+    pf.finish(None)
+    assert torch.equal(pf.tensor, want)
+    pf.close()
+
+
 def test_render_paths_agree_and_pool_overflow_falls_back():
     """The same frame through (a) tile lists + shading kernels, (b) the fused kernel alone, (c) a list pool that
     is far too small, so that most tiles take the fused kernel through the fallback list: all within tolerance
