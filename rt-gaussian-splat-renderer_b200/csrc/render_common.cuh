@@ -188,6 +188,19 @@ __device__ __forceinline__ bool ellipsoid_in_frustum(const Frustum& f, const flo
     return in;
 }
 
+// One plane of that test, two-sided: plane {x: n.x = d} through the camera origin; lo / hi = the ellipsoid
+// reaches the side n.x >= d / the side n.x <= d.  A tile bounded by planes k (lower) and k+1 (upper) along an
+// image axis is touched iff lo[k] && hi[k+1]; neighbouring tiles share the plane between them.
+__device__ __forceinline__ void plane_side(float nx, float ny, float nz, float d, const float4& la, const float4& lb,
+                                           const float2& r01, const float2& r2, bool& lo, bool& hi) {
+    const float dist = nx * la.x + ny * la.y + nz * la.z - d;
+    const float ux = nx * la.w, uy = ny * lb.x, uz = nz * lb.y;
+    const float s2 = 1.003f * (ux * ux + uy * uy + uz * uz) + ux * (uy * r01.x + uz * r01.y) + uy * uz * r2.x;
+    const bool reach = dist * dist <= s2;
+    lo = dist >= 0.0f || reach;
+    hi = dist <= 0.0f || reach;
+}
+
 // ---- float64 exact evaluation from raw parameters (rare path) ---------------------------------
 __device__ __noinline__ static ExactHit exact_eval(const float4* __restrict__ raw, const CamD& cam, int s, int pi,
                                                    int pj) {

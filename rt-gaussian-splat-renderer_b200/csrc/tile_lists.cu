@@ -29,8 +29,9 @@ namespace {
 constexpr int STACK_CAP = 256;
 constexpr int STACK_SINGLE = STACK_CAP - 144;   // above this pop one node at a time: growth/step <= 48, then <= +3 per
                                                 // level over <= 31 two-level steps (tree depth <= 62)
-constexpr int GLIST_CAP = 1024;
-constexpr int CQ_CAP = 128;
+constexpr int GLIST_CAP = 960;
+constexpr int CQ_TILE = 64;                      // per-tile output queue of the fused four-tile filter (< 31 + 32)
+constexpr int CQ_CAP = TILES_PER_GROUP * CQ_TILE;   // the per-tile traversal uses it as one queue (< 31 + 64)
 static_assert(GLIST_CAP >= STACK_CAP, "per-tile traversal keeps its stack in the group list");
 
 struct __align__(16) WarpShared {
@@ -105,11 +106,11 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
     };
 
     // write the last `m` entries of cq as one chunk linked in front of `head`
-    auto write_chunk = [&](int m, int& ncq, int& head, int& count) -> bool {
+    auto write_chunk = [&](const int* q, int m, int& ncq, int& head, int& count) -> bool {
         const int chunk = alloc_chunk();
         if (chunk < 0) return false;
         int v = head;
-        if (lane < m) v = ws.cq[ncq - m + lane];
+        if (lane < m) v = q[ncq - m + lane];
         if (lane < m || lane == CHUNK_INTS - 1) P.pool[(int64_t)chunk * CHUNK_INTS + lane] = v;
         head = chunk;
         ncq -= m;
@@ -146,48 +147,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
             }
         }
 
-#pragma unroll 1
-        for (int sub = 0; sub < TILES_PER_GROUP; ++sub) {
-            const int i0 = gi0 + (sub / GROUP_TJ) * TILE_I, j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
-            if (i0 >= xe || j0 >= ye) continue;
-            const int tile = group * TILES_PER_GROUP + sub;
-            Frustum fr;
-            make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
-            int head = -1, count = 0, ncq = 0;
-            bool ok = true;
-            if (!per_tile) {
-                // filter the group's candidates: leaf box vs tile frustum, 32 per step
-#pragma unroll 1
-                for (int gpos = 0; gpos < ng && ok; gpos += 32) {
-                    const int idx = gpos + lane;
-                    bool h = false;
-                    int s = 0;
-                    if (idx < ng) {
-                        s = ws.glist[idx];
-                        float4 a, b;
-                        ldg256(P.leafbox + (int64_t)s * 2, a, b);
-                        h = ellipsoid_in_frustum(fr, a, b);
-                    }
-                    ST(st_nodes += (unsigned)min(32, ng - gpos));
-                    ST(st_steps += 1);
-                    const unsigned mh = __ballot_sync(FULL, h);
-                    if (h) ws.cq[ncq + __popc(mh & lt_mask)] = s;
-                    ncq += __popc(mh);
-                    __syncwarp();
-                    if (ncq >= CHUNK_IDS) ok = write_chunk(CHUNK_IDS, ncq, head, count);
-                }
-            } else {
-                int top = 1;
-                if (lane == 0) ws.glist[0] = 0;
-                __syncwarp();
-#pragma unroll 1
-                while (top > 0 && ok) {
-                    traverse_step(ws.glist, top, ws.cq, ncq, fr);
-#pragma unroll 1
-                    while (ncq >= CHUNK_IDS && ok) ok = write_chunk(CHUNK_IDS, ncq, head, count);
-                }
-            }
-            if (ok && ncq > 0) ok = write_chunk(ncq, ncq, head, count);
+        // a tile's list is complete: descriptor, or the fallback list if the pool ran out
+        auto finish_tile = [&](int tile, int head, int count, bool ok) {
             if (lane == 0) {
                 TileDesc d;
                 d.head = head;
@@ -196,7 +157,94 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
                 if (!ok) P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
             }
             ST(st_cands += ok ? (unsigned)count : 0u);
+        };
+
+        if (!per_tile) {
+            // ---- fused filter of the group's candidates for its four tiles ------------------------------
+            // The 2x2 tiles are bounded by 3 + 3 planes through the camera origin (pixel edges gi0, +4, +8 and
+            // gj0, +8, +16); a plane serves the tile on either side, so six exact support tests per Gaussian
+            // (render_common.cuh: plane_side) decide all four tiles, and every leaf record is fetched once.
+            float pnx[6], pny[6], pnz[6], pd[6];
+            {
+                const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    d3 n;
+                    if (k < 3) n = cam_rot(cam, 1.0, 0.0, ((double)(gi0 + k * TILE_I) - 0.5 * cam.W) * cam.ifx);
+                    else n = cam_rot(cam, 0.0, 1.0, ((double)(gj0 + (k - 3) * TILE_J) - 0.5 * cam.H) * cam.ify);
+                    pnx[k] = (float)n.x; pny[k] = (float)n.y; pnz[k] = (float)n.z;
+                    pd[k] = pnx[k] * ox + pny[k] * oy + pnz[k] * oz;
+                }
+            }
+            int head[TILES_PER_GROUP], count[TILES_PER_GROUP], ncq[TILES_PER_GROUP];
+            bool ok[TILES_PER_GROUP], valid[TILES_PER_GROUP];
+#pragma unroll
+            for (int t = 0; t < TILES_PER_GROUP; ++t) {
+                head[t] = -1; count[t] = 0; ncq[t] = 0; ok[t] = true;
+                valid[t] = gi0 + (t / GROUP_TJ) * TILE_I < xe && gj0 + (t % GROUP_TJ) * TILE_J < ye;
+            }
+#pragma unroll 1
+            for (int gpos = 0; gpos < ng; gpos += 32) {
+                const int idx = gpos + lane;
+                int s = 0;
+                bool lo[6], hi[6];   // the ellipsoid reaches the >= side / the <= side of plane k
+#pragma unroll
+                for (int k = 0; k < 6; ++k) lo[k] = hi[k] = false;
+                if (idx < ng) {
+                    s = ws.glist[idx];
+                    float4 a, b;
+                    ldg256(P.leafbox + (int64_t)s * 2, a, b);
+                    const float2 r01 = __half22float2(*reinterpret_cast<const __half2*>(&b.z));
+                    const float2 r2 = __half22float2(*reinterpret_cast<const __half2*>(&b.w));
+#pragma unroll
+                    for (int k = 0; k < 6; ++k)
+                        plane_side(pnx[k], pny[k], pnz[k], pd[k], a, b, r01, r2, lo[k], hi[k]);
+                }
+                ST(st_nodes += (unsigned)min(32, ng - gpos));
+                ST(st_steps += 1);
+#pragma unroll
+                for (int t = 0; t < TILES_PER_GROUP; ++t) {
+                    const int ta = t / GROUP_TJ, tb = 3 + t % GROUP_TJ;
+                    const bool h = valid[t] && ok[t] && lo[ta] && hi[ta + 1] && lo[tb] && hi[tb + 1];
+                    const unsigned mh = __ballot_sync(FULL, h);
+                    if (h) ws.cq[t * CQ_TILE + ncq[t] + __popc(mh & lt_mask)] = s;
+                    ncq[t] += __popc(mh);
+                }
+                __syncwarp();
+#pragma unroll
+                for (int t = 0; t < TILES_PER_GROUP; ++t)
+                    if (ncq[t] >= CHUNK_IDS) ok[t] = write_chunk(ws.cq + t * CQ_TILE, CHUNK_IDS, ncq[t], head[t], count[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < TILES_PER_GROUP; ++t) {
+                if (!valid[t]) continue;
+                if (ok[t] && ncq[t] > 0) ok[t] = write_chunk(ws.cq + t * CQ_TILE, ncq[t], ncq[t], head[t], count[t]);
+                finish_tile(group * TILES_PER_GROUP + t, head[t], count[t], ok[t]);
+            }
             __syncwarp();
+        } else {
+            // ---- the group's list did not fit shared memory: one traversal per tile, leaves stream out -------
+#pragma unroll 1
+            for (int sub = 0; sub < TILES_PER_GROUP; ++sub) {
+                const int i0 = gi0 + (sub / GROUP_TJ) * TILE_I, j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
+                if (i0 >= xe || j0 >= ye) continue;
+                Frustum fr;
+                make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
+                int head = -1, count = 0, ncq = 0;
+                bool ok = true;
+                int top = 1;
+                if (lane == 0) ws.glist[0] = 0;
+                __syncwarp();
+#pragma unroll 1
+                while (top > 0 && ok) {
+                    traverse_step(ws.glist, top, ws.cq, ncq, fr);
+#pragma unroll 1
+                    while (ncq >= CHUNK_IDS && ok) ok = write_chunk(ws.cq, CHUNK_IDS, ncq, head, count);
+                }
+                if (ok && ncq > 0) ok = write_chunk(ws.cq, ncq, ncq, head, count);
+                finish_tile(group * TILES_PER_GROUP + sub, head, count, ok);
+                __syncwarp();
+            }
         }
     }
 
