@@ -15,16 +15,16 @@
 //            in the tile-centred frame, float64 from the raw parameters inside the error band), entry
 //            distance, alpha; the hit goes to the lane's K-entry buffer in shared memory (replace-max
 //            once K are held).
-// After the list: rank sort of the lane's entries (keys in registers, near ties ordered by their float64
-// entry distances), compositing in that order with the SH basis evaluated once per ray, and a
-// sector-aligned framebuffer store.
+// After the list: the lane's entries are ordered by a bitonic network over (entry-distance bits | slot) keys in
+// registers (near ties by their float64 entry distances), composited in that order with the SH basis evaluated
+// once per ray (six 256-bit loads per layer), and stored sector-aligned.
 //
 // Numerics: identical to the fused kernel (render.cu) - parity is defined against the float64
 // evaluation of the reference's maths, see DESIGN.md §2.
 //
-// Occupancy is the point of this kernel's layout: 9.25 KB of shared memory per warp and <= 80 registers
-// give 24 warps per SM (the fused kernel: 12 KB, 128 registers, 16 warps), which is what hides the
-// scattered Gaussian-record and SH fetches.
+// The kernel is bound by the L1 data pipe (per-lane gathers of SH and staged records), not by latency:
+// 20 warps x 96 registers per SM is the measured optimum (24 x 80 and 16 x 128 are within 4 %), 9.25 KB of
+// shared memory per warp.  DESIGN.md §4 has the time split.
 #include "render_common.cuh"
 
 using namespace rtgs_dev;

@@ -5,18 +5,20 @@
 // planes through the origin, and "every Gaussian whose bound some ray of the rectangle hits" is a
 // frustum query on the LBVH.  A warp owns one 8x16-pixel GROUP at a time (persistent threads, groups
 // pulled from an atomic counter in 32x32-pixel macro-tile order):
-//   1. group traversal - up to 32 nodes are popped from a shared-memory stack per step, each lane tests
-//      the two child boxes of its node against the 4 planes, survivors are compacted with ballot/popc
-//      (internal children -> stack, leaves -> the group's candidate list in shared memory);
-//   2. for each of the group's four 4x8-pixel tiles the list is filtered with the tile's own frustum
-//      (one leaf box per lane, coalesced because the list is in Morton order) and streamed to the
-//      global list pool in 128-byte chunks (render_common.cuh), where k_shade_tiles picks it up.
-// A group whose list would overflow shared memory traverses the LBVH per tile instead (same code,
-// leaves stream straight to the pool).  A tile whose list does not fit the pool is handed to the fused
-// kernel (render.cu) through the fallback list; nothing is ever dropped.
+//   1. group traversal - up to 16 nodes are popped from a shared-memory stack per step; a pair of lanes
+//      shares a node and each lane tests the two boxes in the record of its child (two-level nodes,
+//      lbvh.cu: one step descends two tree levels) against the 4 planes; survivors are compacted with
+//      ballot/popc (internal -> stack, leaves -> the group's candidate list in shared memory);
+//   2. the list is filtered for the group's four 4x8-pixel tiles at once - the 2x2 tiles are bounded by
+//      3 + 3 planes, one 32-byte leaf record per lane, six exact ellipsoid-vs-plane support tests decide
+//      all four tiles - and streamed to the global list pool in 128-byte chunks (render_common.cuh),
+//      where k_shade_tiles picks it up.
+// A group whose list would overflow shared memory traverses the LBVH per tile instead (leaves stream
+// straight to the pool).  A tile whose list does not fit the pool is handed to the fused kernel
+// (render.cu) through the fallback list; nothing is ever dropped.
 //
-// The kernel holds no per-ray state: ~50 registers and 3.5 KB of shared memory per warp, so 40+ warps
-// per SM hide the dependent node fetches (the fused kernel ran this phase at 16 warps per SM).
+// The kernel holds no per-ray state: 64 registers and 5.75 KB of shared memory per warp, 32 warps per SM.
+// It is bound by instruction issue and the dependent node fetches.
 #include "render_common.cuh"
 
 using namespace rtgs_dev;
