@@ -197,8 +197,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                             ST(st_f64 += h.refined);
                             if (h.hit) {
                                 int slot = -1;
-                                if (cnt < K) slot = cnt++;
-                                else if (h.t1 < kmax_t) slot = kmax_slot;
+                                if (cnt < K) {
+                                    slot = cnt++;
+                                } else {
+                                    // full: nearer than the farthest entry?  Within float32 rounding of each
+                                    // other the float64 entry distances decide (rare)
+                                    bool nearer = h.t1 < kmax_t;
+                                    if (fabsf(h.t1 - kmax_t) <= 4e-6f * kmax_t) {
+                                        nearer = exact_less(P.raw, cam, h.s, ws.kb_i[kmax_slot][lane], pi, pj);
+                                        ST(st_f64 += 2);
+                                    }
+                                    if (nearer) slot = kmax_slot;
+                                }
                                 if (slot >= 0) {
                                     ws.kb_t[slot][lane] = h.t1;
                                     ws.kb_i[slot][lane] = h.s;

@@ -49,6 +49,7 @@ struct __align__(16) WarpShared {
     float kb_t[K][32];         // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
     int kb_i[K][32];
     float kb_a[K][32];
+    float amb[3][32];          // per lane: one hit whose place at the K-th / (K+1)-th boundary is decided later
 };
 static_assert(sizeof(WarpShared) * K2_WARPS * K2_CTAS <= 227 * 1024, "shared-memory budget per SM");
 
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
     const CamD& cam = P.cam;
     const int xe = P.x0 + P.w, ye = P.y0 + P.h;
 
-    unsigned long long st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
+    unsigned long long st_amb = 0, st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
 #define ST(expr) do { if (STATS) { expr; } } while (0)
 
 #pragma unroll 1
@@ -108,6 +109,8 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
         const bool active = pi < xe && pj < ye;
 
         int cnt = 0;
+        int amb_state = 0;       // kmax_slot with its flag bits, after the list
+        float amb_kt = 0.0f;     // kmax_t after the list
         TileRays tr;
         if (desc.count > 0) {
             make_tile_rays(cam, i0, j0, pi, pj, active, tr);
@@ -167,21 +170,39 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                         ST(st_f64 += h.refined);
                         if (h.hit) {
                             int slot = -1;
-                            if (cnt < K) slot = cnt++;
-                            else if (h.t1 < kmax_t) slot = kmax_slot;
+                            if (cnt < K) {
+                                slot = cnt++;
+                            } else if (fabsf(h.t1 - kmax_t) <= 4e-6f * kmax_t) {
+                                // full, and within float32 rounding of the farthest entry: which of the two is
+                                // the K-th nearest needs float64.  The hit is set aside (flag in bit 8 of
+                                // kmax_slot) and merged after the list: the K nearest of A + {c} are the K
+                                // nearest of (the K nearest of A) + {c}.  A second such hit of the same ray
+                                // (bit 9) sends the tile to the fused kernel.
+                                if (kmax_slot & 0x100) {
+                                    kmax_slot |= 0x200;
+                                } else {
+                                    ws.amb[0][lane] = h.t1;
+                                    ws.amb[1][lane] = __int_as_float(h.s);
+                                    ws.amb[2][lane] = h.alpha;
+                                    kmax_slot |= 0x100;
+                                }
+                            } else if (h.t1 < kmax_t) {
+                                slot = kmax_slot & 15;   // full: replace the farthest entry
+                            }
                             if (slot >= 0) {
                                 ws.kb_t[slot][lane] = h.t1;
                                 ws.kb_i[slot][lane] = h.s;
                                 ws.kb_a[slot][lane] = h.alpha;
-                                if (cnt == K) {   // buffer full: track the farthest entry
-                                    // entry distances are positive: their bit patterns order like the
-                                    // floats; the slot rides in the 4 low bits
-                                    unsigned best = 0;
+                                if (cnt == K) {   // buffer full: track the farthest entry (exact float32 maximum:
+                                    float mt = -INFINITY;   // a key with truncated low bits cannot tell near ties
+                                    int ms = 0;             // at the boundary apart)
 #pragma unroll
-                                    for (int k = 0; k < K; ++k)
-                                        best = max(best, (__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k);
-                                    kmax_slot = (int)(best & 15u);
-                                    kmax_t = ws.kb_t[kmax_slot][lane];
+                                    for (int k = 0; k < K; ++k) {
+                                        const float t = ws.kb_t[k][lane];
+                                        if (t > mt) { mt = t; ms = k; }
+                                    }
+                                    kmax_t = mt;
+                                    kmax_slot = ms | (kmax_slot & 0x300);
                                 }
                             }
                         }
@@ -189,6 +210,38 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                     ST(st_ins += 1);
                 }
                 __syncwarp();
+            }
+            amb_state = kmax_slot & 0x300 ? kmax_slot : 0;
+            amb_kt = kmax_t;
+        }
+
+        // ---- boundary hits that were set aside (rare) --------------------------------------------------
+        if (__any_sync(FULL, amb_state != 0)) {
+            ST(st_amb += amb_state != 0);
+            if (__any_sync(FULL, (amb_state & 0x200) != 0)) {
+                // two of them on one ray: k_render (launched next on the stream) renders the tile; nothing of
+                // it has been written yet, so `accumulate` outputs stay correct
+                if (lane == 0) {
+                    P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
+                    *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS + 1) = 1;
+                }
+                continue;
+            }
+            if (amb_state & 0x100) {
+                // the buffer is full; its farthest entry is (amb_kt, slot amb_state & 15)
+                const int slot = amb_state & 15;
+                const float at = ws.amb[0][lane];
+                const int as = __float_as_int(ws.amb[1][lane]);
+                bool nearer = at < amb_kt;
+                if (fabsf(at - amb_kt) <= 4e-6f * amb_kt) {
+                    nearer = exact_less(P.raw, cam, as, ws.kb_i[slot][lane], pi, pj);
+                    ST(st_f64 += 2);
+                }
+                if (nearer) {
+                    ws.kb_t[slot][lane] = at;
+                    ws.kb_i[slot][lane] = as;
+                    ws.kb_a[slot][lane] = ws.amb[2][lane];
+                }
             }
         }
 

@@ -61,6 +61,26 @@ def test_synthetic_parity(n, scale, sh, res, depth):
     assert mx <= TOL and ps >= 60.0
 
 
+@pytest.mark.parametrize("seed", range(12))
+def test_random_scenes_and_cameras(seed):
+    """Many small random configurations (count, size, anisotropy, SH on/off, depth, resolution, pose, fov): rare
+    paths (near ties, float64 band, full k-buffers, empty tiles, ragged edges) get many chances to disagree."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(1, 2500))
+    gs = random_set(n, seed=2000 + seed, mean_scale=float(rng.uniform(0.01, 0.15)), sh=bool(rng.integers(0, 2)))
+    scene = make_scene(gs)
+    W, H = int(rng.integers(17, 150)), int(rng.integers(9, 110))
+    depth = int(rng.choice([1, 3, 8, 16, 16, 16, 24]))
+    cam, ocam = make_camera(float(rng.uniform(0, 6.28)), float(rng.uniform(0.3, 2.8)), float(rng.uniform(0.2, 3.5)),
+                            W, H, fov=float(rng.uniform(30, 110)))
+    img, _ = _render(scene, cam, depth=depth)
+    ref = O.render(gs, ocam, depth=depth)
+    mx, ps, bad = compare(img, ref["rgb"], TOL)
+    print(f"seed {seed}: n={n} {W}x{H} depth={depth} kbar={np.minimum(ref['nhit'], depth).mean():.2f} "
+          f"maxhits={ref['nhit'].max()} max-abs={mx:.2e}")
+    assert mx <= TOL and ps >= 60.0
+
+
 def test_camera_inside_the_cloud():
     # entry points behind the origin are skipped (scene.py:433, t1 > 0): camera inside the cube
     gs = random_set(1500, seed=77, mean_scale=0.08)
