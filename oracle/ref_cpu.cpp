@@ -376,6 +376,13 @@ inline void shade(const Scene& s, int64_t k, const RayT<T>& r, T t1, T t2, T& T_
     T_att *= (T)1 - alpha;
 }
 
+// The step the reference adds to ray.start after every layer (ray_tracer.py:100-102: `t1 + 1e-8`).  In the
+// reference's own float32 arithmetic it is below half an ulp for t1 >= 0.25 and does nothing there; evaluated in
+// float64 it skips a layer that starts within 1e-8 of the previous one (about 3 pixels of a 1080p / 1 M frame).
+// The image oracle therefore runs with 0 (every distinct crossing counts, as in the NumPy brute force); the
+// timed float32 baseline and `restart_eps=1e-8` keep the literal value.
+static double g_restart_eps = 1e-8;
+
 template <typename T>
 void render_t(const Scene& s, const Cam& cam, int depth, int64_t npix, const int32_t* pix, double* rgb, double* Tout,
               int32_t* nlayers, uint64_t* counters) {
@@ -393,7 +400,7 @@ void render_t(const Scene& s, const Cam& cam, int depth, int64_t npix, const int
             if (k < 0) break;                                // ray.start = inf: later steps cannot hit
             shade<T>(s, k, r, t1, t2, T_att, acc);
             ++nl;
-            r.start = t1 + (T)1e-8;                          // ray_tracer.py:100-102
+            r.start = t1 + (T)g_restart_eps;                 // ray_tracer.py:100-102
         }
         rgb[p * 3] = (double)acc[0];
         rgb[p * 3 + 1] = (double)acc[1];
@@ -481,6 +488,8 @@ int rc_max_threads(void) { return omp_get_max_threads(); }
 
 // precision: 0 = float (reference arithmetic), 1 = double.  pix = npix (i,j) pairs.
 // counters (optional, 2 x uint64): node visits, Gaussian tests.
+void rc_set_restart_eps(double eps) { g_restart_eps = eps; }
+
 int rc_render(void* h, const void* cam, int depth, int precision, int64_t npix, const int32_t* pix, double* rgb,
               double* Tout, int32_t* nlayers, uint64_t* counters, int nthreads) {
     Scene* s = (Scene*)h;

@@ -54,6 +54,8 @@ def _load():
         lib.rc_free.argtypes = [C.c_void_p]
         lib.rc_read_lbvh.argtypes = [C.c_void_p] * 6
         lib.rc_max_threads.restype = C.c_int
+        lib.rc_set_restart_eps.argtypes = [C.c_double]
+        lib.rc_set_restart_eps.restype = None
         lib.rc_render.restype = C.c_int
         lib.rc_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
@@ -111,8 +113,15 @@ class CpuScene:
         c.width, c.height = int(cam.width), int(cam.height)
         return c
 
-    def render(self, cam, depth=16, pixels=None, precision="double", threads=0, brute=False):
-        """cam: oracle.ref_numpy.CameraParams.  Returns dict(rgb (npix,3) f64, T, nlayers|nhit, counters)."""
+    def render(self, cam, depth=16, pixels=None, precision="double", threads=0, brute=False, restart_eps=None):
+        """cam: oracle.ref_numpy.CameraParams.  Returns dict(rgb (npix,3) f64, T, nlayers|nhit, counters).
+
+        restart_eps: what is added to ray.start after every layer (ray_tracer.py:100-102 has 1e-8).  Default: 0 for
+        the float64 image oracle (every distinct crossing counts, like the NumPy brute force; see ref_cpu.cpp),
+        the reference's literal 1e-8 for the float32 timed baseline."""
+        if restart_eps is None:
+            restart_eps = 1e-8 if precision == "float" else 0.0
+        _load().rc_set_restart_eps(C.c_double(float(restart_eps)))
         if pixels is None:
             pixels = all_pixels(cam.width, cam.height)
         pixels = np.ascontiguousarray(pixels, dtype=np.int32)
