@@ -196,33 +196,46 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                             const PreciseHit h = precise_test(P, tr.rec[pend_c], ry.dlx, ry.dly, ry.dlz, pi, pj);
                             ST(st_f64 += h.refined);
                             if (h.hit) {
-                                int slot = -1;
-                                if (cnt < K) {
-                                    slot = cnt++;
-                                } else {
-                                    // full: nearer than the farthest entry?  Within float32 rounding of each
-                                    // other the float64 entry distances decide (rare)
-                                    bool nearer = h.t1 < kmax_t;
-                                    if (fabsf(h.t1 - kmax_t) <= 4e-6f * kmax_t) {
-                                        nearer = exact_less(P.raw, cam, h.s, ws.kb_i[kmax_slot][lane], pi, pj);
-                                        ST(st_f64 += 2);
+                                auto find_farthest = [&]() {
+                                    float mt = -INFINITY;
+                                    int ms = 0;
+#pragma unroll 4
+                                    for (int k = 0; k < K; ++k) {
+                                        const float t = ws.kb_t[k][lane];
+                                        if (t > mt) { mt = t; ms = k; }
                                     }
-                                    if (nearer) slot = kmax_slot;
-                                }
-                                if (slot >= 0) {
+                                    kmax_t = mt;
+                                    kmax_slot = ms;
+                                };
+                                if (cnt < K) {
+                                    const int slot = cnt++;
                                     ws.kb_t[slot][lane] = h.t1;
                                     ws.kb_i[slot][lane] = h.s;
                                     ws.kb_a[slot][lane] = h.alpha;
-                                    if (cnt == K) {   // buffer full: track the farthest entry
-                                        float mt = -INFINITY;
-                                        int ms = 0;
-#pragma unroll 4
-                                        for (int k = 0; k < K; ++k) {
-                                            const float t = ws.kb_t[k][lane];
-                                            if (t > mt) { mt = t; ms = k; }
+                                    if (cnt == K) find_farthest();
+                                } else {
+                                    // full: the candidate replaces the farthest entry if it is nearer.  Whenever
+                                    // two contenders for the last place are within float32 rounding of each other
+                                    // - the candidate and the farthest entry, or the evicted entry and the new
+                                    // farthest one - their float64 entry distances decide (exact_less; rare).
+                                    float ct = h.t1, ca = h.alpha;
+                                    int cs = h.s;
+#pragma unroll 1
+                                    for (;;) {
+                                        bool nearer = ct < kmax_t;
+                                        if (fabsf(ct - kmax_t) <= 2e-6f * kmax_t) {
+                                            nearer = exact_less(P.raw, cam, cs, ws.kb_i[kmax_slot][lane], pi, pj);
+                                            ST(st_f64 += 2);
                                         }
-                                        kmax_t = mt;
-                                        kmax_slot = ms;
+                                        if (!nearer) break;
+                                        const float et = kmax_t, ea = ws.kb_a[kmax_slot][lane];
+                                        const int es = ws.kb_i[kmax_slot][lane];
+                                        ws.kb_t[kmax_slot][lane] = ct;
+                                        ws.kb_i[kmax_slot][lane] = cs;
+                                        ws.kb_a[kmax_slot][lane] = ca;
+                                        find_farthest();
+                                        if (!(et - kmax_t <= 2e-6f * et)) break;
+                                        ct = et; cs = es; ca = ea;   // the evicted entry ties with the new farthest
                                     }
                                 }
                             }

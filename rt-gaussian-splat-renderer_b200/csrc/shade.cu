@@ -39,6 +39,7 @@ namespace {
 #endif
 constexpr int SHADE_WARPS = K2_WARPS;   // warps per CTA
 constexpr int K = 16;          // k-buffer entries (depth <= 16)
+constexpr float TIE_BAND = 2e-6f;   // relative: float32 entry distances closer than this are compared in float64
 constexpr int BATCH = 32;      // staged candidates per batch (a chunk fills 31)
 constexpr int REC_Q = 5;       // quads per staged record (80-byte stride: conflict-free gathers)
 
@@ -49,7 +50,7 @@ struct __align__(16) WarpShared {
     float kb_t[K][32];         // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
     int kb_i[K][32];
     float kb_a[K][32];
-    float amb[3][32];          // per lane: one hit whose place at the K-th / (K+1)-th boundary is decided later
+    float amb[2][3][32];       // per lane: up to two hits whose place at the K-th / (K+1)-th boundary is decided later
 };
 static_assert(sizeof(WarpShared) * K2_WARPS * K2_CTAS <= 227 * 1024, "shared-memory budget per SM");
 
@@ -89,7 +90,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
     const CamD& cam = P.cam;
     const int xe = P.x0 + P.w, ye = P.y0 + P.h;
 
-    unsigned long long st_amb = 0, st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
+    unsigned long long st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0, st_ins = 0;
 #define ST(expr) do { if (STATS) { expr; } } while (0)
 
 #pragma unroll 1
@@ -109,8 +110,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
         const bool active = pi < xe && pj < ye;
 
         int cnt = 0;
-        int amb_state = 0;       // kmax_slot with its flag bits, after the list
-        float amb_kt = 0.0f;     // kmax_t after the list
+        int amb_state = 0;       // kmax_slot with its set-aside count, after the list
         TileRays tr;
         if (desc.count > 0) {
             make_tile_rays(cam, i0, j0, pi, pj, active, tr);
@@ -169,33 +169,43 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                         const PreciseHit h = precise_test(P, ws.rec[c], tr.dlx, tr.dly, tr.dlz, pi, pj);
                         ST(st_f64 += h.refined);
                         if (h.hit) {
+                            // Which K entries survive must be decided on float64 entry distances whenever two
+                            // candidates for the last place are within float32 rounding of each other.  Such a
+                            // hit - the incoming one when it ties with the farthest entry, or the evicted farthest
+                            // entry when it ties with the new farthest one - is set aside (up to two per ray,
+                            // counted in bits 8-9 of kmax_slot) and merged after the list with exact_less: the K
+                            // nearest of A + {c} are the K nearest of (the K nearest of A) + {c}.  A third one on
+                            // the same ray sends the tile to the fused kernel, which resolves ties on the spot.
+                            auto set_aside = [&](float t, int sid, float a) {
+                                // 0, 1, 2 set aside so far; 3 = more than fit
+                                if ((kmax_slot & 0x300) == 0) {
+                                    ws.amb[0][0][lane] = t;
+                                    ws.amb[0][1][lane] = __int_as_float(sid);
+                                    ws.amb[0][2][lane] = a;
+                                    kmax_slot |= 0x100;
+                                } else if ((kmax_slot & 0x300) == 0x100) {
+                                    ws.amb[1][0][lane] = t;
+                                    ws.amb[1][1][lane] = __int_as_float(sid);
+                                    ws.amb[1][2][lane] = a;
+                                    kmax_slot ^= 0x300;   // 0x100 -> 0x200
+                                } else {
+                                    kmax_slot |= 0x300;
+                                }
+                            };
                             int slot = -1;
                             if (cnt < K) {
                                 slot = cnt++;
-                            } else if (fabsf(h.t1 - kmax_t) <= 4e-6f * kmax_t) {
-                                // full, and within float32 rounding of the farthest entry: which of the two is
-                                // the K-th nearest needs float64.  The hit is set aside (flag in bit 8 of
-                                // kmax_slot) and merged after the list: the K nearest of A + {c} are the K
-                                // nearest of (the K nearest of A) + {c}.  A second such hit of the same ray
-                                // (bit 9) sends the tile to the fused kernel.
-                                if (kmax_slot & 0x100) {
-                                    kmax_slot |= 0x200;
-                                } else {
-                                    ws.amb[0][lane] = h.t1;
-                                    ws.amb[1][lane] = __int_as_float(h.s);
-                                    ws.amb[2][lane] = h.alpha;
-                                    kmax_slot |= 0x100;
-                                }
+                            } else if (fabsf(h.t1 - kmax_t) <= TIE_BAND * kmax_t) {
+                                set_aside(h.t1, h.s, h.alpha);
                             } else if (h.t1 < kmax_t) {
                                 slot = kmax_slot & 15;   // full: replace the farthest entry
                             }
                             if (slot >= 0) {
                                 ws.kb_t[slot][lane] = h.t1;
-                                ws.kb_i[slot][lane] = h.s;
-                                ws.kb_a[slot][lane] = h.alpha;
-                                if (cnt == K) {   // buffer full: track the farthest entry (exact float32 maximum:
-                                    float mt = -INFINITY;   // a key with truncated low bits cannot tell near ties
-                                    int ms = 0;             // at the boundary apart)
+                                if (cnt == K) {   // buffer full: track the farthest entry (exact float32 maximum)
+                                    const float old_t = kmax_t;   // the evicted entry's distance (inf: none)
+                                    float mt = -INFINITY;
+                                    int ms = 0;
 #pragma unroll
                                     for (int k = 0; k < K; ++k) {
                                         const float t = ws.kb_t[k][lane];
@@ -203,7 +213,12 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                                     }
                                     kmax_t = mt;
                                     kmax_slot = ms | (kmax_slot & 0x300);
+                                    // evicted ~ new farthest: its id and alpha are still in the slot
+                                    if (old_t < 3e38f && old_t - mt <= TIE_BAND * old_t)
+                                        set_aside(old_t, ws.kb_i[slot][lane], ws.kb_a[slot][lane]);
                                 }
+                                ws.kb_i[slot][lane] = h.s;
+                                ws.kb_a[slot][lane] = h.alpha;
                             }
                         }
                     }
@@ -212,14 +227,12 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                 __syncwarp();
             }
             amb_state = kmax_slot & 0x300 ? kmax_slot : 0;
-            amb_kt = kmax_t;
         }
 
         // ---- boundary hits that were set aside (rare) --------------------------------------------------
         if (__any_sync(FULL, amb_state != 0)) {
-            ST(st_amb += amb_state != 0);
-            if (__any_sync(FULL, (amb_state & 0x200) != 0)) {
-                // two of them on one ray: k_render (launched next on the stream) renders the tile; nothing of
+            if (__any_sync(FULL, ((amb_state >> 8) & 3) == 3)) {
+                // more than two on one ray: k_render (launched next on the stream) renders the tile; nothing of
                 // it has been written yet, so `accumulate` outputs stay correct
                 if (lane == 0) {
                     P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
@@ -227,20 +240,28 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                 }
                 continue;
             }
-            if (amb_state & 0x100) {
-                // the buffer is full; its farthest entry is (amb_kt, slot amb_state & 15)
-                const int slot = amb_state & 15;
-                const float at = ws.amb[0][lane];
-                const int as = __float_as_int(ws.amb[1][lane]);
-                bool nearer = at < amb_kt;
-                if (fabsf(at - amb_kt) <= 4e-6f * amb_kt) {
+            const int na = (amb_state >> 8) & 3;
+#pragma unroll 1
+            for (int a = 0; a < na; ++a) {
+                // the buffer is full: merge the hit with it (replace the farthest entry if the hit is nearer)
+                float mt = -INFINITY;
+                int slot = 0;
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {
+                    const float t = ws.kb_t[k][lane];
+                    if (t > mt) { mt = t; slot = k; }
+                }
+                const float at = ws.amb[a][0][lane];
+                const int as = __float_as_int(ws.amb[a][1][lane]);
+                bool nearer = at < mt;
+                if (fabsf(at - mt) <= TIE_BAND * mt) {
                     nearer = exact_less(P.raw, cam, as, ws.kb_i[slot][lane], pi, pj);
                     ST(st_f64 += 2);
                 }
                 if (nearer) {
                     ws.kb_t[slot][lane] = at;
                     ws.kb_i[slot][lane] = as;
-                    ws.kb_a[slot][lane] = ws.amb[2][lane];
+                    ws.kb_a[slot][lane] = ws.amb[a][2][lane];
                 }
             }
         }
