@@ -12,8 +12,10 @@ view-sharded with the scene replicated on every GPU and no collective on the dat
 per-GPU work is fixed as N grows ("scaling": "weak").  One ray = one finished pixel.
 
 value  = whole-job Mrays/s with everything resident in HBM (device-timed, CUDA events, max over ranks)
-e2e    = the same through the public API call with HOST buffers (RayTracer.render: camera struct
-         in, image copied back to host memory inside the timed region)
+e2e    = the same through the public API with HOST buffers: the orbit sweep as a user writes it with
+         RayTracer.render_async()/result() (camera struct in, image delivered to pinned host memory, every step,
+         inside the timed region; two frames in flight so that step s+1 renders while the tail of step s crosses
+         PCIe); e2e.sync_value = the same loop with the blocking RayTracer.render()
 roofline = the dominant kernel, k_shade_tiles (intersection + k-buffer + SH compositing): algorithmic bytes per
          ray (16 + kbar*(64 + 192[sh]), all of them consumed by this kernel) x rays per launch /
          its mean duration, measured with CUDA events the library records around each kernel on the render
@@ -341,13 +343,38 @@ def main():
         set_view(s)
         e2e_step()
     barrier()
-    e2e_s = time.perf_counter() - t0
+    e2e_s = e2e_sync_s = time.perf_counter() - t0
+    e2e_kernels = None
+    if not tiles:
+        # the sweep API: every step still uploads its camera and delivers its image to pinned host memory, but
+        # two frames are in flight (RayTracer.render_async), so step s+1 renders while the tail of step s is
+        # copied out.  Every image is collected inside the timed region.
+        def pipelined(n):
+            prev = None
+            for s in range(n):
+                set_view(s)
+                cur = rt.render_async(DEPTH)
+                if prev is not None:
+                    prev.result()
+                prev = cur
+            prev.result()
+        pipelined(min(args.warmup, 3))
+        barrier()
+        t0 = time.perf_counter()
+        pipelined(args.steps)
+        barrier()
+        e2e_s = time.perf_counter() - t0
+        # untimed repeat with the library's per-kernel events switched on: what the kernels cost in this mode
+        scene.set_option("kernel_timing", timed_frames)
+        pipelined(timed_frames)
+        e2e_kernels = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)
+        scene.set_option("kernel_timing", 0)
 
     if dist is not None:
-        t = torch.tensor([total_ms, e2e_s, float(np.mean(kern_ms)), *per_kernel.tolist()], dtype=torch.float64,
-                         device="cuda")
+        t = torch.tensor([total_ms, e2e_s, e2e_sync_s, float(np.mean(kern_ms)), *per_kernel.tolist()],
+                         dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, kern_mean, *pk = t.tolist()
+        total_ms, e2e_s, e2e_sync_s, kern_mean, *pk = t.tolist()
         per_kernel = np.asarray(pk)
     else:
         kern_mean = float(np.mean(kern_ms))
@@ -372,7 +399,12 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 44 * world,
                     "d2h_bytes_per_step": W * H * 3 * 4 * (1 if tiles else world),
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "api": "stripes gathered on rank 0, then one copy to pinned host memory" if tiles else
+                           "RayTracer.render_async()/result(): two frames in flight, every image collected",
+                    "sync_value": rays_step * args.steps / e2e_sync_s / 1e6,
+                    "sync_api": "RayTracer.render() per step (blocking)",
+                    "kernels_ms": None if e2e_kernels is None else [round(float(v), 5) for v in e2e_kernels]},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": load_traffic(KERNEL_NAMES[dom]), "peak_source": peak_src,

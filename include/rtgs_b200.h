@@ -184,6 +184,18 @@ int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam,
                      int32_t x0, int32_t y0, int32_t w, int32_t h,
                      int32_t depth, float t_cut, float* host_rgb, float* host_T);
 
+/* The same call split in two, for sweeps over many views (the reference's viewer loop, __main__.py:236-252,
+ * and the 64-view orbit of the bench): _submit queues the frame's kernels and returns at once, _collect
+ * delivers the OLDEST submitted frame to the host buffers given at its submit and returns when the image is
+ * complete.  Up to two frames may be in flight, so frame f+1 renders while the last bands of frame f cross
+ * PCIe.  The destination must be pinned (rtgs_host_alloc / cudaHostAlloc / cudaHostRegister) and must not
+ * be touched between submit and collect.  RTGS_ERR_STATE: a third submit, a collect with nothing in
+ * flight, or rtgs_render_host while frames are in flight. */
+int rtgs_render_host_submit(rtgs_scene* s, const rtgs_camera* cam,
+                            int32_t x0, int32_t y0, int32_t w, int32_t h,
+                            int32_t depth, float t_cut, float* host_rgb, float* host_T);
+int rtgs_render_host_collect(rtgs_scene* s);
+
 /* Camera.generate_ray_field — camera.py:57-71.  rays: device, (W,H,8) float32
  * = origin xyz, direction xyz, start, end (ray.py:4-18). */
 int rtgs_generate_rays(const rtgs_camera* cam, int device, float* rays, void* stream);

@@ -50,7 +50,12 @@ void free_scene(rtgs_scene* s) {
     cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
     cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
     cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
-    cudaFree(s->counters); cudaFree(s->stats_dev); cudaFree(s->stage_rgb); cudaFree(s->stage_T);
+    cudaFree(s->counters); cudaFree(s->stats_dev);
+    for (auto& hs : s->host_slot) {
+        cudaFree(hs.stage_rgb); cudaFree(hs.stage_T);
+        if (hs.done) cudaEventDestroy(hs.done);
+        if (hs.copied) cudaEventDestroy(hs.copied);
+    }
     if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
     if (s->pinned_T) cudaFreeHost(s->pinned_T);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
@@ -85,8 +90,16 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream2, cudaStreamNonBlocking));
-    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (RTGS_MAX_BANDS + 2) * sizeof(int), cudaHostAllocMapped));
+    // [0, MAX) band flags of host slot 0, [MAX] [MAX+1] the mirrors, [MAX+2, 2 MAX+2) band flags of host slot 1
+    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (2 * RTGS_MAX_BANDS + 2) * sizeof(int), cudaHostAllocMapped));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&s->band_flags_dev, s->band_flags, 0));
+    for (int k = 0; k < 2; ++k) {
+        const int off = k == 0 ? 0 : RTGS_MAX_BANDS + 2;
+        s->host_slot[k].flags = s->band_flags + off;
+        s->host_slot[k].flags_dev = s->band_flags_dev + off;
+        CUDA_TRY(cudaEventCreateWithFlags(&s->host_slot[k].done, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&s->host_slot[k].copied, cudaEventDisableTiming));
+    }
     TRY(dev_alloc(&s->band_done, RTGS_MAX_BANDS));
     s->band_flags[RTGS_MAX_BANDS] = 0;       // pool demand of the last finished frame (render.cu: ensure_lists)
     s->band_flags[RTGS_MAX_BANDS + 1] = 0;   // some finished frame had fallback tiles (render.cu: launch_render_k)
@@ -112,15 +125,15 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     return RTGS_OK;
 }
 
-int ensure_stage(rtgs_scene* s, size_t pixels) {
-    if (s->stage_pixels < pixels) {
-        cudaFree(s->stage_rgb);
-        cudaFree(s->stage_T);
-        s->stage_rgb = s->stage_T = nullptr;
-        s->stage_pixels = 0;
-        TRY(dev_alloc(&s->stage_rgb, pixels * 3));
-        TRY(dev_alloc(&s->stage_T, pixels));
-        s->stage_pixels = pixels;
+int ensure_stage(rtgs_scene::HostSlot& hs, size_t pixels) {
+    if (hs.stage_pixels < pixels) {
+        cudaFree(hs.stage_rgb);   // (synchronises with the device: no frame is reading it any more)
+        cudaFree(hs.stage_T);
+        hs.stage_rgb = hs.stage_T = nullptr;
+        hs.stage_pixels = 0;
+        TRY(dev_alloc(&hs.stage_rgb, pixels * 3));
+        TRY(dev_alloc(&hs.stage_T, pixels));
+        hs.stage_pixels = pixels;
     }
     return RTGS_OK;
 }
@@ -424,8 +437,8 @@ static void* pinned_device_ptr(const void* host) {
     return at.devicePointer;
 }
 
-int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
-                     int32_t depth, float t_cut, float* host_rgb, float* host_T) {
+static int check_host_render_args(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                                  int32_t depth, float t_cut, const float* host_rgb, const char* who) {
     RTGS_CHECK_ARG(s != nullptr);
     TRY(check_camera(cam));
     RTGS_CHECK_ARG(host_rgb != nullptr);
@@ -433,7 +446,155 @@ int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t 
     RTGS_CHECK_ARG(depth >= 1 && depth <= RTGS_MAX_DEPTH);
     RTGS_CHECK_ARG(t_cut >= 0.0f && t_cut < 1.0f);
     if (!s->built) {
-        rtgs_set_error("rtgs_render_host: call rtgs_scene_build_bvh first");
+        rtgs_set_error("%s: call rtgs_scene_build_bvh first", who);
+        return RTGS_ERR_STATE;
+    }
+    return RTGS_OK;
+}
+
+// Banded delivery, first half: launch the frame into a staging slot with the band flags armed.  Region columns
+// are contiguous in the (w,h,3) i-major buffer, so a band of macro-tile columns is one contiguous block.
+static int submit_banded(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                         int32_t depth, float t_cut, float* host_rgb, float* host_T) {
+    rtgs_scene::HostSlot& hs = s->host_slot[s->host_head];
+    TRY(ensure_stage(hs, (size_t)w * h));
+    const int mrows = (w + 31) / 32;                       // 32-pixel macro-tile columns of the region
+    const int bmc = (mrows + 23) / 24 > 0 ? (mrows + 23) / 24 : 1;
+    const int nb = (mrows + bmc - 1) / bmc;                // <= 24 bands (RTGS_MAX_BANDS 32)
+    static const int sched = getenv("RTGS_BAND_SCHEDULE") ? atoi(getenv("RTGS_BAND_SCHEDULE")) : 2;
+    for (int b = 0; b < nb; ++b) hs.flags[b] = 0;
+    static const bool nosignal = getenv("RTGS_BAND_NOSIGNAL") != nullptr;   // experiment: kernels do not count bands
+    s->bands_active = nosignal ? 0 : nb;
+    s->band_macro_cols = bmc;
+    s->band_schedule = sched;
+    s->band_flags_cur_dev = hs.flags_dev;
+    const int r = rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, hs.stage_rgb,
+                                     host_T ? hs.stage_T : nullptr, s->own_stream, false);
+    s->bands_active = 0;
+    s->band_flags_cur_dev = nullptr;
+    if (r != RTGS_OK) return r;
+    CUDA_TRY(cudaEventRecord(hs.done, s->own_stream));
+    hs.nb = nb; hs.bmc = bmc; hs.sched = sched; hs.w = w; hs.h = h;
+    hs.host_rgb = host_rgb; hs.host_T = host_T;
+    s->host_head ^= 1;
+    ++s->host_inflight;
+    return RTGS_OK;
+}
+
+// Banded delivery, second half, for the oldest frame in flight: the kernels raise a host-visible flag per
+// finished band and this thread queues that band's DMA while the later bands (and the next frame, if one has
+// been submitted) are still rendering.
+static int collect_banded(rtgs_scene* s) {
+    rtgs_scene::HostSlot& hs = s->host_slot[s->host_inflight == 2 ? s->host_head : s->host_head ^ 1];
+    --s->host_inflight;
+    const int nb = hs.nb, bmc = hs.bmc, w = hs.w, h = hs.h, mrows = (w + 31) / 32;
+    volatile int* flags = hs.flags;
+    static const bool dbg = getenv("RTGS_DEBUG_BANDS") != nullptr;
+    static int dbg_frame = 0;
+    struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
+    auto now_us = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - ts0.tv_sec) * 1e6 + (t.tv_nsec - ts0.tv_nsec) * 1e-3; };
+    double tflag[RTGS_MAX_BANDS];
+    int qi = 0;
+    for (int b = 0; b < nb; ++b) {
+        long spins = 0;
+        while (flags[b] == 0) {
+            if ((++spins & 0xfff) == 0 && cudaEventQuery(hs.done) != cudaErrorNotReady) break;   // done or failed
+        }
+        tflag[b] = now_us();
+        // the band's schedule positions -> macro-tile columns (edges inwards, render_common.cuh): at most two
+        // contiguous runs of columns
+        const int p0 = b * bmc, p1 = (b + 1) * bmc < mrows ? (b + 1) * bmc : mrows;
+        int lo[2] = {mrows, mrows}, hi[2] = {-1, -1};      // two runs: columns left / right of the middle
+        for (int p = p0; p < p1; ++p) {
+            const int col = rtgs_dev::macro_column(mrows, p, hs.sched), k = col * 2 >= mrows ? 1 : 0;
+            lo[k] = col < lo[k] ? col : lo[k];
+            hi[k] = col > hi[k] ? col : hi[k];
+        }
+        for (int k = 0; k < 2; ++k) {
+            if (hi[k] < 0) continue;
+            const size_t c0 = (size_t)lo[k] * 32, c1 = (size_t)(hi[k] + 1) * 32 < (size_t)w ? (size_t)(hi[k] + 1) * 32 : (size_t)w;
+            cudaStream_t cs = (qi++ & 1) ? s->copy_stream2 : s->copy_stream;
+            static const bool nocopy = getenv("RTGS_BAND_NOCOPY") != nullptr;   // experiment: no DMA at all
+            if (nocopy) continue;
+            CUDA_TRY(cudaMemcpyAsync(hs.host_rgb + c0 * h * 3, hs.stage_rgb + c0 * h * 3,
+                                     (c1 - c0) * h * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
+            if (hs.host_T)
+                CUDA_TRY(cudaMemcpyAsync(hs.host_T + c0 * h, hs.stage_T + c0 * h, (c1 - c0) * h * sizeof(float),
+                                         cudaMemcpyDeviceToHost, cs));
+        }
+    }
+    const double t_enq = now_us();
+    CUDA_TRY(cudaEventSynchronize(hs.done));
+    const double t_k = now_us();
+    CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
+    CUDA_TRY(cudaStreamSynchronize(s->copy_stream2));
+    if (dbg && ++dbg_frame == 20) {
+        fprintf(stderr, "bands %d: enq_done %.0f kernels_done %.0f copies_done %.0f us; flags:", nb, t_enq, t_k, now_us());
+        for (int b = 0; b < nb; ++b) fprintf(stderr, " %.0f", tflag[b]);
+        fprintf(stderr, "\n");
+    }
+    return RTGS_OK;
+}
+
+// Pipelined delivery (rtgs_render_host_submit / _collect).  With a second frame queued behind it, a frame's copy
+// does not have to start before the frame is finished: the render runs without band signalling (the per-tile
+// release + count costs k_shade_tiles 8 %) and ONE DMA of the whole image follows it on the copy stream, under
+// the next frame's render.  No host polling: _collect waits for the copy's event.
+static int submit_whole(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                        int32_t depth, float t_cut, float* host_rgb, float* host_T) {
+    rtgs_scene::HostSlot& hs = s->host_slot[s->host_head];
+    const size_t px = (size_t)w * h;
+    TRY(ensure_stage(hs, px));
+    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, hs.stage_rgb, host_T ? hs.stage_T : nullptr,
+                           s->own_stream, false));
+    CUDA_TRY(cudaEventRecord(hs.done, s->own_stream));
+    CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, hs.done, 0));
+    CUDA_TRY(cudaMemcpyAsync(host_rgb, hs.stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+    if (host_T)
+        CUDA_TRY(cudaMemcpyAsync(host_T, hs.stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
+    CUDA_TRY(cudaEventRecord(hs.copied, s->copy_stream));
+    hs.nb = 0;   // marks a whole-frame slot for _collect
+    s->host_head ^= 1;
+    ++s->host_inflight;
+    return RTGS_OK;
+}
+
+int rtgs_render_host_submit(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                            int32_t depth, float t_cut, float* host_rgb, float* host_T) {
+    TRY(check_host_render_args(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, "rtgs_render_host_submit"));
+    if (s->host_inflight >= 2) {
+        rtgs_set_error("rtgs_render_host_submit: two frames are in flight already; call rtgs_render_host_collect");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    if (!pinned_device_ptr(host_rgb) || (host_T && !pinned_device_ptr(host_T))) {
+        rtgs_set_error("rtgs_render_host_submit: the destination must be pinned host memory (rtgs_host_alloc)");
+        return RTGS_ERR_INVALID;
+    }
+    static const bool banded = getenv("RTGS_SUBMIT_BANDED") != nullptr;   // experiment: band pipeline here too
+    if (banded) return submit_banded(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, host_T);
+    return submit_whole(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, host_T);
+}
+
+int rtgs_render_host_collect(rtgs_scene* s) {
+    RTGS_CHECK_ARG(s != nullptr);
+    if (s->host_inflight <= 0) {
+        rtgs_set_error("rtgs_render_host_collect: no frame in flight");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    rtgs_scene::HostSlot& hs = s->host_slot[s->host_inflight == 2 ? s->host_head : s->host_head ^ 1];
+    if (hs.nb > 0) return collect_banded(s);
+    --s->host_inflight;
+    CUDA_TRY(cudaEventSynchronize(hs.copied));
+    return RTGS_OK;
+}
+
+int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                     int32_t depth, float t_cut, float* host_rgb, float* host_T) {
+    TRY(check_host_render_args(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, "rtgs_render_host"));
+    if (s->host_inflight != 0) {
+        rtgs_set_error("rtgs_render_host: %d submitted frame(s) not collected yet", s->host_inflight);
         return RTGS_ERR_STATE;
     }
     DeviceGuard g(s->device);
@@ -449,78 +610,22 @@ int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t 
         return RTGS_OK;
     }
     if (pinned && host_mode() == 2) {
-        // banded: region columns are contiguous in the (w,h,3) i-major buffer, so a band of macro-tile columns is
-        // one contiguous block; its DMA starts as soon as the kernels flag it complete
-        TRY(ensure_stage(s, px));
-        const int mrows = (w + 31) / 32;                       // 32-pixel macro-tile columns of the region
-        const int bmc = (mrows + 23) / 24 > 0 ? (mrows + 23) / 24 : 1;
-        const int nb = (mrows + bmc - 1) / bmc;                // <= 24 bands (RTGS_MAX_BANDS 32)
-        for (int b = 0; b < nb; ++b) s->band_flags[b] = 0;
-        s->bands_active = nb;
-        s->band_macro_cols = bmc;
-        static const int sched = getenv("RTGS_BAND_SCHEDULE") ? atoi(getenv("RTGS_BAND_SCHEDULE")) : 2;
-        s->band_schedule = sched;
-        const int r = rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, s->stage_rgb,
-                                         host_T ? s->stage_T : nullptr, st, false);
-        s->bands_active = 0;
-        if (r != RTGS_OK) return r;
-        volatile int* flags = s->band_flags;
-        static const bool dbg = getenv("RTGS_DEBUG_BANDS") != nullptr;
-        static int dbg_frame = 0;
-        struct timespec ts0; clock_gettime(CLOCK_MONOTONIC, &ts0);
-        auto now_us = [&]() { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return (t.tv_sec - ts0.tv_sec) * 1e6 + (t.tv_nsec - ts0.tv_nsec) * 1e-3; };
-        double tflag[RTGS_MAX_BANDS];
-        int qi = 0;
-        for (int b = 0; b < nb; ++b) {
-            long spins = 0;
-            while (flags[b] == 0) {
-                if ((++spins & 0xfff) == 0 && cudaStreamQuery(st) != cudaErrorNotReady) break;   // done or failed
-            }
-            tflag[b] = now_us();
-            // the band's schedule positions -> macro-tile columns (edges inwards, render_common.cuh): at most two
-            // contiguous runs of columns
-            const int p0 = b * bmc, p1 = (b + 1) * bmc < mrows ? (b + 1) * bmc : mrows;
-            int lo[2] = {mrows, mrows}, hi[2] = {-1, -1};      // two runs: columns left / right of the middle
-            for (int p = p0; p < p1; ++p) {
-                const int col = rtgs_dev::macro_column(mrows, p, sched), k = col * 2 >= mrows ? 1 : 0;
-                lo[k] = col < lo[k] ? col : lo[k];
-                hi[k] = col > hi[k] ? col : hi[k];
-            }
-            for (int k = 0; k < 2; ++k) {
-                if (hi[k] < 0) continue;
-                const size_t c0 = (size_t)lo[k] * 32, c1 = (size_t)(hi[k] + 1) * 32 < (size_t)w ? (size_t)(hi[k] + 1) * 32 : (size_t)w;
-                cudaStream_t cs = (qi++ & 1) ? s->copy_stream2 : s->copy_stream;
-                CUDA_TRY(cudaMemcpyAsync(host_rgb + c0 * h * 3, s->stage_rgb + c0 * h * 3,
-                                         (c1 - c0) * h * 3 * sizeof(float), cudaMemcpyDeviceToHost, cs));
-                if (host_T)
-                    CUDA_TRY(cudaMemcpyAsync(host_T + c0 * h, s->stage_T + c0 * h, (c1 - c0) * h * sizeof(float),
-                                             cudaMemcpyDeviceToHost, cs));
-            }
-        }
-        const double t_enq = now_us();
-        CUDA_TRY(cudaStreamSynchronize(st));
-        const double t_k = now_us();
-        CUDA_TRY(cudaStreamSynchronize(s->copy_stream));
-        CUDA_TRY(cudaStreamSynchronize(s->copy_stream2));
-        if (dbg && ++dbg_frame == 20) {
-            fprintf(stderr, "bands %d: enq_done %.0f kernels_done %.0f copies_done %.0f us; flags:", nb, t_enq, t_k, now_us());
-            for (int b = 0; b < nb; ++b) fprintf(stderr, " %.0f", tflag[b]);
-            fprintf(stderr, "\n");
-        }
-        return RTGS_OK;
+        TRY(submit_banded(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, host_T));
+        return collect_banded(s);
     }
-    TRY(ensure_stage(s, px));
-    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, s->stage_rgb, host_T ? s->stage_T : nullptr, st,
+    rtgs_scene::HostSlot& hs = s->host_slot[0];
+    TRY(ensure_stage(hs, px));
+    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, hs.stage_rgb, host_T ? hs.stage_T : nullptr, st,
                            false));
     if (pinned) {
-        CUDA_TRY(cudaMemcpyAsync(host_rgb, s->stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-        if (host_T) CUDA_TRY(cudaMemcpyAsync(host_T, s->stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpyAsync(host_rgb, hs.stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+        if (host_T) CUDA_TRY(cudaMemcpyAsync(host_T, hs.stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         return RTGS_OK;
     }
     TRY(ensure_pinned(s, px));
-    CUDA_TRY(cudaMemcpyAsync(s->pinned_rgb, s->stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
-    if (host_T) CUDA_TRY(cudaMemcpyAsync(s->pinned_T, s->stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(s->pinned_rgb, hs.stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    if (host_T) CUDA_TRY(cudaMemcpyAsync(s->pinned_T, hs.stage_T, px * sizeof(float), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
     memcpy(host_rgb, s->pinned_rgb, px * 3 * sizeof(float));
     if (host_T) memcpy(host_T, s->pinned_T, px * sizeof(float));

@@ -93,9 +93,23 @@ struct rtgs_scene {
     int64_t opt_pool_chunks = -1;             // RTGS_OPT_LIST_POOL_CHUNKS (-1 = default sizing)
     int opt_stripe_mod = 1, opt_stripe_rem = 0;   // RTGS_OPT_STRIPE
     int opt_render_mode = -1;                 // RTGS_OPT_RENDER_MODE (-1 = RTGS_RENDER_MODE env or 0)
-    float* stage_rgb = nullptr;               // device staging for rtgs_render_host
-    float* stage_T = nullptr;
-    size_t stage_pixels = 0;
+    // rtgs_render_host: device staging + band flags, double-buffered so that two frames can be in flight
+    // (rtgs_render_host_submit / _collect: frame f+1 renders while the last bands of frame f are copied out)
+    struct HostSlot {
+        float* stage_rgb = nullptr;
+        float* stage_T = nullptr;
+        size_t stage_pixels = 0;
+        int* flags = nullptr;                 // this slot's part of band_flags (host / device alias)
+        int* flags_dev = nullptr;
+        cudaEvent_t done = nullptr;           // recorded behind the frame's last kernel
+        cudaEvent_t copied = nullptr;         // recorded behind the frame's whole-image DMA (pipelined delivery)
+        int nb = 0, bmc = 0, sched = 0, w = 0, h = 0;
+        float* host_rgb = nullptr;
+        float* host_T = nullptr;
+    };
+    HostSlot host_slot[2];
+    int host_head = 0, host_inflight = 0;     // next slot to submit into; frames submitted and not collected
+    int* band_flags_cur_dev = nullptr;        // flags of the frame being launched (set around rtgs_launch_render)
     float* pinned_rgb = nullptr;
     float* pinned_T = nullptr;
     size_t pinned_pixels = 0;

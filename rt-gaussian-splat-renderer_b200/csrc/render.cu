@@ -82,8 +82,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
 
     if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0) {
         // pool demand of this frame (for the host's sizing) and whether any frame so far needed the fallback
-        *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
-        if (P.counters[CTR_FALLBACK] != 0) *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS + 1) = 1;
+        *reinterpret_cast<volatile int*>(P.mirror) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
+        if (P.counters[CTR_FALLBACK] != 0) *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
     }
 
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
@@ -606,7 +606,8 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
     P.macro_rows = mrows;
     P.schedule = s->bands_active > 0 ? s->band_schedule : 0;
     P.band_done = s->band_done;
-    P.band_flags = s->band_flags_dev;
+    P.band_flags = s->band_flags_cur_dev ? s->band_flags_cur_dev : s->band_flags_dev;
+    P.mirror = s->band_flags_dev + RTGS_MAX_BANDS;
     if (s->bands_active > 0) {
         P.nbands = s->bands_active;
         P.band_macro_cols = s->band_macro_cols;

@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                 // it has been written yet, so `accumulate` outputs stay correct
                 if (lane == 0) {
                     P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
-                    *reinterpret_cast<volatile int*>(P.band_flags + RTGS_MAX_BANDS + 1) = 1;
+                    *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
                 }
                 continue;
             }

@@ -106,6 +106,13 @@ def main(argv=None) -> int:
         [(2 * np.pi * k / args.views, f"view_{k:03d}") for k in views_for_rank(args.views, rank, world)]
     args.out.mkdir(parents=True, exist_ok=True)
     t0 = time.perf_counter()
+    if args.sample == 1 and len(poses) > 1:
+        # one sample per view: the display buffer is the sample itself, so the sweep can run through the two-deep
+        # pipeline (RayTracer.sweep: view k+1 renders while view k is copied out and written)
+        for k, img in tracer.sweep([orbit_pose(theta, args.phi, args.radius) for theta, _ in poses], args.depth):
+            for f in write_image(args.out / poses[k][1], img, args.format):
+                logger.info("wrote %s", f)
+        poses_done, poses = poses, []
     for theta, name in poses:
         camera.position, camera.rotation = orbit_pose(theta, args.phi, args.radius)
         tracer.clear_sample()                                   # __main__.py:214-216 on a camera move
@@ -116,6 +123,8 @@ def main(argv=None) -> int:
         for f in write_image(args.out / name, tracer.disp_buf.to_numpy(), args.format):
             logger.info("wrote %s", f)
     dt = time.perf_counter() - t0
+    if args.sample == 1 and not poses:
+        poses = poses_done
     if poses:
         logger.info("rank %d: %d view(s) of %dx%d in %.3f s incl. image output", rank, len(poses), res[0], res[1], dt)
     return 0

@@ -63,6 +63,9 @@ SIGNATURES = {
     "rtgs_ipc_close": (C.c_int, [C.c_int, _vp]),
     "rtgs_render_host": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                    C.c_int32, C.c_float, _vp, _vp]),
+    "rtgs_render_host_submit": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_int32, C.c_float, _vp, _vp]),
+    "rtgs_render_host_collect": (C.c_int, [_vp]),
     "rtgs_generate_rays": (C.c_int, [C.POINTER(rtgs_camera), C.c_int, _vp, _vp]),
     "rtgs_trace_closest": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "rtgs_scene_destroy": (C.c_int, [_vp]),

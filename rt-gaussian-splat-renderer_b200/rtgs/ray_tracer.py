@@ -20,6 +20,27 @@ from .utils.types import vec2i
 MAX_DEPTH = 32  # RTGS_MAX_DEPTH
 
 
+class PendingFrame:
+    """A frame queued by ``RayTracer.render_async``.  Frames complete in submission order: ``result()``
+    first collects every older frame of the same scene."""
+
+    def __init__(self, scene, out):
+        self._scene = scene
+        self._out = out
+        self.done = False
+
+    def result(self):
+        pending = self._scene._pending
+        while not self.done:
+            head = pending[0]
+            try:
+                _native.check(_native.load().rtgs_render_host_collect(self._scene.handle))
+            finally:
+                pending.popleft()
+                head.done = True
+        return self._out
+
+
 class RayTracer:
     """RayTracer(buf_size, scene, camera) — ray_tracer.py:25-37.
 
@@ -43,6 +64,8 @@ class RayTracer:
         self.num_samples = 0
         self.last_stats = None
         self._pinned = None
+        self._async_ring = None
+        self._async_next = 0
 
     # ------------------------------------------------------------------ reference API
     def sample(self, depth: int):
@@ -109,9 +132,60 @@ class RayTracer:
         elif out.shape != (w, h, 3) or out.dtype != np.float32 or not out.flags.c_contiguous:
             raise ValueError("out must be a C-contiguous float32 array of shape (w, h, 3)")
         cam = self.camera.native()
+        self.scene.drain_pending()
         _native.check(_native.load().rtgs_render_host(self.scene.handle, cam, x0, y0, w, h, int(depth), self.t_cut,
                                                       out.ctypes.data, None))
         return out
+
+    def render_async(self, depth: int = 16, tile=None):
+        """``render()`` without the wait: queue the frame of the CURRENT camera pose and return a
+        ``PendingFrame``; its ``result()`` is the (w,h,3) host image.  Two frames may be in flight per
+        scene, so in a sweep frame f+1 renders while the tail of frame f crosses PCIe::
+
+            prev = None
+            for pose in poses:
+                camera.position, camera.rotation = pose
+                cur = tracer.render_async(16)
+                if prev is not None:
+                    use(prev.result())
+                prev = cur
+            use(prev.result())
+
+        The image lands in one of three pinned buffers owned by this RayTracer, used in turn: a result
+        stays valid until the third ``render_async`` after its own."""
+        W, H = self.buf_size.x, self.buf_size.y
+        x0, y0, w, h = (0, 0, W, H) if tile is None else tile
+        ring = self._async_ring
+        if not ring or ring[0].shape != (w, h, 3):
+            self.scene.drain_pending()
+            ring = self._async_ring = [_native.PinnedBuffer((w, h, 3)) for _ in range(3)]
+            self._async_next = 0
+        buf = ring[self._async_next]
+        self._async_next = (self._async_next + 1) % len(ring)
+        out = buf.view()
+        pending = self.scene._pending
+        while len(pending) >= 2:          # the library holds two frames at most
+            pending[0].result()
+        cam = self.camera.native()
+        _native.check(_native.load().rtgs_render_host_submit(self.scene.handle, cam, x0, y0, w, h, int(depth),
+                                                             self.t_cut, out.ctypes.data, None))
+        frame = PendingFrame(self.scene, out)
+        pending.append(frame)
+        return frame
+
+    def sweep(self, poses, depth: int = 16):
+        """Render ``poses`` (an iterable of (position, rotation)) through the two-deep pipeline and yield
+        ``(index, image)`` in order; the image is valid until the next-but-one iteration."""
+        prev = None
+        k = -1
+        for k, (pos, rot) in enumerate(poses):
+            self.camera.position, self.camera.rotation = pos, rot
+            cur = self.render_async(depth)
+            if prev is not None:
+                yield k - 1, prev.result()
+            prev = cur
+        if prev is not None:
+            yield k, prev.result()
 
     def render_device(self, depth: int = 16, tile=None, out=None, out_T=None, collect_stats: bool = False):
         """Render into device memory (a torch CUDA tensor) on the current stream; no host copy."""

@@ -7,6 +7,7 @@ builder (scene.py:162-404) is replaced by a GPU LBVH (csrc/lbvh.cu).  There is n
 """
 from __future__ import annotations
 
+import collections
 import ctypes as C
 import logging
 import pathlib
@@ -71,6 +72,7 @@ class Scene:
         self._bvh_field = None
         self._lbvh = None
         self.has_sh = False
+        self._pending = collections.deque()   # frames queued by RayTracer.render_async, oldest first
 
     # ------------------------------------------------------------------ construction
     def load_file(self, path: pathlib.Path, scale: float = 1, sh_layout: str = "channel_major",
@@ -159,8 +161,14 @@ class Scene:
         _native.check(_native.load().rtgs_scene_build_bvh(self._handle, int(self.leaf_prim)))
         logger.info(f"Build {2 * self._n - 1} BVH nodes in total. Max leaf node size is 1.")
 
+    def drain_pending(self):
+        """Collect every frame queued by ``RayTracer.render_async`` (the synchronous calls do this first)."""
+        while self._pending:
+            self._pending[0].result()
+
     def _release(self):
         if self._handle is not None:
+            self._pending.clear()
             _native.load().rtgs_scene_destroy(self._handle)
             self._handle = None
 

@@ -49,3 +49,9 @@ def test_cli_renders_the_reference_scene(tmp_path, test_ply):
     assert main(["-o", str(test_ply), "-r", "64,48", "--scale", "30", "--views", "4", "--out", str(tmp_path / "sweep"),
                  "--format", "npy"]) == 0
     assert sorted(p.name for p in (tmp_path / "sweep").iterdir()) == [f"view_{k:03d}.npy" for k in range(4)]
+    # (one sample per view: the sweep went through the pipelined RayTracer.sweep) every view is its own pose
+    f = focal_from_fov(48, 90.0)
+    for k in (1, 3):
+        pos, rot = orbit_pose(2 * np.pi * k / 4, np.pi / 2, 1.0)
+        ref = O.render(gs, O.CameraParams(np.asarray(pos), np.asarray(rot), 64, 48, (f, f)), depth=16)["rgb"]
+        assert np.abs(np.load(tmp_path / "sweep" / f"view_{k:03d}.npy") - ref).max() <= 1e-3
