@@ -64,6 +64,8 @@ def parse_args():
                     help="diagnostic: expected ellipsoid crossings per cube-spanning ray of the synthetic scene "
                          "(default 16, SURVEY.md 8d); larger = bigger Gaussians, denser tiles")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true",
+                    help="multi-GPU: do not pin each rank to the CPU cores next to its GPU")
     ap.add_argument("--cpu-stride", type=int, default=0, help="pixel subsample stride of the CPU legs (0 = auto)")
     return ap.parse_args()
 
@@ -215,6 +217,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    from rtgs.sharding import bind_to_gpu_numa_node
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {"bound": False,
+                                                                                         "why": "not requested"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -424,6 +429,7 @@ def main():
                             "useful_candidates_per_tile": agg["useful_candidates"] / max(agg["tiles"], 1),
                             "fallback_tiles": agg["fallback_tiles"]},
             "bvh_build_ms": build_ms,
+            "numa_bind_rank0": numa,
         }
         if tiles:
             line["tiles_verified_bit_identical"] = tiles_verified

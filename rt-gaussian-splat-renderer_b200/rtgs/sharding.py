@@ -9,6 +9,38 @@ TILE_COLUMNS = 32   # tile = 32 pixel columns x full height: contiguous in the (
 STRIPE_COLUMNS = TILE_COLUMNS   # = the kernels' macro-tile width (RTGS_OPT_STRIPE)
 
 
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """Pin the calling process to the CPU cores next to GPU ``device_index`` (NVML's ideal-CPU mask for the
+    device, i.e. its NUMA node), so that the pinned host image buffers it allocates afterwards are local to the
+    GPU's PCIe root and eight ranks do not pile their framebuffer copies onto one socket.  Call before the first
+    pinned allocation.  Never raises: returns {"bound": False, "why": ...} when NVML or the mask is
+    unavailable."""
+    import os
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus &= allowed
+        if not cpus:
+            return {"bound": False, "why": "empty NVML affinity mask within the allowed CPUs"}
+        if cpus == allowed:
+            return {"bound": False, "why": "single NUMA domain (mask = all allowed CPUs)", "cpus": len(cpus)}
+        os.sched_setaffinity(0, cpus)
+        return {"bound": True, "cpus": len(cpus), "first_cpu": min(cpus)}
+    except Exception as e:   # no NVML, no permission, ...: rendering does not depend on it
+        return {"bound": False, "why": f"{type(e).__name__}: {e}"}
+
+
 def views_for_rank(n_views: int, rank: int, world: int) -> list[int]:
     """View k -> rank k mod world."""
     return list(range(rank, n_views, world))
