@@ -61,6 +61,7 @@ void free_scene(rtgs_scene* s) {
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->copy_stream2) cudaStreamDestroy(s->copy_stream2);
+    if (s->scratch_free) cudaEventDestroy(s->scratch_free);
     cudaFree(s->band_done);
     if (s->band_flags) cudaFreeHost(s->band_flags);
     for (cudaEvent_t e : s->timing_events) cudaEventDestroy(e);

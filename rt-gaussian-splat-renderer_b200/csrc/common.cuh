@@ -109,6 +109,9 @@ struct rtgs_scene {
     };
     HostSlot host_slot[2];
     int host_head = 0, host_inflight = 0;     // next slot to submit into; frames submitted and not collected
+    cudaEvent_t scratch_free = nullptr;       // behind the last frame's kernels (render.cu: rtgs_launch_render)
+    cudaStream_t scratch_stream = nullptr;    // the stream that frame was launched on
+    bool scratch_used = false;
     int* band_flags_cur_dev = nullptr;        // flags of the frame being launched (set around rtgs_launch_render)
     float* pinned_rgb = nullptr;
     float* pinned_T = nullptr;

@@ -97,6 +97,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             tile = (int)atomicAdd(P.counters + CTR_WORK3, 1u);
             if (P.use_fallback_list && tile < nwork) tile = P.fallback_tiles[tile];
             else if (P.use_fallback_list) tile = P.ntiles;
+            else tile = work_to_id(P, tile, P.macro_cols * TILES_PER_MACRO, P.ntiles);
         }
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
@@ -569,9 +570,33 @@ int ensure_lists(rtgs_scene* s, int ntiles) {
 
 }  // namespace
 
+static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
+                            float t_cut, int accumulate, int full_pitch, float* out_rgb, float* out_T,
+                            cudaStream_t stream, bool want_stats);
+
+// A scene's render scratch (work counters, candidate lists, band counters) is shared by all its frames, which is
+// safe in stream order.  A frame launched on ANOTHER stream than the previous one (rtgs_render on the caller's
+// stream, then rtgs_render_host on the library's) first waits for that frame's kernels.
 int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
                        float t_cut, int accumulate, int full_pitch, float* out_rgb, float* out_T,
                        cudaStream_t stream, bool want_stats) {
+    if (!s->scratch_free) CUDA_TRY(cudaEventCreateWithFlags(&s->scratch_free, cudaEventDisableTiming));
+    if (s->scratch_used && s->scratch_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, s->scratch_free, 0));
+    const int r = launch_render_on(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_pitch, out_rgb, out_T, stream,
+                                   want_stats);
+    // (also after a failed launch sequence: whatever was queued still uses the scratch)
+    if (cudaEventRecord(s->scratch_free, stream) == cudaSuccess) {
+        s->scratch_stream = stream;
+        s->scratch_used = true;
+    } else {
+        cudaGetLastError();
+    }
+    return r;
+}
+
+static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
+                            float t_cut, int accumulate, int full_pitch, float* out_rgb, float* out_T,
+                            cudaStream_t stream, bool want_stats) {
     RenderParams P;
     P.nodes = s->nodes;
     P.nodes4 = s->nodes4;

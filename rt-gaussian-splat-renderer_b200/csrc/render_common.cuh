@@ -124,6 +124,18 @@ __device__ __forceinline__ int macro_column(const RenderParams& P, int pos) {
     return macro_column(P.macro_rows, pos, P.schedule);
 }
 
+// Work item k of a launch -> tile / group id (>= `total` when the launch is exhausted).  per_col = ids per
+// macro-tile column.  A stripe-sharded launch (RTGS_OPT_STRIPE) enumerates only the columns it owns: pulling
+// and skipping the foreign ids costs an atomic round trip each, and with 7/8 of them foreign that was most of
+// k_tile_lists at 8 GPUs.  (Banded launches and the rotated schedules keep the plain order: their band counters
+// expect every id to be reported.)
+__device__ __forceinline__ int work_to_id(const RenderParams& P, int k, int per_col, int total) {
+    if (P.stripe_mod <= 1 || P.schedule != 0 || P.nbands > 0) return k;
+    const int c = k / per_col;
+    const int mi = P.stripe_rem + c * P.stripe_mod;
+    return mi < P.macro_rows ? mi * per_col + (k - c * per_col) : total;
+}
+
 // Returns false for a group outside this launch's stripe (its macro-tile column belongs to another GPU).
 __device__ __forceinline__ bool group_origin(const RenderParams& P, int group, int& gi0, int& gj0) {
     const int macro = group / GROUPS_PER_MACRO, lg = group % GROUPS_PER_MACRO;

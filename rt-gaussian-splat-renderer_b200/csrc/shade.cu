@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(P.counters + CTR_WORK2, 1u);
-        tile = __shfl_sync(FULL, tile, 0);
+        tile = work_to_id(P, __shfl_sync(FULL, tile, 0), P.macro_cols * TILES_PER_MACRO, P.ntiles);
         if (tile >= P.ntiles) break;
         int i0, j0;
         if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {

@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
     for (;;) {
         int group = 0;
         if (lane == 0) group = (int)atomicAdd(P.counters + CTR_WORK, 1u);
-        group = __shfl_sync(FULL, group, 0);
+        group = work_to_id(P, __shfl_sync(FULL, group, 0), P.macro_cols * GROUPS_PER_MACRO, P.ntiles / TILES_PER_GROUP);
         if (group * TILES_PER_GROUP >= P.ntiles) break;
         int gi0, gj0;
         if (!group_origin(P, group, gi0, gj0) || gi0 >= xe || gj0 >= ye) continue;

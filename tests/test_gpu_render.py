@@ -332,6 +332,37 @@ def test_pipelined_sweep_is_bit_identical_to_synchronous_renders():
     assert _native.load().rtgs_render_host_collect(scene.handle) == -3
 
 
+def test_renders_on_different_streams_share_the_scene_scratch_safely():
+    """rtgs_render runs on the caller's stream, rtgs_render_host on the library's; both use the scene's work
+    counters and candidate lists.  Back-to-back calls without a synchronisation in between must not overlap."""
+    import torch
+    from rtgs.orbit import orbit_pose
+    from rtgs.ray_tracer import RayTracer
+    gs = random_set(30000, seed=5, mean_scale=0.02)
+    scene = make_scene(gs)
+    cam, _ = make_camera(0.0, 1.3, 2.4, 640, 360)
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    poses = [orbit_pose(0.9 * k, 1.3, 2.4) for k in range(4)]
+    want = []
+    for pos, rot in poses:
+        cam.position, cam.rotation = pos, rot
+        want.append(rt.render(16).copy())
+    side = torch.cuda.Stream()
+    for rep in range(3):
+        cam.position, cam.rotation = poses[0]
+        a = rt.render_device(16)                 # current stream, asynchronous
+        cam.position, cam.rotation = poses[1]
+        b = rt.render(16).copy()                 # library stream, at once
+        cam.position, cam.rotation = poses[2]
+        with torch.cuda.stream(side):
+            c = rt.render_device(16)             # a third stream
+        cam.position, cam.rotation = poses[3]
+        d = rt.render_async(16)
+        torch.cuda.synchronize()
+        assert np.array_equal(a.cpu().numpy(), want[0]) and np.array_equal(b, want[1])
+        assert np.array_equal(c.cpu().numpy(), want[2]) and np.array_equal(d.result(), want[3])
+
+
 def test_device_ply_ingest_matches_host_loader(test_ply):
     from rtgs.scene import Scene
     a = Scene().load_file(test_ply, 30.0).read_gaussians()
