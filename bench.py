@@ -428,7 +428,8 @@ def main():
                             "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1),
                             "useful_candidates_per_tile": agg["useful_candidates"] / max(agg["tiles"], 1),
                             "fallback_tiles": agg["fallback_tiles"]},
-            "bvh_build_ms": build_ms,
+            "bvh_build_ms": scene.build_ms,          # device time of the LBVH build kernels
+            "scene_load_ms": build_ms,               # wall: upload of the arrays + build (+ CUDA start-up on first use)
             "numa_bind_rank0": numa,
         }
         if tiles:

@@ -94,6 +94,9 @@ int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices
  * gaussian.py:86-138), 30-bit Morton codes, radix sort, Karras hierarchy, bottom-up refit.
  * leaf_size is accepted for Scene(leaf_prim=...) compatibility (scene.py:78-87). */
 int rtgs_scene_build_bvh(rtgs_scene* s, int32_t leaf_size);
+/* Device time of that build in milliseconds (CUDA events around its kernels: bounds, Morton codes, radix sort,
+ * Karras, packing, refit).  The reference logs its own build time per node (scene.py:398-404). */
+int rtgs_scene_build_ms(const rtgs_scene* s, float* ms);
 
 int rtgs_scene_num_gaussians(const rtgs_scene* s, int64_t* n);
 int rtgs_scene_device(const rtgs_scene* s, int* device);

@@ -259,6 +259,16 @@ int rtgs_scene_build_bvh(rtgs_scene* s, int32_t leaf_size) {
     return r;
 }
 
+int rtgs_scene_build_ms(const rtgs_scene* s, float* ms) {
+    RTGS_CHECK_ARG(s != nullptr && ms != nullptr);
+    if (!s->built) {
+        rtgs_set_error("rtgs_scene_build_ms: call rtgs_scene_build_bvh first");
+        return RTGS_ERR_STATE;
+    }
+    *ms = s->build_ms;
+    return RTGS_OK;
+}
+
 int rtgs_scene_num_gaussians(const rtgs_scene* s, int64_t* n) {
     RTGS_CHECK_ARG(s && n);
     *n = s->n;

@@ -81,6 +81,7 @@ struct rtgs_scene {
     float4* leafbox = nullptr;   // n*2: leaf box (centre, half extent) by sorted position
     float4* nodes4 = nullptr;    // num_nodes*8: two-level nodes (records of both children), k_tile_lists
     int64_t num_nodes = 0;  // max(n-1, 1)
+    float build_ms = 0.0f;  // device time of the last LBVH build (Morton codes ... packed nodes)
 
     // render scratch
     unsigned int* counters = nullptr;         // 8: work counters, pool cursor, fallback count

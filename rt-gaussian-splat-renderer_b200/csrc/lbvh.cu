@@ -98,17 +98,25 @@ k_rs_hist(const uint64_t* __restrict__ keys, int64_t n, int shift, uint32_t* __r
     for (int b = threadIdx.x; b < RS_BINS; b += blockDim.x) hist[(int64_t)b * ntiles + blockIdx.x] = sh[b];
 }
 
-// single-block exclusive scan over `len` uint32 (len = 256 * ntiles)
+// single-block exclusive scan over `len` uint32 (len = 256 * ntiles): every thread scans SCAN_ITEMS consecutive
+// values serially, the block scans the per-thread totals (8192 values per iteration)
+constexpr int SCAN_ITEMS = 8;
 __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ data, int64_t len) {
     __shared__ uint32_t warp_tot[32];
     __shared__ uint32_t carry_sh;
     if (threadIdx.x == 0) carry_sh = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int64_t base = 0; base < len; base += 1024) {
-        int64_t i = base + threadIdx.x;
-        uint32_t v = i < len ? data[i] : 0u;
-        uint32_t x = v;
+    for (int64_t base = 0; base < len; base += 1024 * SCAN_ITEMS) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * SCAN_ITEMS;
+        uint32_t v[SCAN_ITEMS];
+        uint32_t sum = 0;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            v[k] = i0 + k < len ? data[i0 + k] : 0u;
+            sum += v[k];
+        }
+        uint32_t x = sum;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
@@ -127,9 +135,13 @@ __global__ void __launch_bounds__(1024) k_rs_scan(uint32_t* __restrict__ data, i
             warp_tot[lane] = s - w;  // exclusive warp offsets
         }
         __syncthreads();
-        uint32_t carry = carry_sh;
-        uint32_t incl = x + warp_tot[wid] + carry;
-        if (i < len) data[i] = incl - v;
+        const uint32_t incl = x + warp_tot[wid] + carry_sh;   // inclusive over this thread's values
+        uint32_t run = incl - sum;
+#pragma unroll
+        for (int k = 0; k < SCAN_ITEMS; ++k) {
+            if (i0 + k < len) data[i0 + k] = run;
+            run += v[k];
+        }
         __syncthreads();
         if (threadIdx.x == 1023) carry_sh = incl;
         __syncthreads();
@@ -414,6 +426,11 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     CUDA_TRY(cudaMalloc(&hist.p, (size_t)RS_BINS * ntiles * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&visit.p, (size_t)(n > 1 ? n - 1 : 1) * sizeof(unsigned int)));
 
+    cudaEvent_t e0 = nullptr, e1 = nullptr;   // device time of the build proper (rtgs_scene_build_ms)
+    CUDA_TRY(cudaEventCreate(&e0));
+    CUDA_TRY(cudaEventCreate(&e1));
+    struct EventGuard { cudaEvent_t &a, &b; ~EventGuard() { cudaEventDestroy(a); cudaEventDestroy(b); } } eg{e0, e1};
+    CUDA_TRY(cudaEventRecord(e0, st));
     const int TB = 256;
     const int nb = (int)((n + TB - 1) / TB);
     k_init_bounds<<<1, 32, 0, st>>>(bnd.p);
@@ -450,9 +467,11 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     k_pack_nodes<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->child, s->aabb, s->nodes);
     k_pack_nodes4<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->nodes, s->leafbox, s->nodes4);
     CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(e1, st));
     unsigned int hb[6];
     CUDA_TRY(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    CUDA_TRY(cudaEventElapsedTime(&s->build_ms, e0, e1));
     for (int a = 0; a < 6; ++a) s->bounds[a] = ordered_to_float(hb[a]);
     return RTGS_OK;
 }

@@ -45,6 +45,7 @@ SIGNATURES = {
     "rtgs_scene_create_from_ply_rows": (C.c_int, [C.c_int, C.c_int64, _vp, C.c_int32, _vp, C.c_float,
                                                   C.c_int32, C.POINTER(_vp)]),
     "rtgs_scene_build_bvh": (C.c_int, [_vp, C.c_int32]),
+    "rtgs_scene_build_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
     "rtgs_scene_num_gaussians": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rtgs_scene_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rtgs_scene_read_lbvh": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),

@@ -159,7 +159,8 @@ class Scene:
         self.has_sh = bool(has_sh)
         self._gaussian_field = self._bvh_field = self._lbvh = None
         _native.check(_native.load().rtgs_scene_build_bvh(self._handle, int(self.leaf_prim)))
-        logger.info(f"Build {2 * self._n - 1} BVH nodes in total. Max leaf node size is 1.")
+        logger.info(f"Build {2 * self._n - 1} BVH nodes in total ({self.build_ms:.2f} ms on the device). "
+                    "Max leaf node size is 1.")
 
     def drain_pending(self):
         """Collect every frame queued by ``RayTracer.render_async`` (the synchronous calls do this first)."""
@@ -184,6 +185,13 @@ class Scene:
         if self._handle is None:
             raise RuntimeError("scene is empty: call load_file() or from_arrays() first")
         return self._handle
+
+    @property
+    def build_ms(self) -> float:
+        """Device time of the LBVH build (ms)."""
+        ms = C.c_float()
+        _native.check(_native.load().rtgs_scene_build_ms(self.handle, C.byref(ms)))
+        return float(ms.value)
 
     @property
     def num_gaussians(self) -> int:
