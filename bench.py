@@ -63,6 +63,12 @@ def parse_args():
     ap.add_argument("--h-target", type=float, default=None,
                     help="diagnostic: expected ellipsoid crossings per cube-spanning ray of the synthetic scene "
                          "(default 16, SURVEY.md 8d); larger = bigger Gaussians, denser tiles")
+    ap.add_argument("--morton-bits", type=int, default=0, choices=[0, 30, 63],
+                    help="LBVH code width: 0 = automatic (30, the north-star spec, unless the codes are degenerate), "
+                         "30, 63 (the wide variant for scenes with outliers)")
+    ap.add_argument("--outliers", type=int, default=0,
+                    help="diagnostic: move this many Gaussians ~4000 scene radii away (what stray points of a "
+                         "trained scene do to 10-bit-per-axis Morton codes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-numa-bind", action="store_true",
                     help="multi-GPU: do not pin each rank to the CPU cores next to its GPU")
@@ -232,9 +238,15 @@ def main():
     arrays = make_scene(n_g, seed, sh_deg) if args.h_target is None else make_scene(n_g, seed, sh_deg, args.h_target)
     if args.h_target is not None:
         config["workload"] += f" [diagnostic: h_target {args.h_target}]"
+    if args.outliers > 0:
+        rng = np.random.default_rng(99)
+        arrays["pos"][:args.outliers] = (rng.uniform(-1, 1, (args.outliers, 3)) * 4000.0).astype(np.float32)
+        config["workload"] += f" [diagnostic: {args.outliers} outliers at ~4000 scene radii]"
+    if args.morton_bits == 63:
+        config["workload"] += " [LBVH with 63-bit Morton codes]"
     focal, views = make_views(W, H)
     t0 = time.perf_counter()
-    scene = Scene(device=local_rank).from_arrays(arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"],
+    scene = Scene(device=local_rank, morton_bits=args.morton_bits or "auto").from_arrays(arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"],
                                                  arrays["opacity"], arrays["sh"])
     torch.cuda.synchronize()
     build_ms = 1e3 * (time.perf_counter() - t0)
@@ -429,6 +441,7 @@ def main():
                             "useful_candidates_per_tile": agg["useful_candidates"] / max(agg["tiles"], 1),
                             "fallback_tiles": agg["fallback_tiles"]},
             "bvh_build_ms": scene.build_ms,          # device time of the LBVH build kernels
+            "morton_bits": scene.morton_bits,
             "scene_load_ms": build_ms,               # wall: upload of the arrays + build (+ CUDA start-up on first use)
             "numa_bind_rank0": numa,
         }

@@ -97,6 +97,7 @@ int rtgs_scene_build_bvh(rtgs_scene* s, int32_t leaf_size);
 /* Device time of that build in milliseconds (CUDA events around its kernels: bounds, Morton codes, radix sort,
  * Karras, packing, refit).  The reference logs its own build time per node (scene.py:398-404). */
 int rtgs_scene_build_ms(const rtgs_scene* s, float* ms);
+int rtgs_scene_morton_bits(const rtgs_scene* s, int32_t* bits /* 30 or 63 */);
 
 int rtgs_scene_num_gaussians(const rtgs_scene* s, int64_t* n);
 int rtgs_scene_device(const rtgs_scene* s, int* device);
@@ -106,6 +107,10 @@ int rtgs_scene_device(const rtgs_scene* s, int* device);
  * parent (2n-1, root -1), aabb ((2n-1)*6: min xyz, max xyz). */
 int rtgs_scene_read_lbvh(rtgs_scene* s, uint32_t* morton, uint32_t* sorted_idx,
                          int32_t* child, int32_t* parent, float* aabb);
+
+/* 63-bit Morton codes (original order) of a scene built with RTGS_OPT_MORTON_BITS = 63; spec:
+ * oracle/lbvh_ref.py morton63.  rtgs_scene_read_lbvh then takes morton = NULL. */
+int rtgs_scene_read_morton64(rtgs_scene* s, uint64_t* codes /*n*/);
 
 /* Read back stored Gaussian parameters in original order (Scene.gaussian_field, scene.py:131):
  * host pointers, any may be NULL.  sh is (n,15,3). */
@@ -143,12 +148,20 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
  *  RTGS_OPT_STRIPE           value = (mod << 32) | rem: following renders touch only the 32-pixel-wide column
  *                            stripes mi = (i - x0) / 32 with mi % mod == rem and leave every other pixel of the
  *                            output untouched (tile sharding of one frame over `mod` GPUs; a
- *                            stripe is 32*H*3 contiguous floats of the (W,H,3) image).  (1 << 32) = all (default). */
+ *                            stripe is 32*H*3 contiguous floats of the (W,H,3) image).  (1 << 32) = all (default).
+ *  RTGS_OPT_MORTON_BITS      width of the Morton codes of the NEXT rtgs_scene_build_bvh (call it again to
+ *                            rebuild): 30 = the north-star spec, 63 = 21 bits per axis, 0 (default) = 30 unless
+ *                            more than an eighth of the 30-bit codes repeat - far outliers, or many Gaussians
+ *                            per 1/1024 of the extent - in which case the tree is rebuilt from 63-bit codes
+ *                            (BVH quality; 4 stray points among 1 M Gaussians cost the 30-bit
+ *                            tree a factor 150 in frame time).  The image does not depend on the width, only
+ *                            the traversal cost.  rtgs_scene_morton_bits reports the width in use. */
 typedef enum rtgs_option {
     RTGS_OPT_RENDER_MODE = 0,
     RTGS_OPT_LIST_POOL_CHUNKS = 1,
     RTGS_OPT_KERNEL_TIMING = 2,
-    RTGS_OPT_STRIPE = 3
+    RTGS_OPT_STRIPE = 3,
+    RTGS_OPT_MORTON_BITS = 4
 } rtgs_option;
 int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value);
 

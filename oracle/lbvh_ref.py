@@ -15,6 +15,9 @@ key    = uint64(code) << 32 | uint32(original index)           unique
 order  = ascending key
 tree   = Karras 2012 over the sorted keys with delta(i,j) = clz64(key_i ^ key_j)
 ids    = internal [0, n-1), leaves [n-1, 2n-1) in sorted order; root = internal 0
+
+Optional wide variant (morton63 / build(pos, bits=63)): 21 bits per axis, order = ascending (code, index),
+delta(i,j) = clz64(code_i ^ code_j), or 64 + clz64(i ^ j) for equal codes.
 """
 from __future__ import annotations
 
@@ -53,6 +56,43 @@ def morton30(pos, lo=None, hi=None):
         return (expand_bits(u[:, 0]) << np.uint32(2)) | (expand_bits(u[:, 1]) << np.uint32(1)) | expand_bits(u[:, 2])
 
 
+def expand_bits21(v):
+    """Spread the low 21 bits of v two apart (uint64)."""
+    v = v.astype(np.uint64) & np.uint64(0x1FFFFF)
+    v = (v | (v << np.uint64(32))) & np.uint64(0x001F00000000FFFF)
+    v = (v | (v << np.uint64(16))) & np.uint64(0x001F0000FF0000FF)
+    v = (v | (v << np.uint64(8))) & np.uint64(0x100F00F00F00F00F)
+    v = (v | (v << np.uint64(4))) & np.uint64(0x10C30C30C30C30C3)
+    v = (v | (v << np.uint64(2))) & np.uint64(0x1249249249249249)
+    return v
+
+
+def morton63(pos, lo=None, hi=None):
+    """63-bit Morton codes (uint64), the optional wide variant (RTGS_OPT_MORTON_BITS = 63):
+    x as for morton30, u = uint32(min(max(x * 2^21, 0), 2^21 - 1)), code = spread(ux) << 2 | spread(uy) << 1 |
+    spread(uz).  Codes may repeat: the order is ascending (code, original index) and the hierarchy tells equal
+    codes apart by sorted position (karras(..., duplicates=True))."""
+    pos = np.asarray(pos, dtype=np.float32)
+    if lo is None or hi is None:
+        lo, hi = scene_bounds(pos)
+    lo = np.asarray(lo, dtype=np.float32)
+    hi = np.asarray(hi, dtype=np.float32)
+    ext = (hi - lo).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.where(ext > 0, np.float32(1.0) / ext, np.float32(0.0)).astype(np.float32)
+    x = ((pos - lo).astype(np.float32) * inv).astype(np.float32)
+    q = np.minimum(np.maximum((x * np.float32(2097152.0)).astype(np.float32), np.float32(0.0)),
+                   np.float32(2097151.0))
+    u = q.astype(np.uint32)
+    return (expand_bits21(u[:, 0]) << np.uint64(2)) | (expand_bits21(u[:, 1]) << np.uint64(1)) | expand_bits21(u[:, 2])
+
+
+def sort_codes63(codes):
+    """(sorted 63-bit codes, sorted original indices uint32): ascending (code, index)."""
+    order = np.argsort(codes, kind="stable")
+    return codes[order], order.astype(np.uint32)
+
+
 def sort_keys(codes):
     """(sorted 64-bit keys, sorted original indices uint32)."""
     n = codes.shape[0]
@@ -73,10 +113,11 @@ def _clz64(x):
     return n
 
 
-def karras(keys):
+def karras(keys, duplicates=False):
     """Karras 2012 hierarchy.  Returns child (n-1,2) int32 with node ids in the unified id
     space (leaf k -> n-1+k), parent (2n-1,) int32 (root: -1), rng (n-1,2) int32 = the sorted
-    leaf range [first,last] covered by each internal node."""
+    leaf range [first,last] covered by each internal node.  duplicates=True: `keys` are sorted codes that
+    may repeat; equal ones are told apart by position, delta = 64 + clz64(i ^ j) (Karras 2012, section 4)."""
     keys = np.asarray(keys, dtype=np.uint64)
     n = keys.shape[0]
     if n == 1:
@@ -86,7 +127,12 @@ def karras(keys):
     def delta(a, b):
         ok = (b >= 0) & (b < n)
         bb = np.clip(b, 0, n - 1)
-        return np.where(ok, _clz64(keys[a] ^ keys[bb] | (~ok).astype(np.uint64)), -1)
+        x = keys[a] ^ keys[bb]
+        if duplicates:
+            same = ok & (x == 0)
+            pos = (a.astype(np.uint64) ^ bb.astype(np.uint64)) | (~same).astype(np.uint64)
+            return np.where(same, 64 + _clz64(pos), np.where(ok, _clz64(x | (~ok | same).astype(np.uint64)), -1))
+        return np.where(ok, _clz64(x | (~ok).astype(np.uint64)), -1)
 
     d = np.where(delta(i, i + 1) - delta(i, i - 1) >= 0, 1, -1).astype(np.int64)
     # sign(): delta values are never equal for unique keys except both -1 (n == 1, excluded).
@@ -150,8 +196,14 @@ def refit(child, leaf_min, leaf_max):
     return bmin, bmax
 
 
-def build(pos):
-    """Full integer pipeline: dict(codes, keys, sorted_idx, child, parent, rng)."""
+def build(pos, bits=30):
+    """Full integer pipeline: dict(codes, keys, sorted_idx, child, parent, rng).  bits=63: the wide variant
+    (keys = the sorted codes)."""
+    if bits == 63:
+        codes = morton63(pos)
+        keys, sidx = sort_codes63(codes)
+        child, parent, rng = karras(keys, duplicates=True)
+        return dict(codes=codes, keys=keys, sorted_idx=sidx, child=child, parent=parent, rng=rng)
     codes = morton30(pos)
     keys, sidx = sort_keys(codes)
     child, parent, rng = karras(keys)

@@ -48,6 +48,7 @@ void free_scene(rtgs_scene* s) {
     DeviceGuard g(s->device);
     cudaFree(s->pos); cudaFree(s->rot); cudaFree(s->scale); cudaFree(s->color); cudaFree(s->opacity);
     cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
+    cudaFree(s->morton64);
     cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
     cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
     cudaFree(s->counters); cudaFree(s->stats_dev);
@@ -254,9 +255,30 @@ int rtgs_scene_build_bvh(rtgs_scene* s, int32_t leaf_size) {
     RTGS_CHECK_ARG(s != nullptr);
     (void)leaf_size;  // LBVH leaves hold one Gaussian; accepted for Scene(leaf_prim=...) compatibility
     DeviceGuard g(s->device);
+    s->built = false;
+    s->morton_bits_used = s->opt_morton_bits == 63 ? 63 : 30;
     int r = rtgs_lbvh_build(s);
+    // automatic width: the 30-bit tree is the specification; it is replaced by the 63-bit one when more than an
+    // eighth of the codes repeat, i.e. when 10 bits per axis do not resolve the scene (far outliers, or many
+    // Gaussians per 1/1024 of the extent), which is when its traversal cost explodes
+    if (r == RTGS_OK && s->opt_morton_bits == 0 && s->distinct_codes >= 0 && s->distinct_codes * 8 < s->n * 7) {
+        const float first_ms = s->build_ms;
+        s->morton_bits_used = 63;
+        r = rtgs_lbvh_build(s);
+        s->build_ms += first_ms;
+    }
     if (r == RTGS_OK) s->built = true;
     return r;
+}
+
+int rtgs_scene_morton_bits(const rtgs_scene* s, int32_t* bits) {
+    RTGS_CHECK_ARG(s != nullptr && bits != nullptr);
+    if (!s->built) {
+        rtgs_set_error("rtgs_scene_morton_bits: call rtgs_scene_build_bvh first");
+        return RTGS_ERR_STATE;
+    }
+    *bits = s->morton_bits_used;
+    return RTGS_OK;
 }
 
 int rtgs_scene_build_ms(const rtgs_scene* s, float* ms) {
@@ -290,11 +312,27 @@ int rtgs_scene_read_lbvh(rtgs_scene* s, uint32_t* morton, uint32_t* sorted_idx, 
     }
     DeviceGuard g(s->device);
     const int64_t n = s->n;
+    if (morton && s->morton_bits_used == 63) {
+        rtgs_set_error("rtgs_scene_read_lbvh: the scene was built with 63-bit codes; read them with "
+                       "rtgs_scene_read_morton64 and pass morton = NULL here");
+        return RTGS_ERR_STATE;
+    }
     if (morton) CUDA_TRY(cudaMemcpy(morton, s->morton, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (sorted_idx) CUDA_TRY(cudaMemcpy(sorted_idx, s->sorted_idx, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (child && n > 1) CUDA_TRY(cudaMemcpy(child, s->child, (n - 1) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (parent) CUDA_TRY(cudaMemcpy(parent, s->parent, (2 * n - 1) * sizeof(int32_t), cudaMemcpyDeviceToHost));
     if (aabb) CUDA_TRY(cudaMemcpy(aabb, s->aabb, (2 * n - 1) * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+    return RTGS_OK;
+}
+
+int rtgs_scene_read_morton64(rtgs_scene* s, uint64_t* codes) {
+    RTGS_CHECK_ARG(s != nullptr && codes != nullptr);
+    if (!s->built || s->morton_bits_used != 63 || !s->morton64) {
+        rtgs_set_error("rtgs_scene_read_morton64: the BVH was not built with RTGS_OPT_MORTON_BITS = 63");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    CUDA_TRY(cudaMemcpy(codes, s->morton64, s->n * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return RTGS_OK;
 }
 
@@ -361,6 +399,10 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             s->pool_chunks = 0;
             return RTGS_OK;
         }
+        case RTGS_OPT_MORTON_BITS:
+            RTGS_CHECK_ARG(value == 0 || value == 30 || value == 63);
+            s->opt_morton_bits = (int)value;   // takes effect at the next rtgs_scene_build_bvh
+            return RTGS_OK;
         case RTGS_OPT_STRIPE: {
             const int64_t mod = value >> 32, rem = value & 0xffffffffll;
             RTGS_CHECK_ARG(mod >= 1 && mod <= 1024 && rem >= 0 && rem < mod);

@@ -67,6 +67,10 @@ struct rtgs_scene {
 
     // LBVH integers (parity read-back) and boxes
     uint32_t* morton = nullptr;      // n, original order
+    uint64_t* morton64 = nullptr;    // n, original order: 63-bit codes (RTGS_OPT_MORTON_BITS = 63 only)
+    int opt_morton_bits = 0;         // RTGS_OPT_MORTON_BITS: 0 = automatic, 30, 63
+    int morton_bits_used = 30;       // width of the codes the current tree was built from
+    int64_t distinct_codes = -1;     // distinct 30-bit codes found by the last 30-bit build
     uint32_t* sorted_idx = nullptr;  // n
     int32_t* child = nullptr;        // (n-1)*2 unified ids
     int32_t* parent = nullptr;       // 2n-1

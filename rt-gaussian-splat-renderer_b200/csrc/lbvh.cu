@@ -2,7 +2,7 @@
 //
 // Replaces the reference's host-driven binned-SAH builder (scene.py:162-404: >= 10 kernel
 // launches + 4 device->host syncs per node, ~120 nodes/s) with a fully device-side build:
-//   scene bounds -> 30-bit Morton codes -> LSD radix sort of (code<<32 | index) ->
+//   scene bounds -> 30-bit (or, optionally, 63-bit) Morton codes -> LSD radix sort of (code<<32 | index) ->
 //   Karras 2012 hierarchy -> per-Gaussian preprocessing + packing in sorted order ->
 //   bottom-up AABB refit -> 64-byte two-child traversal nodes.
 // The integer spec (codes, keys, hierarchy ids) is oracle/lbvh_ref.py; it must match bit for bit.
@@ -70,6 +70,64 @@ __global__ void k_morton(const float* __restrict__ pos, int64_t n, const unsigne
     uint32_t code = (expand_bits(u[0]) << 2) | (expand_bits(u[1]) << 1) | expand_bits(u[2]);
     morton[i] = code;
     keys[i] = ((uint64_t)code << 32) | (uint64_t)(uint32_t)i;
+}
+
+// 63-bit variant (RTGS_OPT_MORTON_BITS = 63; spec: oracle/lbvh_ref.py morton63): 21 bits per axis, so that a few
+// far outliers - common in trained 3DGS scenes - do not collapse the rest of the scene into a handful of cells.
+//   u = uint(min(max(x * 2^21, 0), 2^21 - 1)),  code = spread(ux) << 2 | spread(uy) << 1 | spread(uz)
+// Codes are not unique any more and do not leave room for the index in one 64-bit key, so the order
+// (code, index) is produced by two stable 32-bit sorts: on the low word, then on the high word.
+__device__ __forceinline__ uint64_t expand_bits21(uint32_t u) {
+    uint64_t v = u & 0x1fffffull;
+    v = (v | v << 32) & 0x001f00000000ffffull;
+    v = (v | v << 16) & 0x001f0000ff0000ffull;
+    v = (v | v << 8) & 0x100f00f00f00f00full;
+    v = (v | v << 4) & 0x10c30c30c30c30c3ull;
+    v = (v | v << 2) & 0x1249249249249249ull;
+    return v;
+}
+
+__global__ void k_morton63(const float* __restrict__ pos, int64_t n, const unsigned int* __restrict__ bnd,
+                           uint64_t* __restrict__ code64, uint64_t* __restrict__ keys) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t u[3];
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        float lo = ordered_to_float(bnd[a]), hi = ordered_to_float(bnd[3 + a]);
+        float ext = __fsub_rn(hi, lo);
+        float inv = ext > 0.0f ? __fdiv_rn(1.0f, ext) : 0.0f;
+        float x = __fmul_rn(__fsub_rn(pos[i * 3 + a], lo), inv);
+        float q = fminf(fmaxf(__fmul_rn(x, 2097152.0f), 0.0f), 2097151.0f);
+        u[a] = (uint32_t)q;
+    }
+    const uint64_t code = (expand_bits21(u[0]) << 2) | (expand_bits21(u[1]) << 1) | expand_bits21(u[2]);
+    code64[i] = code;
+    keys[i] = (code << 32) | (uint64_t)(uint32_t)i;   // first sort: low word of the code
+}
+
+// number of distinct 30-bit codes among the sorted keys (upper word), for the automatic choice of the code width
+__global__ void k_count_distinct(const uint64_t* __restrict__ sorted_keys, int64_t n, unsigned long long* __restrict__ out) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool first = j < n && (j == 0 || (sorted_keys[j] >> 32) != (sorted_keys[j - 1] >> 32));
+    const unsigned m = __ballot_sync(0xffffffffu, first);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(out, (unsigned long long)__popc(m));
+}
+
+// second sort key: (high word of the code << 32) | index, in the order the first sort produced
+__global__ void k_keys_high(const uint64_t* __restrict__ sorted_low, const uint64_t* __restrict__ code64, int64_t n,
+                            uint64_t* __restrict__ keys) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const uint64_t idx = sorted_low[j] & 0xFFFFFFFFull;
+    keys[j] = (code64[idx] & 0xFFFFFFFF00000000ull) | idx;
+}
+
+__global__ void k_gather_codes(const uint64_t* __restrict__ sorted_keys, const uint64_t* __restrict__ code64,
+                               int64_t n, uint64_t* __restrict__ sorted_codes) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    sorted_codes[j] = code64[sorted_keys[j] & 0xFFFFFFFFull];
 }
 
 // ------------------------------------------------------------------ LSD radix sort (8-bit digits)
@@ -198,29 +256,37 @@ k_rs_scatter(const uint64_t* __restrict__ in, uint64_t* __restrict__ out, int64_
 }
 
 // ------------------------------------------------------------------ Karras 2012 hierarchy
-__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int64_t n, uint64_t ki, int64_t j) {
+// DUP = false: unique keys (code << 32 | index), delta = clz(key_i ^ key_j).  DUP = true: sorted 63-bit codes that
+// may repeat; equal codes are told apart by their sorted positions, delta = 64 + clz(i ^ j) (Karras 2012, sec. 4).
+template <bool DUP>
+__device__ __forceinline__ int delta_fn(const uint64_t* __restrict__ keys, int64_t n, uint64_t ki, int64_t i,
+                                        int64_t j) {
     if (j < 0 || j >= n) return -1;
-    return __clzll((long long)(ki ^ keys[j]));
+    const uint64_t x = ki ^ keys[j];
+    if (DUP && x == 0) return 64 + __clzll((long long)((uint64_t)i ^ (uint64_t)j));
+    return __clzll((long long)x);
 }
 
+template <bool DUP>
 __global__ void k_karras(const uint64_t* __restrict__ keys, int64_t n, int32_t* __restrict__ child,
                          int32_t* __restrict__ parent) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n - 1) return;
     uint64_t ki = keys[i];
-    int d = (delta_fn(keys, n, ki, i + 1) - delta_fn(keys, n, ki, i - 1)) >= 0 ? 1 : -1;
-    int dmin = delta_fn(keys, n, ki, i - d);
+    auto delta = [&](int64_t j) { return delta_fn<DUP>(keys, n, ki, i, j); };
+    int d = (delta(i + 1) - delta(i - 1)) >= 0 ? 1 : -1;
+    int dmin = delta(i - d);
     int64_t lmax = 2;
-    while (delta_fn(keys, n, ki, i + lmax * d) > dmin) lmax <<= 1;
+    while (delta(i + lmax * d) > dmin) lmax <<= 1;
     int64_t l = 0;
     for (int64_t t = lmax >> 1; t >= 1; t >>= 1)
-        if (delta_fn(keys, n, ki, i + (l + t) * d) > dmin) l += t;
+        if (delta(i + (l + t) * d) > dmin) l += t;
     int64_t j = i + l * d;
-    int dnode = delta_fn(keys, n, ki, j);
+    int dnode = delta(j);
     int64_t s = 0, t = l;
     do {
         t = (t + 1) >> 1;
-        if (delta_fn(keys, n, ki, i + (s + t) * d) > dnode) s += t;
+        if (delta(i + (s + t) * d) > dnode) s += t;
     } while (t > 1);
     int64_t gamma = i + s * d + (d < 0 ? -1 : 0);
     int64_t first = i < j ? i : j, last = i < j ? j : i;
@@ -426,6 +492,7 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     CUDA_TRY(cudaMalloc(&hist.p, (size_t)RS_BINS * ntiles * sizeof(uint32_t)));
     CUDA_TRY(cudaMalloc(&visit.p, (size_t)(n > 1 ? n - 1 : 1) * sizeof(unsigned int)));
 
+    if (s->morton_bits_used == 63 && !s->morton64) CUDA_TRY(cudaMalloc(&s->morton64, n * sizeof(uint64_t)));
     cudaEvent_t e0 = nullptr, e1 = nullptr;   // device time of the build proper (rtgs_scene_build_ms)
     CUDA_TRY(cudaEventCreate(&e0));
     CUDA_TRY(cudaEventCreate(&e1));
@@ -433,26 +500,48 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     CUDA_TRY(cudaEventRecord(e0, st));
     const int TB = 256;
     const int nb = (int)((n + TB - 1) / TB);
+    const bool wide = s->morton_bits_used == 63;
     k_init_bounds<<<1, 32, 0, st>>>(bnd.p);
     k_bounds<<<min(nb, s->sm_count * 8), TB, 0, st>>>(s->pos, n, bnd.p);
-    k_morton<<<nb, TB, 0, st>>>(s->pos, n, bnd.p, s->morton, keys_a.p);
+    if (wide) k_morton63<<<nb, TB, 0, st>>>(s->pos, n, bnd.p, s->morton64, keys_a.p);
+    else k_morton<<<nb, TB, 0, st>>>(s->pos, n, bnd.p, s->morton, keys_a.p);
     CUDA_TRY(cudaGetLastError());
 
     uint64_t* src = keys_a.p;
     uint64_t* dst = keys_b.p;
-    for (int pass = 0; pass < 4; ++pass) {
-        int shift = 32 + 8 * pass;
-        k_rs_hist<<<ntiles, RS_WARPS * 32, 0, st>>>(src, n, shift, hist.p, ntiles);
-        k_rs_scan<<<1, 1024, 0, st>>>(hist.p, (int64_t)RS_BINS * ntiles);
-        k_rs_scatter<<<ntiles, RS_WARPS * 32, 0, st>>>(src, dst, n, shift, hist.p, ntiles);
+    // stable sort of `src` on its upper 32 bits; afterwards `src` holds the sorted keys
+    auto sort_upper_word = [&]() {
+        for (int pass = 0; pass < 4; ++pass) {
+            int shift = 32 + 8 * pass;
+            k_rs_hist<<<ntiles, RS_WARPS * 32, 0, st>>>(src, n, shift, hist.p, ntiles);
+            k_rs_scan<<<1, 1024, 0, st>>>(hist.p, (int64_t)RS_BINS * ntiles);
+            k_rs_scatter<<<ntiles, RS_WARPS * 32, 0, st>>>(src, dst, n, shift, hist.p, ntiles);
+            uint64_t* t = src;
+            src = dst;
+            dst = t;
+        }
+    };
+    sort_upper_word();
+    DevBuf<unsigned long long> distinct;
+    if (!wide) {
+        CUDA_TRY(cudaMalloc(&distinct.p, sizeof(unsigned long long)));
+        CUDA_TRY(cudaMemsetAsync(distinct.p, 0, sizeof(unsigned long long), st));
+        k_count_distinct<<<nb, TB, 0, st>>>(src, n, distinct.p);
+    }
+    if (wide) {
+        k_keys_high<<<nb, TB, 0, st>>>(src, s->morton64, n, dst);
         uint64_t* t = src;
         src = dst;
         dst = t;
+        sort_upper_word();
     }
     CUDA_TRY(cudaGetLastError());
-    // src now holds the sorted keys
-    if (n > 1) {
-        k_karras<<<(int)((n - 1 + TB - 1) / TB), TB, 0, st>>>(src, n, s->child, s->parent);
+    // src now holds the sorted keys (low word = original index)
+    if (n > 1 && wide) {
+        k_gather_codes<<<nb, TB, 0, st>>>(src, s->morton64, n, dst);
+        k_karras<true><<<(int)((n - 1 + TB - 1) / TB), TB, 0, st>>>(dst, n, s->child, s->parent);
+    } else if (n > 1) {
+        k_karras<false><<<(int)((n - 1 + TB - 1) / TB), TB, 0, st>>>(src, n, s->child, s->parent);
     } else {
         int32_t m1 = -1;
         CUDA_TRY(cudaMemcpyAsync(s->parent, &m1, sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -470,7 +559,10 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     CUDA_TRY(cudaEventRecord(e1, st));
     unsigned int hb[6];
     CUDA_TRY(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
+    unsigned long long hd = 0;
+    if (!wide) CUDA_TRY(cudaMemcpyAsync(&hd, distinct.p, sizeof(hd), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    s->distinct_codes = wide ? -1 : (int64_t)hd;
     CUDA_TRY(cudaEventElapsedTime(&s->build_ms, e0, e1));
     for (int a = 0; a < 6; ++a) s->bounds[a] = ordered_to_float(hb[a]);
     return RTGS_OK;

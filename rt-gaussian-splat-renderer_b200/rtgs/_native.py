@@ -46,9 +46,11 @@ SIGNATURES = {
                                                   C.c_int32, C.POINTER(_vp)]),
     "rtgs_scene_build_bvh": (C.c_int, [_vp, C.c_int32]),
     "rtgs_scene_build_ms": (C.c_int, [_vp, C.POINTER(C.c_float)]),
+    "rtgs_scene_morton_bits": (C.c_int, [_vp, C.POINTER(C.c_int32)]),
     "rtgs_scene_num_gaussians": (C.c_int, [_vp, C.POINTER(C.c_int64)]),
     "rtgs_scene_device": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "rtgs_scene_read_lbvh": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "rtgs_scene_read_morton64": (C.c_int, [_vp, _vp]),
     "rtgs_scene_read_gaussians": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "rtgs_render": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                               C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp,
@@ -72,7 +74,7 @@ SIGNATURES = {
     "rtgs_scene_destroy": (C.c_int, [_vp]),
 }
 
-OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING, OPT_STRIPE = 0, 1, 2, 3
+OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING, OPT_STRIPE, OPT_MORTON_BITS = 0, 1, 2, 3, 4
 KERNEL_NAMES = ("k_tile_lists", "k_shade_tiles", "k_render")
 
 _lib = None

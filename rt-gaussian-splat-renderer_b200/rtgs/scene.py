@@ -61,11 +61,18 @@ class Scene:
     2n-1 nodes and no balance heuristic, so both are accepted and ignored.  leaf_prim is passed to
     the builder (LBVH leaves currently hold one Gaussian)."""
 
-    def __init__(self, max_num_node: int = 128, balance_weight: int = 1, leaf_prim=8, device: int | None = None):
+    def __init__(self, max_num_node: int = 128, balance_weight: int = 1, leaf_prim=8, device: int | None = None,
+                 morton_bits: int | str = "auto"):
         self.max_num_node = max_num_node
         self.balance_weight = balance_weight
         self.leaf_prim = leaf_prim
         self.device = device
+        if morton_bits not in ("auto", 0, 30, 63):
+            raise ValueError('morton_bits must be "auto", 30 or 63')
+        # LBVH code width requested: "auto" = 30 bits unless they do not resolve the scene (far outliers), then 63;
+        # after the build `morton_bits` is the width in use.  The image does not depend on it.
+        self._morton_request = 0 if morton_bits in ("auto", 0) else int(morton_bits)
+        self.morton_bits = 30
         self._handle = None
         self._n = 0
         self._gaussian_field = None
@@ -158,7 +165,12 @@ class Scene:
         self.device = dev
         self.has_sh = bool(has_sh)
         self._gaussian_field = self._bvh_field = self._lbvh = None
+        _native.check(_native.load().rtgs_scene_set_option(self._handle, _native.OPT_MORTON_BITS,
+                                                           self._morton_request))
         _native.check(_native.load().rtgs_scene_build_bvh(self._handle, int(self.leaf_prim)))
+        bits = C.c_int32()
+        _native.check(_native.load().rtgs_scene_morton_bits(self._handle, C.byref(bits)))
+        self.morton_bits = int(bits.value)
         logger.info(f"Build {2 * self._n - 1} BVH nodes in total ({self.build_ms:.2f} ms on the device). "
                     "Max leaf node size is 1.")
 
@@ -231,15 +243,18 @@ class Scene:
         return out
 
     def read_lbvh(self) -> dict:
-        """LBVH integers and boxes (parity read-back): morton (n) in original order, sorted_idx (n),
+        """LBVH integers and boxes (parity read-back): morton (n; uint64 for morton_bits=63) in original order, sorted_idx (n),
         child (n-1,2) unified ids (leaf k -> n-1+k), parent (2n-1), aabb (2n-1,6)."""
         if self._lbvh is None:
             n = self._n
-            out = dict(morton=np.empty(n, np.uint32), sorted_idx=np.empty(n, np.uint32),
+            wide = self.morton_bits == 63
+            out = dict(morton=np.empty(n, np.uint64 if wide else np.uint32), sorted_idx=np.empty(n, np.uint32),
                        child=np.empty((max(n - 1, 0), 2), np.int32), parent=np.empty(2 * n - 1, np.int32),
                        aabb=np.empty((2 * n - 1, 6), np.float32))
+            if wide:
+                _native.check(_native.load().rtgs_scene_read_morton64(self.handle, out["morton"].ctypes.data))
             _native.check(_native.load().rtgs_scene_read_lbvh(
-                self.handle, out["morton"].ctypes.data, out["sorted_idx"].ctypes.data,
+                self.handle, None if wide else out["morton"].ctypes.data, out["sorted_idx"].ctypes.data,
                 out["child"].ctypes.data if n > 1 else None, out["parent"].ctypes.data, out["aabb"].ctypes.data))
             self._lbvh = out
         return self._lbvh
