@@ -50,7 +50,7 @@ struct __align__(16) WarpShared {
     float kb_t[K][32];         // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
     int kb_i[K][32];
     float kb_a[K][32];
-    float amb[2][3][32];       // per lane: up to two hits whose place at the K-th / (K+1)-th boundary is decided later
+    float amb[2][32];          // per lane: id and alpha of the nearest hit that is NOT in the buffer (its t is e1_t)
 };
 static_assert(sizeof(WarpShared) * K2_WARPS * K2_CTAS <= 227 * 1024, "shared-memory budget per SM");
 
@@ -110,12 +110,18 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
         const bool active = pi < xe && pj < ye;
 
         int cnt = 0;
-        int amb_state = 0;       // kmax_slot with its set-aside count, after the list
+        // The K nearest hits are kept by their float32 entry distances (replace-max once the buffer is full).  Which
+        // of two hits is nearer is only certain beyond float32 rounding (TIE_BAND), so the one place where it
+        // matters - the boundary between the K-th and the (K+1)-th nearest - is re-examined in float64 after the
+        // list: e1_t / ws.amb hold the nearest hit that is NOT in the buffer (a rejected hit or an evicted entry),
+        // bit 8 of kmax_slot says that a second such hit lies within float32 rounding of it.  (Checking every
+        // transient boundary instead sent 8 % of the dense tiles of a surface-like scene to the fused kernel:
+        // a ray with 1000 hits replaces its farthest entry ~60 times.)
+        float e1_t = INFINITY, kmax_t = INFINITY;
+        int kmax_slot = 0;
         TileRays tr;
         if (desc.count > 0) {
             make_tile_rays(cam, i0, j0, pi, pj, active, tr);
-            float kmax_t = INFINITY;
-            int kmax_slot = 0;
             int left = desc.count;
             // one coalesced 128-byte read per chunk: lanes 0..30 candidates, lane 31 the next chunk
             int cur = __ldg(P.pool + (int64_t)desc.head * CHUNK_INTS + lane);
@@ -169,41 +175,23 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                         const PreciseHit h = precise_test(P, ws.rec[c], tr.dlx, tr.dly, tr.dlz, pi, pj);
                         ST(st_f64 += h.refined);
                         if (h.hit) {
-                            // Which K entries survive must be decided on float64 entry distances whenever two
-                            // candidates for the last place are within float32 rounding of each other.  Such a
-                            // hit - the incoming one when it ties with the farthest entry, or the evicted farthest
-                            // entry when it ties with the new farthest one - is set aside (up to two per ray,
-                            // counted in bits 8-9 of kmax_slot) and merged after the list with exact_less: the K
-                            // nearest of A + {c} are the K nearest of (the K nearest of A) + {c}.  A third one on
-                            // the same ray sends the tile to the fused kernel, which resolves ties on the spot.
-                            auto set_aside = [&](float t, int sid, float a) {
-                                // 0, 1, 2 set aside so far; 3 = more than fit
-                                if ((kmax_slot & 0x300) == 0) {
-                                    ws.amb[0][0][lane] = t;
-                                    ws.amb[0][1][lane] = __int_as_float(sid);
-                                    ws.amb[0][2][lane] = a;
-                                    kmax_slot |= 0x100;
-                                } else if ((kmax_slot & 0x300) == 0x100) {
-                                    ws.amb[1][0][lane] = t;
-                                    ws.amb[1][1][lane] = __int_as_float(sid);
-                                    ws.amb[1][2][lane] = a;
-                                    kmax_slot ^= 0x300;   // 0x100 -> 0x200
-                                } else {
-                                    kmax_slot |= 0x300;
-                                }
-                            };
+                            float xt = h.t1, xa = h.alpha;   // the hit that stays outside the buffer (full buffer)
+                            int xi = h.s;
                             int slot = -1;
                             if (cnt < K) {
                                 slot = cnt++;
-                            } else if (fabsf(h.t1 - kmax_t) <= TIE_BAND * kmax_t) {
-                                set_aside(h.t1, h.s, h.alpha);
-                            } else if (h.t1 < kmax_t) {
-                                slot = kmax_slot & 15;   // full: replace the farthest entry
+                            } else if (h.t1 < kmax_t) {   // full: replace the farthest entry, which goes outside
+                                slot = kmax_slot & 15;
+                                xt = kmax_t;
+                                xi = ws.kb_i[slot][lane];
+                                xa = ws.kb_a[slot][lane];
                             }
+                            const bool full = cnt == K;
                             if (slot >= 0) {
                                 ws.kb_t[slot][lane] = h.t1;
-                                if (cnt == K) {   // buffer full: track the farthest entry (exact float32 maximum)
-                                    const float old_t = kmax_t;   // the evicted entry's distance (inf: none)
+                                ws.kb_i[slot][lane] = h.s;
+                                ws.kb_a[slot][lane] = h.alpha;
+                                if (full) {   // track the farthest entry (exact float32 maximum)
                                     float mt = -INFINITY;
                                     int ms = 0;
 #pragma unroll
@@ -211,14 +199,20 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                                         const float t = ws.kb_t[k][lane];
                                         if (t > mt) { mt = t; ms = k; }
                                     }
+                                    kmax_slot = ms | (kmax_slot & 0x100);
+                                    if (kmax_t == INFINITY) xt = INFINITY;   // the buffer has just filled: nothing is outside yet
                                     kmax_t = mt;
-                                    kmax_slot = ms | (kmax_slot & 0x300);
-                                    // evicted ~ new farthest: its id and alpha are still in the slot
-                                    if (old_t < 3e38f && old_t - mt <= TIE_BAND * old_t)
-                                        set_aside(old_t, ws.kb_i[slot][lane], ws.kb_a[slot][lane]);
                                 }
-                                ws.kb_i[slot][lane] = h.s;
-                                ws.kb_a[slot][lane] = h.alpha;
+                            }
+                            if (full && xt < INFINITY) {
+                                if (xt < e1_t) {
+                                    kmax_slot = (e1_t - xt <= TIE_BAND * xt) ? (kmax_slot | 0x100) : (kmax_slot & ~0x100);
+                                    e1_t = xt;
+                                    ws.amb[0][lane] = __int_as_float(xi);
+                                    ws.amb[1][lane] = xa;
+                                } else if (xt - e1_t <= TIE_BAND * e1_t) {
+                                    kmax_slot |= 0x100;
+                                }
                             }
                         }
                     }
@@ -226,42 +220,44 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
                 }
                 __syncwarp();
             }
-            amb_state = kmax_slot & 0x300 ? kmax_slot : 0;
         }
 
-        // ---- boundary hits that were set aside (rare) --------------------------------------------------
-        if (__any_sync(FULL, amb_state != 0)) {
-            if (__any_sync(FULL, ((amb_state >> 8) & 3) == 3)) {
-                // more than two on one ray: k_render (launched next on the stream) renders the tile; nothing of
-                // it has been written yet, so `accumulate` outputs stay correct
+        // ---- the K-th / (K+1)-th boundary (rare): is the nearest outside hit within float32 rounding of the
+        // farthest entry?  Then their float64 entry distances decide, repeatedly while the loser ties again.
+        const bool amb = e1_t - kmax_t <= TIE_BAND * kmax_t;   // false while either is inf
+        if (__any_sync(FULL, amb)) {
+            if (__any_sync(FULL, amb && (kmax_slot & 0x100))) {
+                // three contenders within rounding: k_render (launched next on the stream) renders the tile and
+                // resolves them on the spot; nothing of it has been written yet, so `accumulate` outputs stay correct
                 if (lane == 0) {
                     P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
                     *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
                 }
                 continue;
             }
-            const int na = (amb_state >> 8) & 3;
+            if (amb) {
+                float ct = e1_t, ca = ws.amb[1][lane];
+                int ci = __float_as_int(ws.amb[0][lane]);
+                float mt = kmax_t;
+                int ms = kmax_slot & 15;
 #pragma unroll 1
-            for (int a = 0; a < na; ++a) {
-                // the buffer is full: merge the hit with it (replace the farthest entry if the hit is nearer)
-                float mt = -INFINITY;
-                int slot = 0;
-#pragma unroll 1
-                for (int k = 0; k < K; ++k) {
-                    const float t = ws.kb_t[k][lane];
-                    if (t > mt) { mt = t; slot = k; }
-                }
-                const float at = ws.amb[a][0][lane];
-                const int as = __float_as_int(ws.amb[a][1][lane]);
-                bool nearer = at < mt;
-                if (fabsf(at - mt) <= TIE_BAND * mt) {
-                    nearer = exact_less(P.raw, cam, as, ws.kb_i[slot][lane], pi, pj);
+                for (int it = 0; it < 4; ++it) {
+                    if (!(ct - mt <= TIE_BAND * mt)) break;
                     ST(st_f64 += 2);
-                }
-                if (nearer) {
-                    ws.kb_t[slot][lane] = at;
-                    ws.kb_i[slot][lane] = as;
-                    ws.kb_a[slot][lane] = ws.amb[a][2][lane];
+                    if (!exact_less(P.raw, cam, ci, ws.kb_i[ms][lane], pi, pj)) break;
+                    // the outside hit is nearer: it takes the slot, the former farthest entry is the contender now
+                    const float ot = mt, oa = ws.kb_a[ms][lane];
+                    const int oi = ws.kb_i[ms][lane];
+                    ws.kb_t[ms][lane] = ct;
+                    ws.kb_i[ms][lane] = ci;
+                    ws.kb_a[ms][lane] = ca;
+                    ct = ot; ci = oi; ca = oa;
+                    mt = -INFINITY;
+#pragma unroll 1
+                    for (int k = 0; k < K; ++k) {
+                        const float t = ws.kb_t[k][lane];
+                        if (t > mt) { mt = t; ms = k; }
+                    }
                 }
             }
         }

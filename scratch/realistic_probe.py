@@ -1,0 +1,85 @@
+"""Robustness probe: a scene shaped like a trained 3DGS capture rather than a uniform cloud - Gaussians on surfaces
+(spherical shells and a floor), flat (one axis 10x thinner), heavy-tailed sizes, a few huge translucent blobs and far
+stray points.  Prints per-kernel times and checks a pixel subsample against the float64 C++ oracle."""
+import sys, time, numpy as np, torch
+sys.path.insert(0, 'rt-gaussian-splat-renderer_b200'); sys.path.insert(0, '.')
+from oracle import ref_cpu, ref_numpy as O
+from rtgs.camera import Camera
+from rtgs.orbit import focal_from_fov, orbit_pose
+from rtgs.ray_tracer import RayTracer
+from rtgs.scene import Scene
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
+W, H = 1920, 1080
+rng = np.random.default_rng(4242)
+f32 = np.float32
+# surfaces: 6 shells of different radius / centre + a floor
+pos = np.empty((n, 3), f32)
+k = rng.integers(0, 7, n)
+c = rng.uniform(-0.6, 0.6, (6, 3)); r = rng.uniform(0.15, 0.45, 6)
+u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1, keepdims=True)
+shell = k < 6
+pos[shell] = (c[k[shell]] + r[k[shell], None] * u[shell] * (1 + 0.01 * rng.normal(size=(shell.sum(), 1)))).astype(f32)
+pos[~shell] = np.stack([rng.uniform(-1, 1, (~shell).sum()), rng.uniform(-1, 1, (~shell).sum()),
+                        -0.8 + 0.005 * rng.normal(size=(~shell).sum())], axis=1).astype(f32)
+quat = rng.normal(size=(n, 4)); quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+base = 2.0 * np.sqrt(16.0 / (3 * np.pi * n)) * 2.0
+ls = rng.normal(np.log(base), 1.0, (n, 3))            # heavy tail (sigma 1.0 instead of 0.5)
+ls[:, 2] -= np.log(10.0)                               # flat splats
+scale = np.exp(ls).astype(f32)
+big = rng.choice(n, 40, replace=False)
+scale[big] = rng.uniform(0.2, 0.6, (40, 3)).astype(f32)   # huge blobs
+stray = rng.choice(n, 6, replace=False)
+pos[stray] = (rng.uniform(-1, 1, (6, 3)) * 800.0).astype(f32)
+opacity = (1 / (1 + np.exp(-rng.normal(0.5, 2.0, n)))).astype(f32)
+opacity[big] = 0.05
+color = (1 / (1 + np.exp(-rng.normal(0, 1, (n, 3))))).astype(f32)
+sh = rng.normal(0, 0.15, (n, 15, 3)).astype(f32)
+rot = quat.astype(f32)
+
+t0 = time.perf_counter()
+scene = Scene().from_arrays(pos, rot, scale, color, opacity, sh)
+print(f"n={n} build {scene.build_ms:.2f} ms (device), morton_bits={scene.morton_bits}, load {1e3*(time.perf_counter()-t0):.0f} ms", flush=True)
+f = focal_from_fov(H, 60.0)
+views = [orbit_pose(2 * np.pi * v / 16, np.pi / 2 - 0.3, 2.2) for v in range(16)]
+cam = Camera(views[0][0], views[0][1], (W, H), (f, f))
+rt = RayTracer((W, H), scene, cam, t_cut=1e-4)
+out = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
+agg = {}
+for v in range(16):
+    cam.position, cam.rotation = views[v]; rt.render_device(16, out=out, collect_stats=True)
+    for kk, vv in rt.last_stats.items(): agg[kk] = agg.get(kk, 0) + vv
+print("kbar %.2f hit %.3f cand/tile %.1f useful/tile %.1f fallback tiles %d" % (agg["layers"]/agg["rays"], agg["rays_hit"]/agg["rays"],
+      agg["candidates"]/max(agg["tiles"],1), agg["useful_candidates"]/max(agg["tiles"],1), agg["fallback_tiles"]), flush=True)
+torch.cuda.synchronize()
+scene.set_option("kernel_timing", 32)
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for v in range(32):
+    cam.position, cam.rotation = views[v % 16]; rt.render_device(16, out=out)
+e1.record(); torch.cuda.synchronize()
+t = scene.read_kernel_times(32).astype(np.float64).mean(axis=0)
+ms = e0.elapsed_time(e1) / 32
+print(f"frame {ms:.3f} ms = {W*H/ms/1e3:.0f} Mrays/s; lists {t[0]:.3f} shade {t[1]:.3f} fused {t[2]:.3f} ms", flush=True)
+for v in range(16):
+    cam.position, cam.rotation = views[v]; rt.render_device(16, out=out, collect_stats=True)
+    st = rt.last_stats
+    print(f"  view {v:2d}: cand/tile {st['candidates']/max(st['tiles'],1):7.1f} fallback {st['fallback_tiles']:5d} kbar {st['layers']/st['rays']:.2f} "
+          f"trav steps/tile {st['traversal_steps']/max(st['tiles'],1):.1f} insert rounds/tile {st['insert_rounds']/max(st['tiles'],1):.1f}", flush=True)
+scene.set_option("kernel_timing", 16)
+for v in range(16):
+    cam.position, cam.rotation = views[v]; rt.render_device(16, out=out)
+tt = scene.read_kernel_times(16).astype(np.float64)
+for v in range(16):
+    print(f"  view {v:2d}: lists {tt[v,0]:.3f} shade {tt[v,1]:.3f} fused {tt[v,2]:.3f} ms", flush=True)
+scene.set_option("kernel_timing", 0)
+# parity on a pixel subsample of two views, t_cut = 0
+rt0 = RayTracer((W, H), scene, cam, t_cut=0.0)
+cs = ref_cpu.CpuScene(pos, rot, scale, color, opacity, sh)
+pix = ref_cpu.all_pixels(W, H, 4)
+for v in (0, 5):
+    cam.position, cam.rotation = views[v]
+    img = rt0.render(16).copy()
+    ref = cs.render(O.CameraParams(np.asarray(views[v][0]), np.asarray(views[v][1]), W, H, (f, f)), 16, pixels=pix, precision="double")
+    d = np.abs(img[pix[:, 0], pix[:, 1]].astype(np.float64) - ref["rgb"]).max(axis=1)
+    print(f"view {v}: {len(pix)} px max-abs {d.max():.3e}; >1e-4: {(d>1e-4).sum()}; >1e-3: {(d>1e-3).sum()}", flush=True)
