@@ -50,6 +50,7 @@ struct __align__(16) TraversalScratch {
     float2 polyB[BATCH];        //                   {c4 c5}
     int stack[STACK_CAP];
     int cq[CQ_CAP];
+    Frustum open;               // pyramid of the rays that still lack hits (distance pruning, below)
 };
 
 template <int K>
@@ -124,6 +125,23 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         bool pend = false;
         int pend_c = 0;
 
+        // Distance pruning - the K-nearest form of the reference's "skip a node whose entry distance exceeds the best
+        // hit so far" (scene.py:417-419).  A ray that holds K hits needs nothing farther than its farthest one, so a
+        // box is dropped when it lies beyond `cut` = the largest such distance among the rays that are full (with a
+        // margin far above float32 rounding, so that near-ties at the K-th place still see both contenders) AND
+        // misses the pyramid of the rays that are not full yet (`tr.open`, the bounding pixel rectangle of those
+        // rays; initially the whole tile).  Children are pushed far one first.  This is what keeps a tile that looks
+        // along a surface - thousands of splats in its frustum, the first few dozen of them opaque - affordable.
+        float cut2 = -1.0f;            // (cut * (1 + 1e-4))^2, < 0: no ray is full yet
+        unsigned open_mask = __ballot_sync(FULL, active);
+        bool open_all = true;          // tr.open == fr
+        const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
+        auto box_dist2 = [&](float cx, float cy, float cz, float hx, float hy, float hz) {
+            const float dx = fmaxf(fabsf(ox - cx) - hx, 0.0f), dy = fmaxf(fabsf(oy - cy) - hy, 0.0f),
+                        dz = fmaxf(fabsf(oz - cz) - hz, 0.0f);
+            return dx * dx + dy * dy + dz * dz;
+        };
+
         int top = 1, ncq = 0;
         if (lane == 0) tr.stack[0] = 0;
         __syncwarp();
@@ -147,6 +165,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     c1 = __float_as_int(d.y);
                     h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
                     h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
+                    const float d0 = box_dist2(a.x, a.y, a.z, a.w, b.x, b.y);
+                    const float d1 = box_dist2(b.z, b.w, c.x, c.y, c.z, c.w);
+                    if (cut2 >= 0.0f) {
+                        if (h0 && d0 > cut2)
+                            h0 = open_mask != 0 && (open_all || box_in_frustum(tr.open, a.x, a.y, a.z, a.w, b.x, b.y));
+                        if (h1 && d1 > cut2)
+                            h1 = open_mask != 0 && (open_all || box_in_frustum(tr.open, b.z, b.w, c.x, c.y, c.z, c.w));
+                    }
+                    if (d1 > d0) {   // child 1 is pushed last, i.e. popped first: make it the nearer one
+                        const int ci = c0; c0 = c1; c1 = ci;
+                        const bool hi = h0; h0 = h1; h1 = hi;
+                    }
                 }
                 ST(st_nodes += 2ull * (unsigned)take);
                 ST(st_steps += 1);
@@ -250,6 +280,37 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     }
                 }
                 __syncwarp();
+                // ---- pruning state after the batch: who is full, how far their farthest hit is ----
+                {
+                    const bool full = active && cnt == K;
+                    float cm = full ? kmax_t : -1.0f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
+                    if (cm >= 0.0f) {
+                        cm *= 1.0001f;
+                        cut2 = cm * cm;
+                    }
+                    const unsigned om = __ballot_sync(FULL, active && cnt < K);
+                    if (om != open_mask) {
+                        open_mask = om;
+                        if (om != 0) {
+                            int il = cnt < K && active ? pi : 0x7fffffff, ih = cnt < K && active ? pi : -1;
+                            int jl = cnt < K && active ? pj : 0x7fffffff, jh = cnt < K && active ? pj : -1;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                il = min(il, __shfl_xor_sync(FULL, il, o));
+                                ih = max(ih, __shfl_xor_sync(FULL, ih, o));
+                                jl = min(jl, __shfl_xor_sync(FULL, jl, o));
+                                jh = max(jh, __shfl_xor_sync(FULL, jh, o));
+                            }
+                            Frustum fo;
+                            make_frustum(cam, il, ih + 1, jl, jh + 1, fo);
+                            if (lane == 0) tr.open = fo;
+                            open_all = false;
+                        }
+                        __syncwarp();
+                    }
+                }
             }
         }
 
@@ -626,6 +687,8 @@ static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y
     P.pool_chunks = 0;
     P.fallback_tiles = nullptr;
     P.use_fallback_list = 0;
+    static const int heavy_fused = getenv("RTGS_HEAVY_FUSED") ? atoi(getenv("RTGS_HEAVY_FUSED")) : 1;
+    P.heavy_fused = heavy_fused;
     P.nbands = 0;
     P.band_macro_cols = 1;
     P.macro_rows = mrows;

@@ -224,8 +224,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
                 finish_tile(group * TILES_PER_GROUP + t, head[t], count[t], ok[t]);
             }
             __syncwarp();
+        } else if (P.heavy_fused) {
+            // ---- the group's list did not fit shared memory: its frustum holds ~1000 Gaussians or more, typically
+            // because it looks along a surface.  Listing them all is the wrong plan - the rays will have their K
+            // nearest hits after a small part of them - so the tiles go to the fused kernel, which traverses near
+            // first and prunes by distance as its hit buffers fill (render.cu)
+#pragma unroll 1
+            for (int sub = 0; sub < TILES_PER_GROUP; ++sub) {
+                const int i0 = gi0 + (sub / GROUP_TJ) * TILE_I, j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
+                if (i0 >= xe || j0 >= ye) continue;
+                finish_tile(group * TILES_PER_GROUP + sub, -1, 0, false);
+            }
         } else {
-            // ---- the group's list did not fit shared memory: one traversal per tile, leaves stream out -------
+            // ---- (RTGS_HEAVY_FUSED=0) one traversal per tile, leaves stream out -------
 #pragma unroll 1
             for (int sub = 0; sub < TILES_PER_GROUP; ++sub) {
                 const int i0 = gi0 + (sub / GROUP_TJ) * TILE_I, j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
