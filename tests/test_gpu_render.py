@@ -293,6 +293,35 @@ def test_sample_state_machine():
     assert np.abs(rt.sample_buf.to_numpy() - O.render(gs, ocam2, depth=4)["rgb"]).max() <= TOL
 
 
+def test_overflowing_groups_take_the_pruning_kernel():
+    """A wall of large splats: every 8x16-pixel group frustum holds more candidates than its shared-memory list, so
+    k_tile_lists hands the tiles to k_render, which traverses near first and prunes by distance once the hit buffers
+    are full (most Gaussians of the wall are never tested).  Image within tolerance of the brute-force oracle for
+    depth 16 and 32, default route and fused-only route."""
+    rng = np.random.default_rng(77)
+    n = 6000
+    gs = random_set(n, seed=78, mean_scale=0.25)
+    gs.pos[:, 0] = rng.uniform(-0.9, 0.9, n)          # a slab 1.8 thick in front of the camera (which looks along -x)
+    gs.opacity[:] = rng.uniform(0.2, 0.95, n)
+    scene = make_scene(gs)
+    cam, ocam = make_camera(0.0, np.pi / 2, 2.6, 96, 64)
+    from rtgs.ray_tracer import RayTracer
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    for depth in (16, 32):
+        ref = O.render(gs, ocam, depth=depth)
+        assert np.minimum(ref["nhit"], depth).mean() > 0.9 * depth      # the buffers do fill
+        for mode in (0, 1):
+            scene.set_option("render_mode", mode)
+            img = rt.render(depth).copy()
+            mx, ps, bad = compare(img, ref["rgb"], TOL)
+            assert mx <= TOL and ps >= 60.0, (depth, mode, mx, ps)
+            rt.render_device(depth, collect_stats=True)
+            st = rt.last_stats
+            if mode == 0 and depth == 16:
+                assert st["fallback_tiles"] > 0.5 * (96 // 4) * (64 // 8)      # the groups overflowed
+    scene.set_option("render_mode", 0)
+
+
 def test_pipelined_sweep_is_bit_identical_to_synchronous_renders():
     """RayTracer.render_async / sweep (rtgs_render_host_submit / _collect: two frames in flight, frame f+1
     renders while the tail of frame f is copied out) deliver exactly the frames render() does, in order."""
