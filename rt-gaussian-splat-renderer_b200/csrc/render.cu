@@ -689,6 +689,8 @@ static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y
     P.use_fallback_list = 0;
     static const int heavy_fused = getenv("RTGS_HEAVY_FUSED") ? atoi(getenv("RTGS_HEAVY_FUSED")) : 1;
     P.heavy_fused = heavy_fused;
+    static const int heavy_limit = getenv("RTGS_HEAVY_LIMIT") ? atoi(getenv("RTGS_HEAVY_LIMIT")) : 1 << 30;
+    P.heavy_limit = heavy_limit;
     P.nbands = 0;
     P.band_macro_cols = 1;
     P.macro_rows = mrows;

@@ -61,6 +61,7 @@ struct RenderParams {
     int* fallback_tiles;      // ntiles
     int use_fallback_list;    // k_render: take tile ids from fallback_tiles[0 .. counters[2])
     int heavy_fused;          // k_tile_lists: a group whose list overflows shared memory goes to k_render (distance pruning)
+    int heavy_limit;          // ... "overflows" = more candidates than this (<= the capacity of the shared-memory list)
     // band completion (host-pipelined framebuffer copy, rtgs_render_host): the frame is cut into nbands bands of
     // band_macro_cols 32-pixel columns; a band is finished when all its tile ids have been rendered or skipped
     int nbands, band_macro_cols, macro_rows, schedule;

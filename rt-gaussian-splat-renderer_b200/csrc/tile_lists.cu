@@ -141,7 +141,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
             __syncwarp();
 #pragma unroll 1
             while (top > 0) {
-                if (ng > GLIST_CAP - 64) {   // too many candidates for the shared list
+                if (ng > min(GLIST_CAP - 64, P.heavy_limit)) {   // too many candidates for the shared list
                     per_tile = true;
                     break;
                 }

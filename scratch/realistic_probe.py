@@ -51,6 +51,8 @@ for v in range(16):
     for kk, vv in rt.last_stats.items(): agg[kk] = agg.get(kk, 0) + vv
 print("kbar %.2f hit %.3f cand/tile %.1f useful/tile %.1f fallback tiles %d" % (agg["layers"]/agg["rays"], agg["rays_hit"]/agg["rays"],
       agg["candidates"]/max(agg["tiles"],1), agg["useful_candidates"]/max(agg["tiles"],1), agg["fallback_tiles"]), flush=True)
+for v in range(4):   # warm-up of the non-stats kernel variants (lazy module loading would land in the first timed frame)
+    cam.position, cam.rotation = views[v]; rt.render_device(16, out=out)
 torch.cuda.synchronize()
 scene.set_option("kernel_timing", 32)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
