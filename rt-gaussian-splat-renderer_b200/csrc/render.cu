@@ -12,7 +12,11 @@
 // the tile is a thin pyramid bounded by 4 planes through the origin.  The warp traverses the LBVH
 // ONCE for the tile: up to 32 nodes are popped from a shared-memory stack per step, each lane
 // tests the two child boxes of its node against the 4 planes, and survivors are compacted back with
-// ballot/popc (internal children -> stack, leaves -> candidate queue).  Candidates are staged 32 at
+// ballot/popc (internal children -> stack, the nearer one on top; leaves -> candidate queue).  Once rays hold
+// K hits the traversal prunes by distance as well - the K-nearest form of the reference's far pruning
+// (scene.py:417-419): a box beyond the farthest kept hit of every full ray that also misses the pyramid of the
+// rays still lacking hits is dropped.  That makes this kernel the right one for tiles whose frustum holds
+// thousands of Gaussians (k_tile_lists sends it the groups whose list overflows).  Candidates are staged 32 at
 // a time (one lane each, float64: origin shifted to the closest point of the tile's centre ray)
 // and then every lane tests its own ray against every staged candidate with broadcast
 // shared-memory reads: first a conservative 5-FMA quadratic (q - 3 as a polynomial of the pixel

@@ -14,7 +14,8 @@
 //   precise  warp-wide rounds, each lane takes the next set bit of its mask: exact decision (float32
 //            in the tile-centred frame, float64 from the raw parameters inside the error band), entry
 //            distance, alpha; the hit goes to the lane's K-entry buffer in shared memory (replace-max
-//            once K are held).
+//            once K are held; the nearest hit left outside is remembered, and if it is within float32
+//            rounding of the farthest kept entry the two are compared in float64 after the list).
 // After the list: the lane's entries are ordered by a bitonic network over (entry-distance bits | slot) keys in
 // registers (near ties by their float64 entry distances), composited in that order with the SH basis evaluated
 // once per ray (six 256-bit loads per layer), and stored sector-aligned.
