@@ -39,6 +39,8 @@ def build_parser() -> argparse.ArgumentParser:
     # headless additions
     p.add_argument("--synthetic", default=None, help="render a synthetic bench scene (rtgs.synthetic.CONFIGS name) "
                                                      "instead of --open")
+    p.add_argument("--export-ply", type=pathlib.Path, default=None,
+                   help="with --synthetic: also write the scene as a 62-property 3DGS .ply (the reference can load it)")
     p.add_argument("--theta", type=float, default=0.0)
     p.add_argument("--phi", type=float, default=float(np.pi / 2))
     p.add_argument("--radius", type=float, default=1.0)
@@ -91,6 +93,10 @@ def main(argv=None) -> int:
         from .synthetic import CONFIGS, make_scene
         n, seed, deg, _ = CONFIGS[args.synthetic]
         a = make_scene(n, seed, deg)
+        if args.export_ply is not None:
+            from .synthetic import export_ply
+            export_ply(args.export_ply, a)
+            logger.info("wrote %s", args.export_ply)
         scene.from_arrays(a["pos"], a["rot"], a["scale"], a["color"], a["opacity"], a["sh"])
     elif args.open is not None:
         scene.load_file(args.open, args.scale)

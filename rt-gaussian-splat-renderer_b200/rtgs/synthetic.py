@@ -44,3 +44,27 @@ def make_scene(n: int, seed: int, sh_degree: int = 3, h_target: float = H_TARGET
     opacity = sigmoid(opacity_logit)                               # scene.py:114
     return dict(pos=pos, rot=rot.astype(f32), scale=scale.astype(f32), color=color.astype(f32),
                 opacity=opacity.astype(f32), sh=sh)
+
+
+def export_ply(path, arrays: dict) -> None:
+    """Write post-activation arrays (``make_scene``) as a 62-property 3DGS ``.ply`` in the layout of
+    tests/data/test.ply, undoing the loader's activations (scene.py:101-114: log scale, logit colour / opacity,
+    scalar-first quaternion, channel-major ``f_rest``), so that the reference itself - or ``Scene.load_file`` here -
+    can consume the bench scenes."""
+    from .ply import write_gs_ply
+    f64 = np.float64
+    logit = lambda p: np.log(np.asarray(p, f64)) - np.log1p(-np.asarray(p, f64))
+    pos, rot = np.asarray(arrays["pos"]), np.asarray(arrays["rot"])
+    cols = {"x": pos[:, 0], "y": pos[:, 1], "z": pos[:, 2],
+            "rot_0": rot[:, 3], "rot_1": rot[:, 0], "rot_2": rot[:, 1], "rot_3": rot[:, 2],
+            "opacity": logit(arrays["opacity"])}
+    ls = np.log(np.asarray(arrays["scale"], f64))
+    dc = logit(arrays["color"])
+    for k in range(3):
+        cols[f"scale_{k}"] = ls[:, k]
+        cols[f"f_dc_{k}"] = dc[:, k]
+    if arrays.get("sh") is not None:
+        rest = np.asarray(arrays["sh"]).reshape(-1, 15, 3).transpose(0, 2, 1).reshape(-1, 45)   # f_rest_{15c+k} = sh[k][c]
+        for i in range(45):
+            cols[f"f_rest_{i}"] = rest[:, i]
+    write_gs_ply(path, cols)

@@ -100,3 +100,20 @@ def test_vec_types():
 def test_sigmoid():
     x = np.array([-2.0, 0.0, 3.0], dtype=np.float32)
     assert sigmoid(x).dtype == np.float32 and np.allclose(sigmoid(x), 1 / (1 + np.exp(-x.astype(np.float64))), atol=1e-6)
+
+
+def test_synthetic_scene_round_trips_through_a_3dgs_ply(tmp_path):
+    """rtgs.synthetic.export_ply writes what the reference's loader (scene.py:95-114) reads: raw columns whose
+    activations give the bench scene back."""
+    from oracle import ref_numpy as O
+    from rtgs.ply import GS_PROPERTIES, read_ply
+    from rtgs.synthetic import export_ply, make_scene
+    a = make_scene(500, seed=11, sh_degree=3)
+    export_ply(tmp_path / "s.ply", a)
+    cols = read_ply(tmp_path / "s.ply")
+    assert list(cols) == GS_PROPERTIES and len(cols["x"]) == 500
+    act = O.activate(cols, 1.0)
+    for k, tol in (("pos", 0), ("rot", 1e-6), ("scale", 1e-6), ("color", 1e-6), ("opacity", 1e-6), ("sh", 0)):
+        got, want = np.asarray(act[k], np.float64), np.asarray(a[k], np.float64)
+        assert got.shape == want.shape, k
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max()), k
