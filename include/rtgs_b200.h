@@ -174,8 +174,8 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value);
 int rtgs_scene_read_kernel_times(rtgs_scene* s, int32_t frames, float* ms /* frames * RTGS_NUM_KERNELS */);
 
 /* Pinned (page-locked, device-mapped) host memory for image outputs.  rtgs_render_host is
- * fastest when its output buffers come from here (the kernel then writes the framebuffer
- * straight into host memory over PCIe while it renders); any host pointer is accepted. */
+ * fastest when its output buffers come from here (DMA straight into the destination,
+ * overlapped with the render); rtgs_render_host_submit requires it. */
 int rtgs_host_alloc(size_t bytes, void** out);
 int rtgs_host_free(void* p);
 
@@ -193,9 +193,10 @@ int rtgs_ipc_close(int device, void* p);
 
 /* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
  * RayTracer makes: camera in, image out): `host_rgb` ((w,h,3) float32) and optionally
- * `host_T` ((w,h)).  Synchronous.  Pinned buffers (rtgs_host_alloc, cudaHostAlloc,
- * cudaHostRegister) are written by the render kernel directly (zero-copy) or by one DMA;
- * pageable buffers are staged through library-owned pinned memory. */
+ * `host_T` ((w,h)).  Synchronous.  For pinned buffers (rtgs_host_alloc, cudaHostAlloc,
+ * cudaHostRegister) the frame is rendered into device memory in up to 24 bands of 32-pixel
+ * columns and every band's DMA is queued as soon as the kernels flag it complete, so the copy
+ * overlaps the render; pageable buffers are staged through library-owned pinned memory. */
 int rtgs_render_host(rtgs_scene* s, const rtgs_camera* cam,
                      int32_t x0, int32_t y0, int32_t w, int32_t h,
                      int32_t depth, float t_cut, float* host_rgb, float* host_T);

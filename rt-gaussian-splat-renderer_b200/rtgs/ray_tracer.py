@@ -118,7 +118,8 @@ class RayTracer:
 
         With ``pinned=True`` (default) the image lands in a pinned host buffer owned by this RayTracer
         and reused by the next ``render()`` of the same size (copy it if you need to keep it); the
-        kernel writes that buffer directly over PCIe.  ``out`` may name any float32 (w,h,3) host array
+        frame is copied into it band by band while later bands still render.  For a sweep over many poses
+        use ``render_async`` / ``sweep``.  ``out`` may name any float32 (w,h,3) host array
         instead; ``pinned=False`` returns a fresh pageable array."""
         W, H = self.buf_size.x, self.buf_size.y
         x0, y0, w, h = (0, 0, W, H) if tile is None else tile
