@@ -158,3 +158,57 @@ def test_camera_rays_centre_and_layout():
     assert np.allclose(d[2, 1], [-1, 0, 0], atol=1e-6)             # centre pixel looks at the origin
     assert d[4, 1, 1] > d[0, 1, 1]                                  # i grows to the right (+y here)
     assert d[2, 2, 2] > d[2, 0, 2]                                  # j grows upward (+z here)
+
+
+# ---- size-independent properties of the image oracle ---------------------------------------------------------------
+def _rand_set(n, seed, sh=False):
+    rng = np.random.default_rng(seed)
+    q = rng.normal(size=(n, 4))
+    q /= np.linalg.norm(q, axis=1, keepdims=True)
+    return O.GaussianSet(pos=rng.uniform(-1, 1, (n, 3)), rot=q, scale=np.exp(rng.normal(np.log(0.12), 0.5, (n, 3))),
+                         color=rng.uniform(0, 1, (n, 3)), opacity=rng.uniform(0.1, 0.95, n),
+                         sh=rng.normal(0, 0.15, (n, 15, 3)) if sh else None)
+
+
+def test_image_is_invariant_under_a_rigid_motion_of_scene_and_camera():
+    """Without SH (whose colour depends on the world direction) moving every Gaussian and the camera by the same
+    rotation + translation must not change a pixel: pins the quaternion conventions of Sigma = R S S^T R^T
+    (gaussian.py:86-102) against those of the camera rays (camera.py:31-55)."""
+    gs = _rand_set(300, 5)
+    pos, rot = O.orbit_pose(0.4, 1.1, 2.6)
+    cam = O.CameraParams(np.asarray(pos), np.asarray(rot), 48, 32, (40.0, 40.0))
+    a = O.render(gs, cam, depth=16)
+    g = np.array([0.3, -0.5, 0.2, 0.79])
+    g /= np.linalg.norm(g)
+    t = np.array([0.7, -1.3, 2.1])
+    gs2 = O.GaussianSet(pos=O.rot_vec3(g, gs.pos) + t, rot=O.quat_mul(g, gs.rot), scale=gs.scale, color=gs.color,
+                        opacity=gs.opacity, sh=None)
+    cam2 = O.CameraParams(O.rot_vec3(g, np.asarray(pos)) + t, O.quat_mul(g, np.asarray(rot)), 48, 32, (40.0, 40.0))
+    b = O.render(gs2, cam2, depth=16)
+    # (the moved parameters are rounded to float32 again when the set is built: invariance up to that rounding)
+    assert np.abs(a["rgb"] - b["rgb"]).max() < 2e-6 and (a["nhit"] != b["nhit"]).mean() < 1e-3
+
+
+def test_depth_prefix_permutation_and_colour_linearity():
+    gs = _rand_set(400, 9, sh=True)
+    pos, rot = O.orbit_pose(1.0, 1.3, 2.4)
+    cam = O.CameraParams(np.asarray(pos), np.asarray(rot), 40, 30, (36.0, 36.0))
+    full = O.render(gs, cam, depth=16)
+    # the order of the Gaussians in memory does not matter
+    perm = np.random.default_rng(1).permutation(gs.n)
+    gp = O.GaussianSet(pos=gs.pos[perm], rot=gs.rot[perm], scale=gs.scale[perm], color=gs.color[perm],
+                       opacity=gs.opacity[perm], sh=gs.sh[perm])
+    assert np.abs(O.render(gp, cam, depth=16)["rgb"] - full["rgb"]).max() < 1e-12
+    # front-to-back compositing: T never increases with depth, and every partial sum is a prefix of the next
+    prev = O.render(gs, cam, depth=1)
+    for d in (2, 4, 8, 16):
+        cur = O.render(gs, cam, depth=d)
+        assert (cur["T"] <= prev["T"] + 1e-15).all()
+        same = np.asarray(cur["nhit"]).reshape(-1) <= d // 2                        # rays that gained no layer
+        assert same.any() and (~same).any()
+        assert np.abs(cur["rgb"].reshape(-1, 3)[same] - prev["rgb"].reshape(-1, 3)[same]).max() < 1e-12
+        assert (np.abs(cur["rgb"].reshape(-1, 3)[~same] - prev["rgb"].reshape(-1, 3)[~same]).max(axis=1) > 0).mean() > 0.9
+        prev = cur
+    # the image is linear in the colours: scaling DC colour and SH by s scales every pixel by s
+    gl = O.GaussianSet(pos=gs.pos, rot=gs.rot, scale=gs.scale, color=0.5 * gs.color, opacity=gs.opacity, sh=0.5 * gs.sh)
+    assert np.abs(O.render(gl, cam, depth=16)["rgb"] - 0.5 * full["rgb"]).max() < 1e-12
