@@ -83,3 +83,36 @@ def test_depth_truncation_is_a_prefix():
     rt.render_device(16, out_T=T)
     Tn = T.cpu().numpy()
     assert Tn.min() >= 0.0 and Tn.max() <= 1.0
+
+
+def test_full_size_frame_is_invariant_under_a_rigid_motion():
+    """Size-independent property at bench size (config 2: 100 k Gaussians, SH degree 0, 1920x1080): moving every
+    Gaussian and the camera by the same rotation + translation gives the same image.  The moved parameters are
+    rounded to float32 again (1e-7 of the scene size = 5e-5 in q for these 0.008-sized splats), which flips the
+    sqrt(3)-sigma silhouette decision of a few dozen of the 2 M rays (alpha jumps by 0.05 * opacity there; 42 pixels
+    above 1e-3 when written), hence a count and a PSNR instead of a bare max-abs."""
+    from rtgs.camera import Camera
+    from rtgs.orbit import focal_from_fov, orbit_pose
+    from rtgs.ray_tracer import RayTracer
+    from rtgs.scene import Scene
+    from rtgs.synthetic import CONFIGS, FOV_DEG, ORBIT_R, make_scene
+    n, seed, deg, (W, H) = CONFIGS["100k_deg0_1080p"]
+    a = make_scene(n, seed, deg)
+    f = focal_from_fov(H, FOV_DEG)
+    pos, rot = orbit_pose(0.9, np.pi / 2, ORBIT_R)
+
+    def frame(p, q, cpos, crot):
+        scene = Scene().from_arrays(p, q, a["scale"], a["color"], a["opacity"], None)
+        cam = Camera(cpos, crot, (W, H), (f, f))
+        return RayTracer((W, H), scene, cam, t_cut=0.0).render(16).copy()
+
+    img0 = frame(a["pos"], a["rot"], pos, rot)
+    g = np.array([0.3, -0.5, 0.2, 0.79])
+    g /= np.linalg.norm(g)
+    t = np.array([0.25, -0.4, 0.3])
+    p64, q64 = a["pos"].astype(np.float64), a["rot"].astype(np.float64)
+    img1 = frame((O.rot_vec3(g, p64) + t).astype(np.float32), O.quat_mul(g, q64).astype(np.float32),
+                 O.rot_vec3(g, np.asarray(pos, np.float64)) + t, O.quat_mul(g, np.asarray(rot, np.float64)))
+    d = np.abs(img0.astype(np.float64) - img1).max(axis=-1)
+    assert (d > 1e-3).sum() <= 400 and np.median(d[d > 0]) < 1e-6, ((d > 1e-3).sum(), d.max())
+    assert O.psnr(img0, img1) >= 70.0
