@@ -54,12 +54,13 @@ def parse_args():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="1m_deg3_1080p")
-    ap.add_argument("--sharding", default="views", choices=["views", "tiles"],
-                    help="multi-GPU partition: camera views (weak scaling, default) or 32-column stripes of every "
-                         "frame gathered on rank 0 (strong scaling)")
-    ap.add_argument("--gather", default="peer", choices=["peer", "nccl"],
-                    help="--sharding tiles: every rank stores its stripes straight into rank 0's framebuffer over "
-                         "NVLink (CUDA IPC peer mapping, default) or packs them for one NCCL gather")
+    ap.add_argument("--no-tiles", action="store_true",
+                    help="skip the tile-sharded (strong-scaling) measurement that follows the view-sharded one")
+    ap.add_argument("--tile-modes", default="0,2",
+                    help="render modes tried for the tile-sharded frames (0 = two launches, 2 = one-launch frame kernel); "
+                         "the faster one is reported, all are listed")
+    ap.add_argument("--config4", action="store_true",
+                    help="also measure BASELINE config 4 (3 M Gaussians, 3840x2160, tiles over all GPUs); default at 8 GPUs")
     ap.add_argument("--h-target", type=float, default=None,
                     help="diagnostic: expected ellipsoid crossings per cube-spanning ray of the synthetic scene "
                          "(default 16, SURVEY.md 8d); larger = bigger Gaussians, denser tiles")
@@ -70,8 +71,6 @@ def parse_args():
                     help="diagnostic: move this many Gaussians ~4000 scene radii away (what stray points of a "
                          "trained scene do to 10-bit-per-axis Morton codes)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-numa-bind", action="store_true",
-                    help="multi-GPU: do not pin each rank to the CPU cores next to its GPU")
     ap.add_argument("--cpu-stride", type=int, default=0, help="pixel subsample stride of the CPU legs (0 = auto)")
     return ap.parse_args()
 
@@ -161,6 +160,8 @@ def cpu_leg(cfg_name, scene_arrays, W, H, focal, views, steps, warmup, stride):
     from oracle import ref_cpu
     from oracle import ref_numpy as O
     ref_cpu.build()
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU arm must use every core this process may run on
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     t0 = time.perf_counter()
     cs = ref_cpu.CpuScene(scene_arrays["pos"], scene_arrays["rot"], scene_arrays["scale"], scene_arrays["color"],
                           scene_arrays["opacity"], scene_arrays["sh"])
@@ -171,15 +172,213 @@ def cpu_leg(cfg_name, scene_arrays, W, H, focal, views, steps, warmup, stride):
         pos, rot = views[s % N_VIEWS]
         cam = O.CameraParams(np.asarray(pos), np.asarray(rot), W, H, (focal, focal))
         t0 = time.perf_counter()
-        cs.render(cam, DEPTH, pixels=pix, precision="float")
+        cs.render(cam, DEPTH, pixels=pix, precision="float", threads=threads)
         dt = time.perf_counter() - t0
         if s >= warmup:
             times.append(dt)
     total = sum(times)
     return {"mrays": pix.shape[0] * len(times) / total / 1e6, "ms_per_step": 1e3 * total / len(times),
-            "cores": ref_cpu.max_threads(), "rays_per_step": int(pix.shape[0]), "build_s": build_s,
+            "cores": threads, "rays_per_step": int(pix.shape[0]), "build_s": build_s,
             "sample": f"every {stride}th column and row of each {W}x{H} view ({pix.shape[0]} rays/step), "
                       f"{len(times)} steps, float32, K={DEPTH} closest-hit restarts over the LBVH"}
+
+
+def views_of(W, H):
+    return make_views(W, H)
+
+
+class TwoStreams:
+    """Two CUDA streams used alternately, frame by frame, bracketed by events on the default stream: frames on
+    different streams use different frame scratch in the library (csrc/render.cu), so the head of frame f+1
+    overlaps the tail of frame f on the device."""
+
+    def __init__(self, torch, n=2):
+        self.torch = torch
+        self.streams = [torch.cuda.Stream() for _ in range(n)]
+
+    def begin(self):
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        for s in self.streams:
+            s.wait_event(e)
+        return e
+
+    def stream(self, k):
+        return self.torch.cuda.stream(self.streams[k % len(self.streams)])
+
+    def end(self):
+        cur = self.torch.cuda.current_stream()
+        for s in self.streams:
+            cur.wait_stream(s)
+        e = self.torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+
+def allmax(dist, torch, vals):
+    if dist is None:
+        return list(vals)
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.tolist()
+
+
+def allgather(dist, torch, vals, world):
+    t = torch.tensor(list(vals), dtype=torch.float64, device="cuda")
+    if dist is None:
+        return [t.tolist()]
+    out = [torch.zeros_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [o.tolist() for o in out]
+
+
+def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W, H, steps, warmup, barrier, modes):
+    """Strong scaling of ONE frame (BASELINE configs 3 / 4): 32-pixel column stripes dealt round-robin to the ranks,
+    every rank's kernels store straight into rank 0's framebuffer over NVLink (rtgs.sharding.PeerFrame), hand-over
+    by device-side counters - no collective, no host synchronisation.  Measures, in the same processes:
+      t1   rank 0 alone renders the whole frame (the 1-GPU reference of the speed-up), latency and two-stream
+      tN   all ranks, one frame in flight per rank (frame latency) and frames alternating on two streams (throughput)
+    and verifies the assembled frame bit for bit against rank 0's own full render."""
+    from rtgs.sharding import PeerFrame
+    res = {}
+    out_local = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
+    ts = TwoStreams(torch)
+    nv = len(views)
+
+    def set_view(s):
+        cam.position, cam.rotation = views[s % nv]
+
+    def timed(step_fn, two_streams, n_warm, n_steps):
+        for s in range(n_warm):
+            set_view(s)
+            step_fn(s, None)
+        barrier()
+        if two_streams:
+            e0 = ts.begin()
+            for s in range(n_steps):
+                set_view(s)
+                with ts.stream(s):
+                    step_fn(s, None)
+            e1 = ts.end()
+        else:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for s in range(n_steps):
+                set_view(s)
+                step_fn(s, None)
+            e1.record()
+        barrier()
+        return e0.elapsed_time(e1) / n_steps
+
+    # ---- 1-GPU reference on rank 0 (whole frames, same views), in each candidate render mode
+    scene.set_stripe()
+    single = {}
+    for mode in modes:
+        scene.set_option("render_mode", mode)
+        if rank == 0:
+            single[mode] = (timed(lambda s, _: rt.render_device(DEPTH, out=out_local), False, warmup, steps),
+                            timed(lambda s, _: rt.render_device(DEPTH, out=out_local), True, warmup, steps))
+        else:
+            barrier(); barrier(); barrier(); barrier()
+    t1_lat = min(v[0] for v in single.values()) if rank == 0 else 0.0
+    t1_pipe = min(min(v) for v in single.values()) if rank == 0 else 0.0
+
+    # ---- all ranks: stripes into rank 0's frame
+    peer = PeerFrame(W, H, rank, world, local_rank, dist, slots=1, buffers=4)
+    scene.set_stripe(world, rank)
+
+    def tile_step(s, _):
+        rt.render_device(DEPTH, out=peer.begin(scene))
+        if rank == 0:
+            peer.wait()
+            peer.release()
+
+    per_mode = {}
+    for mode in modes:
+        scene.set_option("render_mode", mode)
+        lat = timed(tile_step, False, warmup, steps)
+        pipe = timed(tile_step, True, warmup, steps)
+        scene.set_option("kernel_timing", min(steps, 256))
+        timed(tile_step, False, 0, min(steps, 256))
+        kt = scene.read_kernel_times(min(steps, 256)).astype(np.float64).mean(axis=0)
+        scene.set_option("kernel_timing", 0)
+        lat, pipe = allmax(dist, torch, [lat, pipe])
+        per_rank = allgather(dist, torch, kt.tolist(), world)
+        per_mode[mode] = {"ms_per_frame": lat, "ms_per_frame_two_streams": pipe, "kernel_names": list(scene.kernel_names),
+                          "kernels_ms_per_rank": [[round(v, 5) for v in r] for r in per_rank]}
+    best = min(per_mode, key=lambda m: per_mode[m]["ms_per_frame_two_streams"])
+    scene.set_option("render_mode", best)
+
+    # ---- untimed check: the assembled frame == rank 0's own full-frame render, bit for bit
+    set_view(0)
+    torch.cuda.synchronize()
+    barrier()
+    tile_step(0, None)
+    torch.cuda.synchronize()
+    barrier()
+    verified = None
+    if rank == 0:
+        assembled = peer.frame().clone()
+        scene.set_stripe()
+        set_view(0)
+        full = rt.render_device(DEPTH, out=out_local)
+        torch.cuda.synchronize()
+        verified = bool(torch.equal(full, assembled))
+        scene.set_stripe(world, rank)
+    barrier()
+
+    # ---- end to end: every frame delivered to pinned host memory on rank 0 (one DMA of the gathered frame)
+    host = [torch.empty((W, H, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else None
+
+    def e2e_step(s, _):
+        rt.render_device(DEPTH, out=peer.begin(scene))
+        if rank == 0:
+            peer.wait()
+            host[s % 2].copy_(peer.frame(), non_blocking=True)
+            peer.release()
+
+    for s in range(2):
+        set_view(s)
+        e2e_step(s, None)
+    torch.cuda.synchronize()
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(steps):
+        set_view(s)
+        with ts.stream(s):
+            e2e_step(s, None)
+    torch.cuda.synchronize()
+    barrier()
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
+    (e2e_ms,) = allmax(dist, torch, [e2e_ms])
+    scene.set_stripe()
+    scene.set_option("render_mode", modes[0])
+    peer.close()
+    if rank != 0:
+        return None
+    b = per_mode[best]
+    k = b["kernels_ms_per_rank"]
+    kmax = [max(r[i] for r in k) for i in range(3)]
+    dom = int(np.argmax(kmax))
+    res = {"resolution": [W, H], "frames": steps, "render_mode": best,
+           "ms_per_frame": b["ms_per_frame_two_streams"], "mrays": W * H / b["ms_per_frame_two_streams"] / 1e3,
+           "ms_per_frame_latency": b["ms_per_frame"],
+           "ms_per_frame_1gpu": t1_pipe, "ms_per_frame_1gpu_latency": t1_lat,
+           "speedup_vs_n1": t1_pipe / b["ms_per_frame_two_streams"],
+           "speedup_vs_n1_latency": t1_lat / b["ms_per_frame"],
+           "verified_bit_identical": verified,
+           "limiting_kernel": {"name": b["kernel_names"][dom], "slowest_rank_ms": kmax[dom],
+                               "per_rank_ms": [r[dom] for r in k],
+                               "frame_minus_kernels_ms": b["ms_per_frame"] - sum(kmax)},
+           "by_mode": {str(m): {"ms_per_frame_latency": v["ms_per_frame"], "ms_per_frame_two_streams": v["ms_per_frame_two_streams"],
+                                "kernels": v["kernel_names"], "kernels_ms_per_rank": v["kernels_ms_per_rank"]}
+                       for m, v in per_mode.items()},
+           "single_gpu_by_mode": {str(m): {"ms_per_frame_latency": v[0], "ms_per_frame_two_streams": v[1]}
+                                  for m, v in single.items()},
+           "e2e": {"ms_per_frame": e2e_ms, "mrays": W * H / e2e_ms / 1e3, "d2h_bytes_per_frame": W * H * 12,
+                   "api": "stripes stored into rank 0's frame over NVLink, then one DMA to pinned host memory per frame"},
+           "gather": "peer stores + device-side arrive/grant counters (no collective)"}
+    return res
 
 
 def main():
@@ -193,9 +392,8 @@ def main():
     config = {"workload": f"synthetic {n_g} random Gaussians, SH degree {sh_deg}, seed {seed}, {W}x{H}, fov 60, "
                           f"orbit r=2.2, depth {DEPTH}, t_cut {T_CUT}; 64-view orbit, view (step*N+rank)%64",
               "gaussians": n_g, "sh_degree": sh_deg, "resolution": [W, H], "depth": DEPTH,
-              "sharding": "camera views (scene replicated, no collective)" if args.sharding == "views" else
-                          "32-column stripes of every frame, dealt round-robin (scene replicated; the finished "
-                          "stripes are gathered on rank 0 after the render)",
+              "sharding": "camera views (scene replicated, no collective; at N > 1 every rank's kernels store their "
+                          "frame into GPU 0's memory over NVLink and GPU 0 waits for the arrival counters)",
               "l2": "inputs larger than L2 (packed scene 528 MB > 126 MB) and a new view every step"}
 
     # ------------------------------------------------------------------ reference arm (CPU port)
@@ -224,9 +422,6 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the render path has no CPU fallback")
     torch.cuda.set_device(local_rank)
-    from rtgs.sharding import bind_to_gpu_numa_node
-    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not args.no_numa_bind else {"bound": False,
-                                                                                         "why": "not requested"}
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -247,39 +442,38 @@ def main():
         config["workload"] += " [LBVH with 63-bit Morton codes]"
     focal, views = make_views(W, H)
     t0 = time.perf_counter()
-    scene = Scene(device=local_rank, morton_bits=args.morton_bits or "auto").from_arrays(arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"],
-                                                 arrays["opacity"], arrays["sh"])
+    scene = Scene(device=local_rank, morton_bits=args.morton_bits or "auto").from_arrays(
+        arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"], arrays["opacity"], arrays["sh"])
     torch.cuda.synchronize()
     build_ms = 1e3 * (time.perf_counter() - t0)
     cam = Camera(views[0][0], views[0][1], (W, H), (focal, focal), device=local_rank)
     rt = RayTracer((W, H), scene, cam, t_cut=T_CUT)
     out = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
+    base_mode = scene.render_mode
+    bvh_build_ms, morton_bits = scene.build_ms, scene.morton_bits
+    kernel_names = [k or "-" for k in scene.kernel_names]
+    launches_per_frame = sum(1 for k in scene.kernel_names if k)
 
-    tiles = args.sharding == "tiles"
-    gather = None
     peer = None
-    if tiles:
-        from rtgs.sharding import PeerFrame, StripeGather
-        scene.set_stripe(world, rank)
-        if args.gather == "peer":
-            peer = PeerFrame(W, H, rank, world, local_rank, dist)
-            out = peer.tensor            # rank 0's image, peer-mapped on the other ranks
-        else:
-            gather = StripeGather(W, H, rank, world, torch.device("cuda", local_rank))
-        config["sharding"] += f" [{args.gather}]"
+    if world > 1:
+        # the multi-GPU frame time ends with the framebuffers resident on GPU 0.  Slot r of the
+        # peer-mapped buffer receives rank r's frame straight from its render kernels' stores.
+        from rtgs.sharding import PeerFrame
+        peer = PeerFrame(W, H, rank, world, local_rank, dist, slots=world, buffers=2)
 
     def set_view(step):
-        v = step % N_VIEWS if tiles else (step * world + rank) % N_VIEWS
+        v = (step * world + rank) % N_VIEWS
         cam.position, cam.rotation = views[v]
         return v
 
     def render_step():
-        rt.render_device(DEPTH, out=out)
-        if tiles and dist is not None:
-            if peer is not None:
-                peer.finish(dist)
-            else:
-                gather(out, dist)
+        if peer is None:
+            rt.render_device(DEPTH, out=out)
+            return
+        rt.render_device(DEPTH, out=peer.begin(scene, slot=rank))
+        if rank == 0:
+            peer.wait()          # all `world` frames of this step are in GPU 0's memory
+            peer.release()
 
     def barrier():
         if dist is not None:
@@ -287,15 +481,12 @@ def main():
         torch.cuda.synchronize()
 
     # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views (whole frames)
-    scene.set_stripe()
     agg = {}
     for s in range(min(args.steps, N_VIEWS)):
         set_view(s)
         rt.render_device(DEPTH, out=out, collect_stats=True)
         for k, v in rt.last_stats.items():
             agg[k] = agg.get(k, 0) + v
-    if tiles:
-        scene.set_stripe(world, rank)
     kbar = agg["layers"] / agg["rays"]
     bytes_ray = 16 + kbar * (64 + (192 if sh_deg > 0 else 0))
 
@@ -303,18 +494,19 @@ def main():
         set_view(s)
         render_step()
     barrier()
-    tiles_verified = None
-    if tiles:
-        # untimed check: the frame assembled from all ranks' stripes == rank 0's own full-frame render, bit for bit
+    gathered_ok = None
+    if peer is not None:
+        # untimed check of the gather: slot r on GPU 0 == what GPU 0 renders itself for rank r's view
         set_view(0)
         render_step()
         barrier()
         if rank == 0:
-            scene.set_stripe()
-            full = rt.render_device(DEPTH)
-            scene.set_stripe(world, rank)
+            got = [peer.frame(r).clone() for r in range(world)]
+            gathered_ok = True
+            for r in range(world):
+                cam.position, cam.rotation = views[r % N_VIEWS]
+                gathered_ok = gathered_ok and bool(torch.equal(rt.render_device(DEPTH, out=out), got[r]))
             torch.cuda.synchronize()
-            tiles_verified = bool(torch.equal(full, out))
         barrier()
     timed_frames = min(args.steps, 4096)
     scene.set_option("kernel_timing", timed_frames)   # events around every kernel of the timed steps
@@ -331,106 +523,112 @@ def main():
         ev[s][0].record()
         render_step()
         ev[s][1].record()
-        launches += 3     # k_tile_lists, k_shade_tiles, k_render (fallback list; returns at once when empty)
+        launches += launches_per_frame
     e_end.record()
     barrier()
     total_ms = e_beg.elapsed_time(e_end)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
-    per_kernel = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)   # ms: lists, shade, fused
+    per_kernel = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)   # ms of the frame's launches
     scene.set_option("kernel_timing", 0)
 
-    # end-to-end: public API call with host buffers (camera in, image out on the host)
-    if tiles:
-        host = torch.empty((W, H, 3), dtype=torch.float32, pin_memory=True) if rank == 0 else None
+    # end-to-end: public API call with host buffers (camera in, image out on the host), every rank its own frames
+    def blocking(n):
+        for s in range(n):
+            set_view(s)
+            rt.render(DEPTH)
 
-        def e2e_step():
-            render_step()
-            if rank == 0:
-                host.copy_(out, non_blocking=True)
-                torch.cuda.synchronize()
-    else:
-        def e2e_step():
-            return rt.render(DEPTH)
-    for s in range(min(args.warmup, 2)):
-        set_view(s)
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        set_view(s)
-        e2e_step()
-    barrier()
-    e2e_s = e2e_sync_s = time.perf_counter() - t0
-    e2e_kernels = None
-    if not tiles:
+    def pipelined(n):
         # the sweep API: every step still uploads its camera and delivers its image to pinned host memory, but
-        # two frames are in flight (RayTracer.render_async), so step s+1 renders while the tail of step s is
-        # copied out.  Every image is collected inside the timed region.
-        def pipelined(n):
-            prev = None
-            for s in range(n):
-                set_view(s)
-                cur = rt.render_async(DEPTH)
-                if prev is not None:
-                    prev.result()
-                prev = cur
-            prev.result()
-        pipelined(min(args.warmup, 3))
+        # two frames are in flight (RayTracer.render_async), so step s+1 renders while step s is copied out.
+        # Every image is collected inside the timed region.
+        prev = None
+        for s in range(n):
+            set_view(s)
+            cur = rt.render_async(DEPTH)
+            if prev is not None:
+                prev.result()
+            prev = cur
+        prev.result()
+
+    def wall(fn, n):
+        fn(min(args.warmup, 3))
         barrier()
         t0 = time.perf_counter()
-        pipelined(args.steps)
+        fn(n)
         barrier()
-        e2e_s = time.perf_counter() - t0
+        return time.perf_counter() - t0
+
+    e2e_sync_s = wall(blocking, args.steps)
+    e2e_pipe_s = wall(pipelined, args.steps)
     # the sampler has been running through all timed loops (device-timed steps and both end-to-end loops)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["window"] = "device-timed steps + end-to-end loops"
-    if not tiles:
-        # untimed repeat with the library's per-kernel events switched on: what the kernels cost in this mode
-        scene.set_option("kernel_timing", timed_frames)
-        pipelined(timed_frames)
-        e2e_kernels = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)
-        scene.set_option("kernel_timing", 0)
+    # untimed repeat with the library's per-kernel events switched on: what the kernels cost in the pipelined mode
+    scene.set_option("kernel_timing", timed_frames)
+    pipelined(timed_frames)
+    e2e_kernels = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)
+    scene.set_option("kernel_timing", 0)
 
-    if dist is not None:
-        t = torch.tensor([total_ms, e2e_s, e2e_sync_s, float(np.mean(kern_ms)), *per_kernel.tolist()],
-                         dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        total_ms, e2e_s, e2e_sync_s, kern_mean, *pk = t.tolist()
-        per_kernel = np.asarray(pk)
-    else:
-        kern_mean = float(np.mean(kern_ms))
+    total_ms, e2e_pipe_s, e2e_sync_s, kern_mean, *pk = allmax(
+        dist, torch, [total_ms, e2e_pipe_s, e2e_sync_s, float(np.mean(kern_ms)), *per_kernel.tolist()])
+    per_kernel = np.asarray(pk)
+
+    # ------------------------------------------------------------------ strong scaling: tile-sharded frames
+    tiles = tiles4 = None
+    tile_modes = [int(m) for m in args.tile_modes.split(",")]
+    if not args.no_tiles:
+        tiles = measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W, H,
+                              min(args.steps, 128), args.warmup, barrier, tile_modes)
+        scene.set_option("render_mode", base_mode)
+    if (world >= 8 or args.config4) and not args.no_tiles and args.config == "1m_deg3_1080p":
+        # BASELINE config 4: 3 M Gaussians, 3840x2160, tiles over all GPUs
+        n4, seed4, deg4, (W4, H4) = CONFIGS["3m_deg3_2160p"]
+        del rt, cam
+        scene._release()
+        a4 = make_scene(n4, seed4, deg4)
+        focal4, views4 = make_views(W4, H4)
+        scene4 = Scene(device=local_rank).from_arrays(a4["pos"], a4["rot"], a4["scale"], a4["color"], a4["opacity"], a4["sh"])
+        cam4 = Camera(views4[0][0], views4[0][1], (W4, H4), (focal4, focal4), device=local_rank)
+        rt4 = RayTracer((W4, H4), scene4, cam4, t_cut=T_CUT)
+        tiles4 = measure_tiles(torch, dist, rank, world, local_rank, scene4, rt4, cam4, views4, W4, H4,
+                               min(args.steps, 32), min(args.warmup, 3), barrier, tile_modes)
+        if tiles4 is not None:
+            tiles4["workload"] = f"synthetic {n4} random Gaussians, SH degree {deg4}, seed {seed4}, {W4}x{H4}"
 
     if rank == 0:
-        rays_step = W * H * (1 if tiles else world)
+        rays_step = W * H * world
         value = rays_step * args.steps / (total_ms * 1e-3) / 1e6
+        e2e_s = min(e2e_pipe_s, e2e_sync_s)
         e2e_val = rays_step * args.steps / e2e_s / 1e6
         peak, peak_src = load_peak()
-        from rtgs._native import KERNEL_NAMES
         dom = int(np.argmax(per_kernel))
         dom_ms = float(per_kernel[dom])
-        rays_launch = W * H / (world if tiles else 1)      # rays one launch of the kernel processes
+        rays_launch = W * H                                 # rays one launch of the kernel processes
         achieved = rays_launch * bytes_ray / (dom_ms * 1e-3) / 1e9
         step_ms = float(per_kernel.sum())
-        kernels = [{"kernel": KERNEL_NAMES[k], "ms": float(per_kernel[k]), "share": float(per_kernel[k] / step_ms)}
-                   for k in range(len(KERNEL_NAMES))]
+        kernels = [{"kernel": kernel_names[k], "ms": float(per_kernel[k]), "share": float(per_kernel[k] / step_ms)}
+                   for k in range(len(kernel_names)) if kernel_names[k] != "-"]
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
-            "scaling": "strong" if tiles else "weak",
+            "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 44 * world,
-                    "d2h_bytes_per_step": W * H * 3 * 4 * (1 if tiles else world),
+                    "d2h_bytes_per_step": W * H * 3 * 4 * world,
                     "ms_per_step": 1e3 * e2e_s / args.steps,
-                    "api": "stripes gathered on rank 0, then one copy to pinned host memory" if tiles else
-                           "RayTracer.render_async()/result(): two frames in flight, every image collected",
+                    "api": ("RayTracer.render_async()/result(): two frames in flight, every image collected"
+                            if e2e_pipe_s <= e2e_sync_s else "RayTracer.render() per step (blocking)") +
+                           " [the faster of the two loops; both are reported]",
+                    "pipelined_value": rays_step * args.steps / e2e_pipe_s / 1e6,
                     "sync_value": rays_step * args.steps / e2e_sync_s / 1e6,
                     "sync_api": "RayTracer.render() per step (blocking)",
-                    "kernels_ms": None if e2e_kernels is None else [round(float(v), 5) for v in e2e_kernels]},
+                    "kernels_ms": [round(float(v), 5) for v in e2e_kernels]},
             "gpu_launches": launches,
+            "render_mode": base_mode,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": load_traffic(KERNEL_NAMES[dom]), "peak_source": peak_src,
-                         "kernel": KERNEL_NAMES[dom], "kernel_ms": dom_ms, "step_ms": kern_mean,
+                         "traffic": load_traffic(kernel_names[dom]), "peak_source": peak_src,
+                         "kernel": kernel_names[dom], "kernel_ms": dom_ms, "step_ms": kern_mean,
                          "bytes_per_ray": bytes_ray, "kbar": kbar,
                          "note": "algorithmic bytes assume zero reuse between rays; neighbouring rays share "
                                  "Gaussians through L1/L2, so achieved may exceed what DRAM moved (see traffic)"},
@@ -445,13 +643,18 @@ def main():
                             "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1),
                             "useful_candidates_per_tile": agg["useful_candidates"] / max(agg["tiles"], 1),
                             "fallback_tiles": agg["fallback_tiles"]},
-            "bvh_build_ms": scene.build_ms,          # device time of the LBVH build kernels
-            "morton_bits": scene.morton_bits,
+            "bvh_build_ms": bvh_build_ms,            # device time of the LBVH build kernels
+            "morton_bits": morton_bits,
             "scene_load_ms": build_ms,               # wall: upload of the arrays + build (+ CUDA start-up on first use)
-            "numa_bind_rank0": numa,
         }
-        if tiles:
-            line["tiles_verified_bit_identical"] = tiles_verified
+        if peer is not None:
+            line["gathered_on_gpu0"] = {"verified_bit_identical": gathered_ok,
+                                        "how": "peer stores from every rank's render kernels + device-side arrival "
+                                               "counters; the device-timed value includes rank 0's wait for them"}
+        if tiles is not None:
+            line["tiles"] = tiles
+        if tiles4 is not None:
+            line["tiles_config4"] = tiles4
         if world == 1 and not args.no_cpu_baseline:
             stride = args.cpu_stride or (4 if W * H <= 1920 * 1080 else 8)
             r = cpu_leg(args.config, arrays, W, H, focal, views, min(args.steps, 32), 1, stride)   # ~10-20 s of CPU work

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define RTGS_ABI_VERSION 2
+#define RTGS_ABI_VERSION 3
 #define RTGS_MAX_DEPTH 32        /* largest `depth` rtgs_render composites in one pass */
 
 typedef enum rtgs_status {
@@ -83,8 +83,11 @@ int rtgs_scene_create(int device, int64_t n,
  * little-endian PLY vertex block (n rows of `stride_floats` float32), `col` the 59 column
  * offsets in the order x,y,z, f_dc_0..2, f_rest_0..44, opacity, scale_0..2, rot_0..3 (any
  * offset < 0 = property absent -> 0).  Applies the activations of scene.py:110-114 on device.
- * sh_layout: 0 = channel-major (sh_k[c] = f_rest_{15c+k}), 1 = "taichi as executed"
- * (sh_k[c] = f_rest_{3k+c}); see SURVEY.md §7 hard part 7. */
+ * sh_layout: 0 = channel-major (sh_k[c] = f_rest_{15c+k}: the 3DGS file layout, the intent of the reference's
+ * reshape((-1,3,15)), scene.py:106-107), 1 = interleaved (sh_k[c] = f_rest_{3k+c}: that (N,3,15) buffer
+ * reinterpreted flat as (N,15,3), which is what the Taichi stand-in behind the committed goldens executes).
+ * What real Taichi stores for the reference's untransposed copy (scene.py:122,127) is not verifiable offline;
+ * SURVEY.md §7 hard part 7 derives a third candidate.  The layouts are named for what they do. */
 int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices,
                                     int32_t stride_floats, const int32_t* col /*[59]*/,
                                     float scale, int32_t sh_layout, rtgs_scene** out);
@@ -136,9 +139,11 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
                 float* out_rgb, float* out_T, void* stream, rtgs_render_stats* stats);
 
 /* Tuning knobs of one scene's render path (no reference counterpart; defaults need no call).
- *  RTGS_OPT_RENDER_MODE      0 (default): k_tile_lists + k_shade_tiles, the fused kernel only for tiles whose
- *                            candidate list did not fit the pool; 1: the fused kernel alone.  depth > 16 always
- *                            uses the fused kernel.
+ *  RTGS_OPT_RENDER_MODE      2 (default): k_frame - traversal and shading of the frame in ONE launch (persistent
+ *                            warps alternate between the two; the fused kernel is tail-launched from the device
+ *                            only when some tile's candidate list did not fit the pool); 0: the same code as
+ *                            separate launches k_tile_lists + k_shade_tiles + k_render; 1: the fused kernel
+ *                            alone.  depth > 16 always uses the fused kernel.
  *  RTGS_OPT_LIST_POOL_CHUNKS capacity of the candidate-list pool in 128-byte chunks (31 candidates each);
  *                            -1 (default) = 16 chunks per 4x8-pixel tile of the rendered region, doubled whenever a
  *                            finished frame used more than 70 % of it.  A small pool is
@@ -161,15 +166,23 @@ typedef enum rtgs_option {
     RTGS_OPT_LIST_POOL_CHUNKS = 1,
     RTGS_OPT_KERNEL_TIMING = 2,
     RTGS_OPT_STRIPE = 3,
-    RTGS_OPT_MORTON_BITS = 4
+    RTGS_OPT_MORTON_BITS = 4,
+    RTGS_OPT_TREE_DEPTH = 5      /* read-only: depth of the deepest LBVH leaf (root = 0); the traversal stacks are
+                                  * sized for <= 96 (62 for unique 30-bit keys, 63 + 30 for repeated 63-bit codes)
+                                  * and rtgs_scene_build_bvh fails with RTGS_ERR_STATE beyond that */
 } rtgs_option;
 int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value);
+/* Current value of an option (RTGS_OPT_RENDER_MODE: the mode in effect, environment default included;
+ * RTGS_OPT_LIST_POOL_CHUNKS: the pool's present capacity; RTGS_OPT_MORTON_BITS: the width in use once built). */
+int rtgs_scene_get_option(const rtgs_scene* s, int32_t option, int64_t* value);
 
 /* Per-kernel device times (measurement only).  RTGS_OPT_KERNEL_TIMING = n > 0 makes every following render
  * bracket its kernels with CUDA events on the render stream (a ring of n frames; 0 switches it off).
  * rtgs_scene_read_kernel_times synchronises the device and returns, for the last `frames` renders (oldest
- * first), RTGS_NUM_KERNELS floats each: milliseconds of k_tile_lists, k_shade_tiles and the fused k_render
- * (0 for a kernel that did not run).  Fails with RTGS_ERR_STATE if fewer frames were timed. */
+ * first), RTGS_NUM_KERNELS floats each, the milliseconds of the frame's (up to) three launches in order:
+ * mode 0: k_tile_lists, k_shade_tiles, k_render; mode 2: 0, k_frame (a device-side tail launch of k_render
+ * included), host-launched k_render if any; mode 1: 0, 0, k_render.  Fails with RTGS_ERR_STATE if fewer
+ * frames were timed. */
 #define RTGS_NUM_KERNELS 3
 int rtgs_scene_read_kernel_times(rtgs_scene* s, int32_t frames, float* ms /* frames * RTGS_NUM_KERNELS */);
 
@@ -190,6 +203,28 @@ int rtgs_device_free(int device, void* p);
 int rtgs_ipc_export(int device, const void* dev_ptr, unsigned char* handle /*[64]*/);
 int rtgs_ipc_open(int device, const unsigned char* handle /*[64]*/, void** out);
 int rtgs_ipc_close(int device, void* p);
+
+/* Multi-GPU hand-over without a collective ("only the final framebuffer gathered, no NCCL on the hot
+ * path"; ray_tracer.py:85 - pixels are independent, so ranks exchange nothing but finished pixels).  The pointers
+ * are DEVICE pointers to 32-bit counters, typically in the gathering rank's memory and peer-mapped here
+ * (rtgs_ipc_open).  They apply to the NEXT frame launched on the scene (rtgs_render / _render_host*) and are
+ * cleared by it:
+ *   arrive       when the frame's last kernel has performed all its framebuffer stores, its last CTA increments
+ *                *arrive once at system scope (release).  The gathering rank waits for world x frames arrivals
+ *                (rtgs_stream_wait_counter) - no extra kernel on the producing ranks, no collective.
+ *   grant, grant_value   before a warp's first framebuffer store of the frame it waits until
+ *                (int32)(*grant - grant_value) >= 0: the consumer has released the buffer being overwritten
+ *                (rtgs_stream_set_counter on the consumer's stream); NULL = do not wait.
+ * rtgs_stream_wait_counter / _set_counter queue a one-thread kernel on `stream` of `device`; _set_counter raises the
+ * counter to `value` (a maximum, so that releases queued on different streams commute). */
+int rtgs_scene_set_frame_sync(rtgs_scene* s, uint32_t* arrive, const uint32_t* grant, uint32_t grant_value);
+int rtgs_stream_wait_counter(int device, const uint32_t* counter, uint32_t value, void* stream);
+int rtgs_stream_set_counter(int device, uint32_t* counter, uint32_t value, void* stream);
+
+/* Page-lock (and device-map) an existing host range, e.g. a POSIX shared-memory segment that several ranks
+ * deliver their stripes of one frame into (each over its own PCIe link).  Portable across devices. */
+int rtgs_host_register(void* p, size_t bytes);
+int rtgs_host_unregister(void* p);
 
 /* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
  * RayTracer makes: camera in, image out): `host_rgb` ((w,h,3) float32) and optionally

@@ -17,7 +17,7 @@ HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIBDIR = HERE / "lib"
 LIB = LIBDIR / os.environ.get("RTGS_LIB_NAME", "librtgs_b200.so")
-SOURCES = ["abi.cu", "lbvh.cu", "render.cu", "tile_lists.cu", "shade.cu"]
+SOURCES = ["abi.cu", "lbvh.cu", "render.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -25,6 +25,10 @@ FLAGS = [
     "-Xcompiler", "-fPIC",
     "-Xptxas", "-v",
 ] + os.environ.get("RTGS_NVCC_EXTRA", "").split()
+# RTGS_CDP=1: k_frame tail-launches k_render from the device (CUDA dynamic parallelism): relocatable device code
+CDP = os.environ.get("RTGS_CDP", "0") == "1"
+if CDP:
+    FLAGS += ["-rdc=true", "-DRTGS_CDP=1"]
 
 
 def _stale() -> bool:
@@ -62,7 +66,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if verbose:
         print("\n".join(log))
     cmd = [NVCC, "-shared", "-o", str(LIB), *[str(o) for _, o, _ in results],
-           "-gencode", "arch=compute_100a,code=sm_100a"]
+           "-gencode", "arch=compute_100a,code=sm_100a"] + (["-rdc=true", "-lcudadevrt"] if CDP else [])
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -4,6 +4,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <cmath>
 #include <new>
 
 #include "render_common.cuh"
@@ -50,8 +51,12 @@ void free_scene(rtgs_scene* s) {
     cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
     cudaFree(s->morton64);
     cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
-    cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
-    cudaFree(s->counters); cudaFree(s->stats_dev);
+    for (auto& fs : s->scratch) {
+        cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.ready);
+        cudaFree(fs.counters);
+        if (fs.free_event) cudaEventDestroy(fs.free_event);
+    }
+    cudaFree(s->stats_dev);
     for (auto& hs : s->host_slot) {
         cudaFree(hs.stage_rgb); cudaFree(hs.stage_T);
         if (hs.done) cudaEventDestroy(hs.done);
@@ -60,9 +65,9 @@ void free_scene(rtgs_scene* s) {
     if (s->pinned_rgb) cudaFreeHost(s->pinned_rgb);
     if (s->pinned_T) cudaFreeHost(s->pinned_T);
     if (s->own_stream) cudaStreamDestroy(s->own_stream);
+    if (s->own_stream2) cudaStreamDestroy(s->own_stream2);
     if (s->copy_stream) cudaStreamDestroy(s->copy_stream);
     if (s->copy_stream2) cudaStreamDestroy(s->copy_stream2);
-    if (s->scratch_free) cudaEventDestroy(s->scratch_free);
     cudaFree(s->band_done);
     if (s->band_flags) cudaFreeHost(s->band_flags);
     for (cudaEvent_t e : s->timing_events) cudaEventDestroy(e);
@@ -90,10 +95,12 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     CUDA_TRY(cudaGetDeviceProperties(&prop, device));
     s->sm_count = prop.multiProcessorCount;
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream2, cudaStreamNonBlocking));
-    // [0, MAX) band flags of host slot 0, [MAX] [MAX+1] the mirrors, [MAX+2, 2 MAX+2) band flags of host slot 1
-    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (2 * RTGS_MAX_BANDS + 2) * sizeof(int), cudaHostAllocMapped));
+    // [0, MAX) band flags of host slot 0, [MAX] [MAX+1] the mirrors of frame scratch 0, [MAX+2, 2 MAX+2) band flags
+    // of host slot 1, [2 MAX+2] [2 MAX+3] the mirrors of frame scratch 1
+    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (2 * RTGS_MAX_BANDS + 4) * sizeof(int), cudaHostAllocMapped));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&s->band_flags_dev, s->band_flags, 0));
     for (int k = 0; k < 2; ++k) {
         const int off = k == 0 ? 0 : RTGS_MAX_BANDS + 2;
@@ -103,8 +110,17 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
         CUDA_TRY(cudaEventCreateWithFlags(&s->host_slot[k].copied, cudaEventDisableTiming));
     }
     TRY(dev_alloc(&s->band_done, RTGS_MAX_BANDS));
-    s->band_flags[RTGS_MAX_BANDS] = 0;       // pool demand of the last finished frame (render.cu: ensure_lists)
-    s->band_flags[RTGS_MAX_BANDS + 1] = 0;   // some finished frame had fallback tiles (render.cu: launch_render_k)
+    for (int k = 0; k < 2; ++k) {
+        rtgs_scene::FrameScratch& fs = s->scratch[k];
+        const int off = k == 0 ? RTGS_MAX_BANDS : 2 * RTGS_MAX_BANDS + 2;
+        fs.mirror = s->band_flags + off;
+        fs.mirror_dev = s->band_flags_dev + off;
+        fs.mirror[0] = 0;   // pool demand of the last finished frame (render.cu: ensure_lists)
+        fs.mirror[1] = 0;   // some finished frame had fallback tiles (render.cu: launch_render_k)
+        TRY(dev_alloc(&fs.counters, 8));
+        CUDA_TRY(cudaMemset(fs.counters, 0, 8 * sizeof(unsigned int)));   // k_frame leaves them zeroed frame after frame
+        CUDA_TRY(cudaEventCreateWithFlags(&fs.free_event, cudaEventDisableTiming));
+    }
     TRY(dev_alloc(&s->pos, n * 3));
     TRY(dev_alloc(&s->rot, n * 4));
     TRY(dev_alloc(&s->scale, n * 3));
@@ -122,7 +138,6 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->leafbox, n * 2));
     TRY(dev_alloc(&s->nodes4, s->num_nodes * 8));
-    TRY(dev_alloc(&s->counters, 8));
     TRY(dev_alloc(&s->stats_dev, 12));
     return RTGS_OK;
 }
@@ -151,6 +166,12 @@ int ensure_pinned(rtgs_scene* s, size_t pixels) {
         s->pinned_pixels = pixels;
     }
     return RTGS_OK;
+}
+
+bool all_finite(const float* v, int64_t count) {
+    bool fin = true;
+    for (int64_t i = 0; i < count; ++i) fin = fin && std::isfinite(v[i]);
+    return fin;
 }
 
 int check_camera(const rtgs_camera* cam) {
@@ -184,14 +205,24 @@ int rtgs_scene_create(int device, int64_t n, const float* pos, const float* rot_
         rtgs_set_error("cudaSetDevice(%d) failed", device);
         return RTGS_ERR_CUDA;
     }
+    // Morton codes, the hierarchy and every box test assume finite geometry: a NaN / Inf centre, rotation or scale
+    // has no place in the tree (and the reference's own SAH split would not survive it either: scene.py:263-266)
+    if (!all_finite(pos, n * 3) || !all_finite(rot_xyzw, n * 4) || !all_finite(scale, n * 3)) {
+        rtgs_set_error("rtgs_scene_create: positions, rotations and scales must be finite (NaN or Inf found)");
+        return RTGS_ERR_INVALID;
+    }
     rtgs_scene* s = nullptr;
     int r = alloc_scene(device, n, sh != nullptr, &s);
     if (r == RTGS_OK) {
+        // uploads are queued on the stream the build runs on (a pageable cudaMemcpy on the legacy stream is not
+        // ordered against a non-blocking stream); the host arrays are borrowed only until this call returns
+        cudaStream_t st = s->own_stream;
         auto up = [&](float* d, const float* h, size_t cnt) {
-            return cudaMemcpy(d, h, cnt * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess;
+            return cudaMemcpyAsync(d, h, cnt * sizeof(float), cudaMemcpyHostToDevice, st) == cudaSuccess;
         };
         bool ok = up(s->pos, pos, n * 3) && up(s->rot, rot_xyzw, n * 4) && up(s->scale, scale, n * 3) &&
                   up(s->color, color, n * 3) && up(s->opacity, opacity, n) && (!sh || up(s->sh, sh, n * 45));
+        ok = ok && cudaStreamSynchronize(st) == cudaSuccess;
         if (!ok) {
             rtgs_set_error("host->device upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             r = RTGS_ERR_CUDA;
@@ -215,6 +246,18 @@ int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices
     bool has_sh = false;
     for (int k = 6; k < 51; ++k) has_sh = has_sh || col[k] >= 0;
     for (int k = 0; k < 59; ++k) RTGS_CHECK_ARG(col[k] < stride_floats);
+    // finite geometry only (see rtgs_scene_create): x,y,z (0-2), log-scales (52-54), rot_0..3 (55-58)
+    for (int64_t i = 0; i < n; ++i) {
+        const float* row = vertices + i * stride_floats;
+        bool fin = true;
+        for (int k : {0, 1, 2, 52, 53, 54, 55, 56, 57, 58})
+            if (col[k] >= 0) fin = fin && std::isfinite(row[col[k]]);
+        if (!fin) {
+            rtgs_set_error("rtgs_scene_create_from_ply_rows: vertex %lld has a NaN or Inf position, scale or rotation",
+                           (long long)i);
+            return RTGS_ERR_INVALID;
+        }
+    }
     DeviceGuard g(device);
     if (!g.ok) {
         rtgs_set_error("cudaSetDevice(%d) failed", device);
@@ -227,8 +270,11 @@ int rtgs_scene_create_from_ply_rows(int device, int64_t n, const float* vertices
     if (r == RTGS_OK) r = dev_alloc(&rows, (size_t)n * stride_floats);
     if (r == RTGS_OK) r = dev_alloc(&dcol, 59);
     if (r == RTGS_OK) {
-        cudaError_t e = cudaMemcpy(rows, vertices, (size_t)n * stride_floats * sizeof(float), cudaMemcpyHostToDevice);
-        if (e == cudaSuccess) e = cudaMemcpy(dcol, col, 59 * sizeof(int32_t), cudaMemcpyHostToDevice);
+        cudaStream_t st = s->own_stream;   // same stream as the activation kernel and the build
+        cudaError_t e = cudaMemcpyAsync(rows, vertices, (size_t)n * stride_floats * sizeof(float),
+                                        cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(dcol, col, 59 * sizeof(int32_t), cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
             rtgs_set_error("host->device upload failed: %s", cudaGetErrorString(e));
             r = RTGS_ERR_CUDA;
@@ -385,7 +431,7 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
     RTGS_CHECK_ARG(s != nullptr);
     switch (option) {
         case RTGS_OPT_RENDER_MODE:
-            RTGS_CHECK_ARG(value == 0 || value == 1);
+            RTGS_CHECK_ARG(value >= 0 && value <= 2);
             s->opt_render_mode = (int)value;
             return RTGS_OK;
         case RTGS_OPT_LIST_POOL_CHUNKS: {
@@ -393,10 +439,12 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             DeviceGuard g(s->device);
             s->opt_pool_chunks = value;
             // dropped here, re-created with the new capacity by the next render
-            cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
-            s->tile_desc = nullptr; s->list_pool = nullptr; s->fallback_tiles = nullptr;
-            s->list_tiles = 0;
-            s->pool_chunks = 0;
+            for (auto& fs : s->scratch) {
+                cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.ready);
+                fs.tile_desc = nullptr; fs.list_pool = nullptr; fs.fallback_tiles = nullptr; fs.ready = nullptr;
+                fs.list_tiles = 0;
+                fs.pool_chunks = 0;
+            }
             return RTGS_OK;
         }
         case RTGS_OPT_MORTON_BITS:
@@ -425,10 +473,83 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             }
             return RTGS_OK;
         }
+        case RTGS_OPT_TREE_DEPTH:
+            rtgs_set_error("RTGS_OPT_TREE_DEPTH is read-only");
+            return RTGS_ERR_INVALID;
         default:
             rtgs_set_error("unknown option %d", (int)option);
             return RTGS_ERR_INVALID;
     }
+}
+
+int rtgs_scene_get_option(const rtgs_scene* s, int32_t option, int64_t* value) {
+    RTGS_CHECK_ARG(s != nullptr && value != nullptr);
+    switch (option) {
+        case RTGS_OPT_RENDER_MODE: {
+            // the mode a depth <= 16 frame renders in: the per-scene option, else RTGS_RENDER_MODE, else 2
+            int m = s->opt_render_mode;
+            if (m < 0) {
+                const char* e = getenv("RTGS_RENDER_MODE");
+                m = e ? atoi(e) : 2;
+                if (m < 0 || m > 2) m = 2;
+            }
+            *value = m;
+            return RTGS_OK;
+        }
+        case RTGS_OPT_LIST_POOL_CHUNKS: *value = s->scratch[0].pool_chunks; return RTGS_OK;
+        case RTGS_OPT_KERNEL_TIMING: *value = (int64_t)s->timing_ran.size(); return RTGS_OK;
+        case RTGS_OPT_STRIPE: *value = ((int64_t)s->opt_stripe_mod << 32) | (int64_t)s->opt_stripe_rem; return RTGS_OK;
+        case RTGS_OPT_MORTON_BITS: *value = s->built ? s->morton_bits_used : s->opt_morton_bits; return RTGS_OK;
+        case RTGS_OPT_TREE_DEPTH:
+            if (!s->built) {
+                rtgs_set_error("rtgs_scene_get_option(RTGS_OPT_TREE_DEPTH): call rtgs_scene_build_bvh first");
+                return RTGS_ERR_STATE;
+            }
+            *value = s->max_depth;
+            return RTGS_OK;
+        default:
+            rtgs_set_error("unknown option %d", (int)option);
+            return RTGS_ERR_INVALID;
+    }
+}
+
+int rtgs_scene_set_frame_sync(rtgs_scene* s, uint32_t* arrive, const uint32_t* grant, uint32_t grant_value) {
+    RTGS_CHECK_ARG(s != nullptr);
+    s->sync_arrive = arrive;
+    s->sync_grant = grant;
+    s->sync_grant_value = grant_value;
+    return RTGS_OK;
+}
+
+int rtgs_stream_wait_counter(int device, const uint32_t* counter, uint32_t value, void* stream) {
+    RTGS_CHECK_ARG(counter != nullptr);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    return rtgs_launch_wait_counter(counter, value, (cudaStream_t)stream);
+}
+
+int rtgs_stream_set_counter(int device, uint32_t* counter, uint32_t value, void* stream) {
+    RTGS_CHECK_ARG(counter != nullptr);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    return rtgs_launch_set_counter(counter, value, (cudaStream_t)stream);
+}
+
+int rtgs_host_register(void* p, size_t bytes) {
+    RTGS_CHECK_ARG(p != nullptr && bytes > 0);
+    CUDA_TRY(cudaHostRegister(p, bytes, cudaHostRegisterPortable | cudaHostRegisterMapped));
+    return RTGS_OK;
+}
+
+int rtgs_host_unregister(void* p) {
+    if (p) CUDA_TRY(cudaHostUnregister(p));
+    return RTGS_OK;
 }
 
 int rtgs_scene_read_kernel_times(rtgs_scene* s, int32_t frames, float* ms) {
@@ -598,9 +719,13 @@ static int submit_whole(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32
     rtgs_scene::HostSlot& hs = s->host_slot[s->host_head];
     const size_t px = (size_t)w * h;
     TRY(ensure_stage(hs, px));
-    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, hs.stage_rgb, host_T ? hs.stage_T : nullptr,
-                           s->own_stream, false));
-    CUDA_TRY(cudaEventRecord(hs.done, s->own_stream));
+    // the two frames in flight render on alternating streams (each with its own frame scratch, render.cu), so the
+    // head of frame f+1 overlaps the tail of frame f on the device
+    static const bool one_stream = getenv("RTGS_SUBMIT_ONE_STREAM") != nullptr;   // experiment: serialised renders
+    cudaStream_t rs = (s->host_head == 0 || one_stream) ? s->own_stream : s->own_stream2;
+    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, hs.stage_rgb, host_T ? hs.stage_T : nullptr, rs,
+                           false));
+    CUDA_TRY(cudaEventRecord(hs.done, rs));
     CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, hs.done, 0));
     CUDA_TRY(cudaMemcpyAsync(host_rgb, hs.stage_rgb, px * 3 * sizeof(float), cudaMemcpyDeviceToHost, s->copy_stream));
     if (host_T)

@@ -10,6 +10,9 @@
 
 #define RTGS_SM_COUNT_FALLBACK 148
 #define RTGS_MAX_BANDS 32
+// Deepest leaf the traversal stacks are sized for: 62 levels for unique (30-bit code, index) keys, 63 + 30 for
+// 63-bit codes with repeats (lbvh.cu: k_karras<DUP>, k_max_depth); the build refuses anything deeper.
+#define RTGS_MAX_TREE_DEPTH 96
 
 // ---- error plumbing (never abort across the ABI) ---------------------------------------------
 void rtgs_set_error(const char* fmt, ...);
@@ -86,15 +89,36 @@ struct rtgs_scene {
     float4* nodes4 = nullptr;    // num_nodes*8: two-level nodes (records of both children), k_tile_lists
     int64_t num_nodes = 0;  // max(n-1, 1)
     float build_ms = 0.0f;  // device time of the last LBVH build (Morton codes ... packed nodes)
+    int max_depth = 0;      // depth of the deepest leaf of the current tree (root = 0)
 
-    // render scratch
-    unsigned int* counters = nullptr;         // 8: work counters, pool cursor, fallback count
+    // render scratch.  A frame's work counters and candidate lists live in a FrameScratch; a scene has two, so
+    // that frames launched on two alternating streams overlap on the device (frame f+1's traversal fills the SMs
+    // that frame f's shading tail leaves idle) instead of being serialised by the library.
+    struct FrameScratch {
+        unsigned int* counters = nullptr;     // CTR_COUNT: work counters, pool cursor, fallback count
+        void* tile_desc = nullptr;            // candidate lists (render_common.cuh), sized on first use
+        int* list_pool = nullptr;
+        int* fallback_tiles = nullptr;
+        unsigned int* ready = nullptr;        // per traversal group: sequence number of the frame whose lists are complete
+        unsigned int frame_seq = 0;           // frames launched through k_frame so far (ready[] is compared with it)
+        bool counters_dirty = false;          // the last frame did not zero the work counters itself
+        int list_tiles = 0;
+        int pool_chunks = 0;
+        int* mirror = nullptr;                // mapped pinned host memory: [0] pool demand of the last finished frame,
+        int* mirror_dev = nullptr;            //                            [1] some finished frame had fallback tiles
+        cudaEvent_t free_event = nullptr;     // behind the last frame that used this scratch
+        cudaStream_t stream = nullptr;        // the stream that frame was launched on
+        bool used = false;
+        uint64_t last_use = 0;
+    };
+    FrameScratch scratch[2];
+    uint64_t scratch_clock = 0;
+    bool exclusive_inflight = false;         // the last frame launched used the once-only counters (statistics, bands)
     unsigned long long* stats_dev = nullptr;  // 12 counters
-    void* tile_desc = nullptr;                // candidate lists (render_common.cuh), sized on first render
-    int* list_pool = nullptr;
-    int* fallback_tiles = nullptr;
-    int list_tiles = 0;
-    int pool_chunks = 0;
+    // multi-GPU hand-over of the NEXT frame (rtgs_scene_set_frame_sync; cleared when that frame is launched)
+    unsigned int* sync_arrive = nullptr;
+    const unsigned int* sync_grant = nullptr;
+    unsigned int sync_grant_value = 0;
     int64_t opt_pool_chunks = -1;             // RTGS_OPT_LIST_POOL_CHUNKS (-1 = default sizing)
     int opt_stripe_mod = 1, opt_stripe_rem = 0;   // RTGS_OPT_STRIPE
     int opt_render_mode = -1;                 // RTGS_OPT_RENDER_MODE (-1 = RTGS_RENDER_MODE env or 0)
@@ -114,14 +138,12 @@ struct rtgs_scene {
     };
     HostSlot host_slot[2];
     int host_head = 0, host_inflight = 0;     // next slot to submit into; frames submitted and not collected
-    cudaEvent_t scratch_free = nullptr;       // behind the last frame's kernels (render.cu: rtgs_launch_render)
-    cudaStream_t scratch_stream = nullptr;    // the stream that frame was launched on
-    bool scratch_used = false;
     int* band_flags_cur_dev = nullptr;        // flags of the frame being launched (set around rtgs_launch_render)
     float* pinned_rgb = nullptr;
     float* pinned_T = nullptr;
     size_t pinned_pixels = 0;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t own_stream2 = nullptr;       // pipelined delivery: the two frames in flight render on alternating streams
     cudaStream_t copy_stream = nullptr;       // framebuffer DMA of rtgs_render_host, overlapping the render
     cudaStream_t copy_stream2 = nullptr;      // second DMA queue (bands alternate, hiding the per-copy set-up)
     unsigned int* band_done = nullptr;        // device: finished tile ids per band
@@ -145,6 +167,8 @@ int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, in
 int rtgs_launch_generate_rays(const rtgs_camera* cam, float* rays, cudaStream_t stream);
 int rtgs_launch_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays, int32_t* idx,
                               float* t12, cudaStream_t stream);
+int rtgs_launch_wait_counter(const unsigned int* counter, unsigned int value, cudaStream_t stream);
+int rtgs_launch_set_counter(unsigned int* counter, unsigned int value, cudaStream_t stream);
 int rtgs_launch_activate_ply(int64_t n, const float* rows_dev, int stride, const int32_t* col,
                              float scale, int sh_layout, float* pos, float* rot, float* sca,
                              float* color, float* opacity, float* sh, cudaStream_t stream);

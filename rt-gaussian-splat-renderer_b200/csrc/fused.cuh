@@ -1,0 +1,433 @@
+// fused.cuh — k_render: the whole per-ray render path fused per tile (sm_100a).
+//
+//   camera ray generation        camera.py:31-71              (registers; rays never stored)
+//   BVH traversal                scene.py:406-450             (warp-coherent frustum traversal)
+//   ray-Gaussian intersection    gaussian.py:203-230          (local-frame quadratic)
+//   response + SH colour         gaussian.py:140-201
+//   front-to-back compositing    ray_tracer.py:79-104         (k-buffer of the `depth` nearest entries)
+//
+// Execution model.  A warp owns one 4x8-pixel tile at a time (lane = pixel) and pulls tiles from
+// a global atomic counter (persistent threads).  All 32 primary rays share the camera origin, so
+// the tile is a thin pyramid bounded by 4 planes through the origin.  The warp traverses the LBVH
+// ONCE for the tile: up to 32 nodes are popped from a shared-memory stack per step, each lane
+// tests the two child boxes of its node against the 4 planes, and survivors are compacted back with
+// ballot/popc (internal children -> stack, the nearer one on top; leaves -> candidate queue).  Once rays hold
+// K hits the traversal prunes by distance as well - the K-nearest form of the reference's far pruning
+// (scene.py:417-419): a box beyond the farthest kept hit of every full ray that also misses the pyramid of the
+// rays still lacking hits is dropped.  That makes this kernel the right one for tiles whose frustum holds
+// thousands of Gaussians (lists_group sends it the groups whose list overflows).  Candidates are staged 32 at
+// a time (one lane each, float64: origin shifted to the closest point of the tile's centre ray)
+// and then every lane tests its own ray against every staged candidate with broadcast
+// shared-memory reads: first a conservative 5-FMA quadratic (q - 3 as a polynomial of the pixel
+// offset), then - in warp-wide rounds, one pending candidate per lane - the precise test, the entry
+// distance and alpha.  Hits are appended to a per-lane K-entry buffer in shared memory (replace-max
+// when full); after the traversal each lane ranks its entries and composites front to back.
+//
+// It renders depth > 16 (K = 32), RTGS_OPT_RENDER_MODE = 1, and - launched behind the list kernels, by the host
+// or by k_frame's last CTA as a device-side tail launch - the tiles on the fallback list.
+//
+// Numerics.  The reference's f32 formulation (B^2 - 4AC with a cofactor inverse) is ill-conditioned
+// (SURVEY.md §7 hard part 1), and parity is defined against a float64 evaluation of the
+// reference's maths.  The fast path is float32 but expressed relative to (Gaussian centre, tile
+// centre ray), which keeps all magnitudes O(tile size / sigma); a hit/miss decision within a
+// small band of the sqrt(3)-sigma surface, an entry distance within a band of 0, and adjacent
+// k-buffer entries closer than a few ulp are re-evaluated in float64 from the raw parameters.
+#pragma once
+#include "render_common.cuh"
+
+namespace rtgs_dev {
+namespace fused {
+
+#ifndef RTGS_STACK_CAP
+#define RTGS_STACK_CAP 512
+#endif
+constexpr int STACK_CAP = RTGS_STACK_CAP;
+// Above STACK_SINGLE the traversal pops one node at a time (depth first): a batch step grows the stack by <= 32
+// (two children per popped node), a single pop by <= 1 per level descended, i.e. by <= RTGS_MAX_TREE_DEPTH in all.
+constexpr int STACK_SINGLE = STACK_CAP - 32 - RTGS_MAX_TREE_DEPTH;
+static_assert(STACK_SINGLE >= 64, "k_render: stack too small for batched traversal");
+constexpr int CQ_CAP = 96;
+constexpr int BATCH = 32;
+constexpr int REC_Q = 5;                 // quads per staged record (80-byte stride: conflict-free gathers)
+
+struct __align__(16) TraversalScratch {
+    float4 rec[BATCH][REC_Q];   // precise records (render_common.cuh: stage_candidate)
+    float4 polyA[BATCH];        // coarse quadratics {c0 c1 c2 c3}
+    float2 polyB[BATCH];        //                   {c4 c5}
+    int stack[STACK_CAP];
+    int cq[CQ_CAP];
+    Frustum open;               // pyramid of the rays that still lack hits (distance pruning, below)
+};
+
+template <int K>
+struct __align__(16) WarpShared {
+    union {
+        TraversalScratch t;        // traversal phase
+        struct {                   // compositing phase: hits in ascending entry distance
+            int so_i[K][32];
+            float so_a[K][32];
+        } c;
+    };
+    float kb_t[K][32];     // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
+    int kb_i[K][32];
+    float kb_a[K][32];
+};
+
+// STATS = true compiles the per-render counters in (rtgs_render with a stats pointer); the timed path
+// uses STATS = false so that the 64-bit counters do not occupy registers.
+template <int K, bool STATS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_render(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpShared<K>& ws = reinterpret_cast<WarpShared<K>*>(smem_raw)[threadIdx.x >> 5];
+    TraversalScratch& tr = ws.t;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const CamD& cam = P.cam;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+    // work items: every tile id, or (fallback mode) the tiles k_tile_lists could not store a list for
+    const int nwork = P.use_fallback_list ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : P.ntiles;
+
+    if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0) {
+        // pool demand of this frame (for the host's sizing) and whether any frame so far needed the fallback
+        *reinterpret_cast<volatile int*>(P.mirror) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
+        if (P.counters[CTR_FALLBACK] != 0) *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
+    }
+
+    PeerGrant grant;
+    grant_begin(P, grant);
+    unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
+                       st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
+#define ST(expr) do { if (STATS) { expr; } } while (0)
+
+#pragma unroll 1
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) {
+            tile = (int)atomicAdd(P.counters + CTR_WORK3, 1u);
+            if (P.use_fallback_list && tile < nwork) tile = P.fallback_tiles[tile];
+            else if (P.use_fallback_list) tile = P.ntiles;
+            else tile = work_to_id(P, tile, P.macro_cols * TILES_PER_MACRO, P.ntiles);
+        }
+        tile = __shfl_sync(FULL, tile, 0);
+        if (tile >= P.ntiles) break;
+        int i0, j0;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
+            tile_done(P, tile, lane);
+            continue;
+        }
+        const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
+        const bool active = pi < xe && pj < ye;
+
+        TileRays ry;
+        make_tile_rays(cam, i0, j0, pi, pj, active, ry);
+        Frustum fr;
+        make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
+
+        // ---- per-lane hit buffer (shared memory, unsorted; replace-max once K entries are held) --
+        int cnt = 0;
+        float kmax_t = INFINITY;
+        int kmax_slot = 0;
+
+        // one pending candidate per lane; the precise test and the hit-only work (entry distance,
+        // alpha, float64 refinement, buffer append) run in warp-wide rounds
+        bool pend = false;
+        int pend_c = 0;
+
+        // Distance pruning - the K-nearest form of the reference's "skip a node whose entry distance exceeds the best
+        // hit so far" (scene.py:417-419).  A ray that holds K hits needs nothing farther than its farthest one, so a
+        // box is dropped when it lies beyond `cut` = the largest such distance among the rays that are full (with a
+        // margin far above float32 rounding, so that near-ties at the K-th place still see both contenders) AND
+        // misses the pyramid of the rays that are not full yet (`tr.open`, the bounding pixel rectangle of those
+        // rays; initially the whole tile).  Children are pushed far one first.  This is what keeps a tile that looks
+        // along a surface - thousands of splats in its frustum, the first few dozen of them opaque - affordable.
+        float cut2 = -1.0f;            // (cut * (1 + 1e-4))^2, < 0: no ray is full yet
+        unsigned open_mask = __ballot_sync(FULL, active);
+        bool open_all = true;          // tr.open == fr
+        const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
+        auto box_dist2 = [&](float cx, float cy, float cz, float hx, float hy, float hz) {
+            const float dx = fmaxf(fabsf(ox - cx) - hx, 0.0f), dy = fmaxf(fabsf(oy - cy) - hy, 0.0f),
+                        dz = fmaxf(fabsf(oz - cz) - hz, 0.0f);
+            return dx * dx + dy * dy + dz * dz;
+        };
+
+        int top = 1, ncq = 0;
+        if (lane == 0) tr.stack[0] = 0;
+        __syncwarp();
+
+        // ================================ traversal ==========================================
+#pragma unroll 1
+        while (top > 0 || ncq > 0) {
+            if (top > 0) {
+                const int take = top > STACK_SINGLE ? 1 : min(32, top);
+                int node = -1;
+                if (lane < take) node = tr.stack[top - 1 - lane];
+                top -= take;
+                __syncwarp();
+                bool h0 = false, h1 = false;
+                int c0 = 0, c1 = 0;
+                if (node >= 0) {
+                    float4 a, b, c, d;
+                    ldg256(P.nodes + (int64_t)node * 4 + 0, a, b);
+                    ldg256(P.nodes + (int64_t)node * 4 + 2, c, d);
+                    c0 = __float_as_int(d.x);
+                    c1 = __float_as_int(d.y);
+                    h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
+                    h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
+                    const float d0 = box_dist2(a.x, a.y, a.z, a.w, b.x, b.y);
+                    const float d1 = box_dist2(b.z, b.w, c.x, c.y, c.z, c.w);
+                    if (cut2 >= 0.0f) {
+                        if (h0 && d0 > cut2)
+                            h0 = open_mask != 0 && (open_all || box_in_frustum(tr.open, a.x, a.y, a.z, a.w, b.x, b.y));
+                        if (h1 && d1 > cut2)
+                            h1 = open_mask != 0 && (open_all || box_in_frustum(tr.open, b.z, b.w, c.x, c.y, c.z, c.w));
+                    }
+                    if (d1 > d0) {   // child 1 is pushed last, i.e. popped first: make it the nearer one
+                        const int ci = c0; c0 = c1; c1 = ci;
+                        const bool hi = h0; h0 = h1; h1 = hi;
+                    }
+                }
+                ST(st_nodes += 2ull * (unsigned)take);
+                ST(st_steps += 1);
+                const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
+                const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
+                if (h0 && c0 >= 0) tr.stack[top + __popc(mI0 & lt_mask)] = c0;
+                const int topa = top + __popc(mI0);
+                if (h1 && c1 >= 0) tr.stack[topa + __popc(mI1 & lt_mask)] = c1;
+                top = topa + __popc(mI1);
+                if (h0 && c0 < 0) tr.cq[ncq + __popc(mL0 & lt_mask)] = ~c0;
+                const int ncqa = ncq + __popc(mL0);
+                if (h1 && c1 < 0) tr.cq[ncqa + __popc(mL1 & lt_mask)] = ~c1;
+                ncq = ncqa + __popc(mL1);
+                __syncwarp();
+            }
+            // -------- candidate batch: stage (one lane each, float64) then test (all lanes) --
+#pragma unroll 1
+            while (ncq >= BATCH || (top == 0 && ncq > 0)) {
+                const int m = min(BATCH, ncq);
+                ncq -= m;
+                if (lane < m) {
+                    float4 rec[5];
+                    float poly[6];
+                    stage_candidate(P, ry, tr.cq[ncq + lane], rec, poly);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) tr.rec[lane][k] = rec[k];
+                    tr.polyA[lane] = make_float4(poly[0], poly[1], poly[2], poly[3]);
+                    tr.polyB[lane] = make_float2(poly[4], poly[5]);
+                }
+                __syncwarp();
+                ST(st_cands += (unsigned)m);
+                ST(st_pairs += 32ull * (unsigned)m);
+#pragma unroll 1
+                for (int c = 0; c <= m; ++c) {
+                    bool cand = false;
+                    if (c < m) {
+                        const float4 pA = tr.polyA[c];
+                        const float2 pB = tr.polyB[c];
+                        const float ta = fmaf(ry.pa, pA.w, fmaf(ry.pb, pB.x, pA.y));   // c1 + a c3 + b c4
+                        const float tb = fmaf(ry.pb, pB.y, pA.z);                      // c2 + b c5
+                        const float S = fmaf(ry.pa, ta, fmaf(ry.pb, tb, pA.x));
+                        cand = active && (S < 0.0f);
+                    }
+                    // flush when a lane gets a second candidate, and once at the end of the batch
+                    // (the staged records are about to be overwritten)
+                    if (__any_sync(FULL, pend && (cand || c == m))) {
+                        if (pend) {
+                            const PreciseHit h = precise_test(P, tr.rec[pend_c], ry.dlx, ry.dly, ry.dlz, pi, pj);
+                            ST(st_f64 += h.refined);
+                            if (h.hit) {
+                                auto find_farthest = [&]() {
+                                    float mt = -INFINITY;
+                                    int ms = 0;
+#pragma unroll 4
+                                    for (int k = 0; k < K; ++k) {
+                                        const float t = ws.kb_t[k][lane];
+                                        if (t > mt) { mt = t; ms = k; }
+                                    }
+                                    kmax_t = mt;
+                                    kmax_slot = ms;
+                                };
+                                if (cnt < K) {
+                                    const int slot = cnt++;
+                                    ws.kb_t[slot][lane] = h.t1;
+                                    ws.kb_i[slot][lane] = h.s;
+                                    ws.kb_a[slot][lane] = h.alpha;
+                                    if (cnt == K) find_farthest();
+                                } else {
+                                    // full: the candidate replaces the farthest entry if it is nearer.  Whenever
+                                    // two contenders for the last place are within float32 rounding of each other
+                                    // - the candidate and the farthest entry, or the evicted entry and the new
+                                    // farthest one - their float64 entry distances decide (exact_less; rare).
+                                    float ct = h.t1, ca = h.alpha;
+                                    int cs = h.s;
+#pragma unroll 1
+                                    for (;;) {
+                                        bool nearer = ct < kmax_t;
+                                        if (fabsf(ct - kmax_t) <= 2e-6f * kmax_t) {
+                                            nearer = exact_less(P.raw, cam, cs, ws.kb_i[kmax_slot][lane], pi, pj);
+                                            ST(st_f64 += 2);
+                                        }
+                                        if (!nearer) break;
+                                        const float et = kmax_t, ea = ws.kb_a[kmax_slot][lane];
+                                        const int es = ws.kb_i[kmax_slot][lane];
+                                        ws.kb_t[kmax_slot][lane] = ct;
+                                        ws.kb_i[kmax_slot][lane] = cs;
+                                        ws.kb_a[kmax_slot][lane] = ca;
+                                        find_farthest();
+                                        if (!(et - kmax_t <= 2e-6f * et)) break;
+                                        ct = et; cs = es; ca = ea;   // the evicted entry ties with the new farthest
+                                    }
+                                }
+                            }
+                            pend = false;
+                        }
+                        ST(st_ins += 1);
+                    }
+                    if (cand) {
+                        pend = true;
+                        pend_c = c;
+                    }
+                }
+                __syncwarp();
+                // ---- pruning state after the batch: who is full, how far their farthest hit is ----
+                {
+                    const bool full = active && cnt == K;
+                    float cm = full ? kmax_t : -1.0f;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
+                    if (cm >= 0.0f) {
+                        cm *= 1.0001f;
+                        cut2 = cm * cm;
+                    }
+                    const unsigned om = __ballot_sync(FULL, active && cnt < K);
+                    if (om != open_mask) {
+                        open_mask = om;
+                        if (om != 0) {
+                            int il = cnt < K && active ? pi : 0x7fffffff, ih = cnt < K && active ? pi : -1;
+                            int jl = cnt < K && active ? pj : 0x7fffffff, jh = cnt < K && active ? pj : -1;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) {
+                                il = min(il, __shfl_xor_sync(FULL, il, o));
+                                ih = max(ih, __shfl_xor_sync(FULL, ih, o));
+                                jl = min(jl, __shfl_xor_sync(FULL, jl, o));
+                                jh = max(jh, __shfl_xor_sync(FULL, jh, o));
+                            }
+                            Frustum fo;
+                            make_frustum(cam, il, ih + 1, jl, jh + 1, fo);
+                            if (lane == 0) tr.open = fo;
+                            open_all = false;
+                        }
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+
+        // ---- order the hits by ascending entry distance: rank counting into the compositing list --
+        // rank_i = #{j : t_j < t_i}; pairs within float32 rounding of each other are ordered by their
+        // float64 entry distances (exact_less).  The traversal scratch is dead from here on.
+        int maxcnt = cnt;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
+        __syncwarp();
+        if (maxcnt > 0) {
+            float tk[K];
+#pragma unroll
+            for (int k = 0; k < K; ++k) tk[k] = k < cnt ? ws.kb_t[k][lane] : INFINITY;
+#pragma unroll 1
+            for (int i = 0; i < maxcnt; ++i) {
+                if (i < cnt) {
+                    const float ti_ = ws.kb_t[i][lane];
+                    const float band = 2e-6f * fabsf(ti_);
+                    int rank = 0, nnear = 0;
+#pragma unroll
+                    for (int j = 0; j < K; ++j) {
+                        rank += tk[j] < ti_;
+                        nnear += fabsf(tk[j] - ti_) <= band;
+                    }
+                    const int id = ws.kb_i[i][lane];
+                    if (nnear > 1) {   // rare: resolve near ties exactly
+                        rank = 0;
+#pragma unroll 1
+                        for (int j = 0; j < cnt; ++j) {
+                            if (j == i) continue;
+                            const float tj_ = ws.kb_t[j][lane];
+                            if (fabsf(tj_ - ti_) <= band) {
+                                rank += exact_less(P.raw, cam, ws.kb_i[j][lane], id, pi, pj);
+                                ST(st_f64 += 2);
+                            } else {
+                                rank += tj_ < ti_;
+                            }
+                        }
+                    }
+                    ws.c.so_i[rank][lane] = id;
+                    ws.c.so_a[rank][lane] = ws.kb_a[i][lane];
+                }
+            }
+        }
+        __syncwarp();
+
+        // ================================ compositing ========================================
+        // accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98), rgb = color +
+        // eval_sh(normalize(dir)) (gaussian.py:199-200).
+        float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+        int nl = 0;
+        {
+            float Y[15];
+            sh_basis(ry.dnx, ry.dny, ry.dnz, Y);
+            const int nmine = min(cnt, P.depth);
+            const int nloop = min(maxcnt, P.depth);
+#pragma unroll 1
+            for (int k = 0; k < nloop; ++k) {
+                if (k < nmine && T >= P.t_cut) {
+                    const int s = ws.c.so_i[k][lane];
+                    const float alpha = ws.c.so_a[k][lane];
+                    float r, g, b;
+                    eval_colour(P, s, Y, r, g, b);
+                    const float wgt = T * alpha;
+                    cr = fmaf(wgt, r, cr);
+                    cg = fmaf(wgt, g, cg);
+                    cb = fmaf(wgt, b, cb);
+                    T *= 1.0f - alpha;
+                    ++nl;
+                }
+            }
+        }
+        grant_wait(P, grant);
+        store_tile(P, reinterpret_cast<float*>(&ws.kb_t[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
+        tile_done(P, tile, lane);
+        if (active) {
+            ST(st_rays += 1);
+            ST(st_hit += nl > 0);
+            ST(st_layers += (unsigned)nl);
+        }
+        ST(if (lane == 0) st_tiles += 1);
+    }
+
+    if (STATS && P.stats) {
+        unsigned long long v[ST_COUNT] = {0};
+        v[ST_RAYS] = st_rays; v[ST_RAYS_HIT] = st_hit; v[ST_LAYERS] = st_layers; v[ST_F64] = st_f64;
+        // warp-uniform counters are taken from lane 0 only
+        if (lane == 0) {
+            v[ST_NODES] = st_nodes;
+            v[ST_CANDS] = st_cands;
+            v[ST_PAIRS] = st_pairs;
+            v[ST_TILES] = st_tiles;
+            v[ST_STEPS] = st_steps;
+            v[ST_INSERTS] = st_ins;
+            v[ST_FALLBACK] = P.use_fallback_list ? st_tiles : 0;
+        }
+#pragma unroll
+        for (int k = 0; k < ST_COUNT; ++k) {
+            unsigned long long x = v[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+            if (lane == 0 && x) atomicAdd(P.stats + k, x);
+        }
+    }
+    if (P.final_kernel) cta_finish(P, CTR_DONE2);
+}
+#undef ST
+
+
+}  // namespace fused
+}  // namespace rtgs_dev

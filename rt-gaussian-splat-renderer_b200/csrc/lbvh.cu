@@ -397,6 +397,25 @@ __global__ void k_refit(int64_t n, const int32_t* __restrict__ child, const int3
     }
 }
 
+// ------------------------------------------------------------------ tree depth
+// Depth of the deepest leaf (root = depth 0, so a leaf at depth d has d ancestors).  The traversal kernels size
+// their stacks from the bound RTGS_MAX_TREE_DEPTH: unique 62-bit keys give <= 62 levels, 63-bit codes with repeats
+// 63 + 30 (one level per differing bit of the sorted positions of equal codes); the build verifies it.
+__global__ void k_max_depth(int64_t n, const int32_t* __restrict__ parent, unsigned int* __restrict__ out) {
+    int64_t s = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    unsigned d = 0;
+    if (s < n) {
+        int32_t node = parent[(n - 1) + s];
+        while (node >= 0 && d < 4096u) {
+            ++d;
+            node = parent[node];
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) d = max(d, __shfl_xor_sync(0xffffffffu, d, o));
+    if ((threadIdx.x & 31) == 0 && d) atomicMax(out, d);
+}
+
 // ------------------------------------------------------------------ traversal nodes (64 B)
 // Child boxes are stored as (centre, half extent) with the half extent rounded UP so that
 // [c-h, c+h] contains the exact float32 [min, max] box.
@@ -553,6 +572,10 @@ int rtgs_lbvh_build(rtgs_scene* s) {
         CUDA_TRY(cudaMemsetAsync(visit.p, 0, (size_t)(n - 1) * sizeof(unsigned int), st));
         k_refit<<<nb, TB, 0, st>>>(n, s->child, s->parent, s->aabb, visit.p);
     }
+    DevBuf<unsigned int> depth;
+    CUDA_TRY(cudaMalloc(&depth.p, sizeof(unsigned int)));
+    CUDA_TRY(cudaMemsetAsync(depth.p, 0, sizeof(unsigned int), st));
+    if (n > 1) k_max_depth<<<nb, TB, 0, st>>>(n, s->parent, depth.p);
     k_pack_nodes<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->child, s->aabb, s->nodes);
     k_pack_nodes4<<<(int)((s->num_nodes + TB - 1) / TB), TB, 0, st>>>(n, s->nodes, s->leafbox, s->nodes4);
     CUDA_TRY(cudaGetLastError());
@@ -561,7 +584,14 @@ int rtgs_lbvh_build(rtgs_scene* s) {
     CUDA_TRY(cudaMemcpyAsync(hb, bnd.p, sizeof(hb), cudaMemcpyDeviceToHost, st));
     unsigned long long hd = 0;
     if (!wide) CUDA_TRY(cudaMemcpyAsync(&hd, distinct.p, sizeof(hd), cudaMemcpyDeviceToHost, st));
+    unsigned int hdepth = 0;
+    CUDA_TRY(cudaMemcpyAsync(&hdepth, depth.p, sizeof(hdepth), cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
+    s->max_depth = (int)hdepth;
+    if (s->max_depth > RTGS_MAX_TREE_DEPTH) {   // cannot happen for < 2^30 Gaussians (see k_max_depth); never traverse it
+        rtgs_set_error("LBVH depth %d exceeds the traversal stacks' bound %d", s->max_depth, RTGS_MAX_TREE_DEPTH);
+        return RTGS_ERR_STATE;
+    }
     s->distinct_codes = wide ? -1 : (int64_t)hd;
     CUDA_TRY(cudaEventElapsedTime(&s->build_ms, e0, e1));
     for (int a = 0; a < 6; ++a) s->bounds[a] = ordered_to_float(hb[a]);

@@ -1,415 +1,57 @@
-// render.cu — the fused per-ray render kernel (sm_100a) and its small companions.
+// render.cu — the render kernels of the per-ray path (sm_100a) and their launchers.
 //
-// One persistent kernel renders a whole sample of RayTracer.sample (ray_tracer.py:39-104):
-//   camera ray generation        camera.py:31-71              (registers; rays never stored)
-//   BVH traversal                scene.py:406-450             (warp-coherent frustum traversal)
-//   ray-Gaussian intersection    gaussian.py:203-230          (local-frame quadratic)
-//   response + SH colour         gaussian.py:140-201
-//   front-to-back compositing    ray_tracer.py:79-104         (register-resident k-buffer)
+// One frame = RayTracer.sample for a whole sample (ray_tracer.py:39-104): camera ray generation (camera.py:31-71),
+// BVH traversal (scene.py:406-450), ray-Gaussian intersection (gaussian.py:203-230), response + SH colour
+// (gaussian.py:140-201) and front-to-back compositing of the `depth` nearest entries (ray_tracer.py:79-104).
 //
-// Execution model.  A warp owns one 4x8-pixel tile at a time (lane = pixel) and pulls tiles from
-// a global atomic counter (persistent threads).  All 32 primary rays share the camera origin, so
-// the tile is a thin pyramid bounded by 4 planes through the origin.  The warp traverses the LBVH
-// ONCE for the tile: up to 32 nodes are popped from a shared-memory stack per step, each lane
-// tests the two child boxes of its node against the 4 planes, and survivors are compacted back with
-// ballot/popc (internal children -> stack, the nearer one on top; leaves -> candidate queue).  Once rays hold
-// K hits the traversal prunes by distance as well - the K-nearest form of the reference's far pruning
-// (scene.py:417-419): a box beyond the farthest kept hit of every full ray that also misses the pyramid of the
-// rays still lacking hits is dropped.  That makes this kernel the right one for tiles whose frustum holds
-// thousands of Gaussians (k_tile_lists sends it the groups whose list overflows).  Candidates are staged 32 at
-// a time (one lane each, float64: origin shifted to the closest point of the tile's centre ray)
-// and then every lane tests its own ray against every staged candidate with broadcast
-// shared-memory reads: first a conservative 5-FMA quadratic (q - 3 as a polynomial of the pixel
-// offset), then - in warp-wide rounds, one pending candidate per lane - the precise test, the entry
-// distance and alpha.  Hits are appended to a per-lane K-entry buffer in shared memory (replace-max
-// when full); after the traversal each lane loads its entries into registers, sorts them with a
-// bitonic network and composites front to back (register-resident k-buffer compositor).
-//
-// Numerics.  The reference's f32 formulation (B^2 - 4AC with a cofactor inverse) is ill-conditioned
-// (SURVEY.md §7 hard part 1), and parity is defined against a float64 evaluation of the
-// reference's maths.  The fast path is float32 but expressed relative to (Gaussian centre, tile
-// centre ray), which keeps all magnitudes O(tile size / sigma); a hit/miss decision within a
-// small band of the sqrt(3)-sigma surface, an entry distance within a band of 0, and adjacent
-// k-buffer entries closer than a few ulp are re-evaluated in float64 from the raw parameters.
+//   k_frame        (default, RTGS_OPT_RENDER_MODE 2) ONE launch per frame.  Persistent warps alternate between the
+//                  two halves of the path: one 8x16-pixel group of the traversal (tile_lists.cuh: lists_group,
+//                  which publishes the group's four candidate lists), then four 4x8-pixel tiles of shading
+//                  (shade.cuh: shade_tile, which acquires the publication of its tile's group).  Claims are
+//                  ordered - a tile is only ever claimed after its group - so a waiting warp always waits for a
+//                  warp that is running.  Traversal (issue- and latency-bound) and shading (L1-pipe-bound) overlap
+//                  on every SM, there is no kernel boundary inside the frame, and a frame that is spread over many
+//                  GPUs is no longer floored by a traversal kernel that runs before any shading can start.
+//                  The last CTA completes the frame: it mirrors the list-pool demand to the host, tail-launches the
+//                  fused kernel from the device if (and only if) some tile went to the fallback list, signals the
+//                  `arrive` counter of a multi-GPU gather and zeroes the work counters for the next frame.
+//   k_tile_lists + k_shade_tiles (+ k_render)   the same device code as separate launches (mode 0; A/B and ncu)
+//   k_render       fused.cuh (mode 1, depth > 16, fallback tiles)
+//   k_generate_rays, k_trace_closest, k_activate_ply   API companions (Camera.generate_ray_field, Scene.hit, PLY ingest)
 #include <stdlib.h>
 
-#include "render_common.cuh"
+#include "fused.cuh"
+#include "shade.cuh"
+#include "tile_lists.cuh"
+
+#ifndef RTGS_CDP
+#define RTGS_CDP 0   // 1: k_frame tail-launches k_render from the device (needs -rdc=true and cudadevrt)
+#endif
 
 using namespace rtgs_dev;
+using rtgs_dev::fused::k_render;
 
 namespace {
 
-#ifndef RTGS_STACK_CAP
-#define RTGS_STACK_CAP 512
-#endif
-constexpr int STACK_CAP = RTGS_STACK_CAP;
-constexpr int STACK_SINGLE = STACK_CAP - 100;   // above this pop one node at a time: growth/step <= 32, then DFS depth <= 62
-constexpr int CQ_CAP = 96;
-constexpr int BATCH = 32;
-constexpr int REC_Q = 5;                 // quads per staged record (80-byte stride: conflict-free gathers)
-
-struct __align__(16) TraversalScratch {
-    float4 rec[BATCH][REC_Q];   // precise records (render_common.cuh: stage_candidate)
-    float4 polyA[BATCH];        // coarse quadratics {c0 c1 c2 c3}
-    float2 polyB[BATCH];        //                   {c4 c5}
-    int stack[STACK_CAP];
-    int cq[CQ_CAP];
-    Frustum open;               // pyramid of the rays that still lack hits (distance pruning, below)
-};
-
-template <int K>
-struct __align__(16) WarpShared {
-    union {
-        TraversalScratch t;        // traversal phase
-        struct {                   // compositing phase: hits in ascending entry distance
-            int so_i[K][32];
-            float so_a[K][32];
-        } c;
-    };
-    float kb_t[K][32];     // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
-    int kb_i[K][32];
-    float kb_a[K][32];
-};
-
-// STATS = true compiles the per-render counters in (rtgs_render with a stats pointer); the timed path
-// uses STATS = false so that the 64-bit counters do not occupy registers.
-template <int K, bool STATS>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_render(const __grid_constant__ RenderParams P) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpShared<K>& ws = reinterpret_cast<WarpShared<K>*>(smem_raw)[threadIdx.x >> 5];
-    TraversalScratch& tr = ws.t;
-    const int lane = threadIdx.x & 31;
-    const unsigned lt_mask = (1u << lane) - 1u;
-    const CamD& cam = P.cam;
-    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
-    // work items: every tile id, or (fallback mode) the tiles k_tile_lists could not store a list for
-    const int nwork = P.use_fallback_list ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : P.ntiles;
-
-    if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0) {
-        // pool demand of this frame (for the host's sizing) and whether any frame so far needed the fallback
-        *reinterpret_cast<volatile int*>(P.mirror) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
-        if (P.counters[CTR_FALLBACK] != 0) *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
+// ---- shared epilogue: per-warp statistics -> global counters ------------------------------------------------
+template <bool STATS>
+__device__ __forceinline__ void flush_lists_stats(const RenderParams& P, const ListsState& S, int lane) {
+    if (STATS && P.stats && lane == 0) {
+        if (S.st_nodes) atomicAdd(P.stats + ST_NODES, S.st_nodes);
+        if (S.st_steps) atomicAdd(P.stats + ST_STEPS, S.st_steps);
+        if (S.st_cands) atomicAdd(P.stats + ST_CANDS, S.st_cands);
     }
-
-    unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
-                       st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
-#define ST(expr) do { if (STATS) { expr; } } while (0)
-
-#pragma unroll 1
-    for (;;) {
-        int tile = 0;
-        if (lane == 0) {
-            tile = (int)atomicAdd(P.counters + CTR_WORK3, 1u);
-            if (P.use_fallback_list && tile < nwork) tile = P.fallback_tiles[tile];
-            else if (P.use_fallback_list) tile = P.ntiles;
-            else tile = work_to_id(P, tile, P.macro_cols * TILES_PER_MACRO, P.ntiles);
-        }
-        tile = __shfl_sync(FULL, tile, 0);
-        if (tile >= P.ntiles) break;
-        int i0, j0;
-        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
-            tile_done(P, tile, lane);
-            continue;
-        }
-        const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
-        const bool active = pi < xe && pj < ye;
-
-        TileRays ry;
-        make_tile_rays(cam, i0, j0, pi, pj, active, ry);
-        Frustum fr;
-        make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
-
-        // ---- per-lane hit buffer (shared memory, unsorted; replace-max once K entries are held) --
-        int cnt = 0;
-        float kmax_t = INFINITY;
-        int kmax_slot = 0;
-
-        // one pending candidate per lane; the precise test and the hit-only work (entry distance,
-        // alpha, float64 refinement, buffer append) run in warp-wide rounds
-        bool pend = false;
-        int pend_c = 0;
-
-        // Distance pruning - the K-nearest form of the reference's "skip a node whose entry distance exceeds the best
-        // hit so far" (scene.py:417-419).  A ray that holds K hits needs nothing farther than its farthest one, so a
-        // box is dropped when it lies beyond `cut` = the largest such distance among the rays that are full (with a
-        // margin far above float32 rounding, so that near-ties at the K-th place still see both contenders) AND
-        // misses the pyramid of the rays that are not full yet (`tr.open`, the bounding pixel rectangle of those
-        // rays; initially the whole tile).  Children are pushed far one first.  This is what keeps a tile that looks
-        // along a surface - thousands of splats in its frustum, the first few dozen of them opaque - affordable.
-        float cut2 = -1.0f;            // (cut * (1 + 1e-4))^2, < 0: no ray is full yet
-        unsigned open_mask = __ballot_sync(FULL, active);
-        bool open_all = true;          // tr.open == fr
-        const float ox = (float)cam.o[0], oy = (float)cam.o[1], oz = (float)cam.o[2];
-        auto box_dist2 = [&](float cx, float cy, float cz, float hx, float hy, float hz) {
-            const float dx = fmaxf(fabsf(ox - cx) - hx, 0.0f), dy = fmaxf(fabsf(oy - cy) - hy, 0.0f),
-                        dz = fmaxf(fabsf(oz - cz) - hz, 0.0f);
-            return dx * dx + dy * dy + dz * dz;
-        };
-
-        int top = 1, ncq = 0;
-        if (lane == 0) tr.stack[0] = 0;
-        __syncwarp();
-
-        // ================================ traversal ==========================================
-#pragma unroll 1
-        while (top > 0 || ncq > 0) {
-            if (top > 0) {
-                const int take = top > STACK_SINGLE ? 1 : min(32, top);
-                int node = -1;
-                if (lane < take) node = tr.stack[top - 1 - lane];
-                top -= take;
-                __syncwarp();
-                bool h0 = false, h1 = false;
-                int c0 = 0, c1 = 0;
-                if (node >= 0) {
-                    float4 a, b, c, d;
-                    ldg256(P.nodes + (int64_t)node * 4 + 0, a, b);
-                    ldg256(P.nodes + (int64_t)node * 4 + 2, c, d);
-                    c0 = __float_as_int(d.x);
-                    c1 = __float_as_int(d.y);
-                    h0 = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
-                    h1 = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
-                    const float d0 = box_dist2(a.x, a.y, a.z, a.w, b.x, b.y);
-                    const float d1 = box_dist2(b.z, b.w, c.x, c.y, c.z, c.w);
-                    if (cut2 >= 0.0f) {
-                        if (h0 && d0 > cut2)
-                            h0 = open_mask != 0 && (open_all || box_in_frustum(tr.open, a.x, a.y, a.z, a.w, b.x, b.y));
-                        if (h1 && d1 > cut2)
-                            h1 = open_mask != 0 && (open_all || box_in_frustum(tr.open, b.z, b.w, c.x, c.y, c.z, c.w));
-                    }
-                    if (d1 > d0) {   // child 1 is pushed last, i.e. popped first: make it the nearer one
-                        const int ci = c0; c0 = c1; c1 = ci;
-                        const bool hi = h0; h0 = h1; h1 = hi;
-                    }
-                }
-                ST(st_nodes += 2ull * (unsigned)take);
-                ST(st_steps += 1);
-                const unsigned mI0 = __ballot_sync(FULL, h0 && c0 >= 0), mI1 = __ballot_sync(FULL, h1 && c1 >= 0);
-                const unsigned mL0 = __ballot_sync(FULL, h0 && c0 < 0), mL1 = __ballot_sync(FULL, h1 && c1 < 0);
-                if (h0 && c0 >= 0) tr.stack[top + __popc(mI0 & lt_mask)] = c0;
-                const int topa = top + __popc(mI0);
-                if (h1 && c1 >= 0) tr.stack[topa + __popc(mI1 & lt_mask)] = c1;
-                top = topa + __popc(mI1);
-                if (h0 && c0 < 0) tr.cq[ncq + __popc(mL0 & lt_mask)] = ~c0;
-                const int ncqa = ncq + __popc(mL0);
-                if (h1 && c1 < 0) tr.cq[ncqa + __popc(mL1 & lt_mask)] = ~c1;
-                ncq = ncqa + __popc(mL1);
-                __syncwarp();
-            }
-            // -------- candidate batch: stage (one lane each, float64) then test (all lanes) --
-#pragma unroll 1
-            while (ncq >= BATCH || (top == 0 && ncq > 0)) {
-                const int m = min(BATCH, ncq);
-                ncq -= m;
-                if (lane < m) {
-                    float4 rec[5];
-                    float poly[6];
-                    stage_candidate(P, ry, tr.cq[ncq + lane], rec, poly);
-#pragma unroll
-                    for (int k = 0; k < 5; ++k) tr.rec[lane][k] = rec[k];
-                    tr.polyA[lane] = make_float4(poly[0], poly[1], poly[2], poly[3]);
-                    tr.polyB[lane] = make_float2(poly[4], poly[5]);
-                }
-                __syncwarp();
-                ST(st_cands += (unsigned)m);
-                ST(st_pairs += 32ull * (unsigned)m);
-#pragma unroll 1
-                for (int c = 0; c <= m; ++c) {
-                    bool cand = false;
-                    if (c < m) {
-                        const float4 pA = tr.polyA[c];
-                        const float2 pB = tr.polyB[c];
-                        const float ta = fmaf(ry.pa, pA.w, fmaf(ry.pb, pB.x, pA.y));   // c1 + a c3 + b c4
-                        const float tb = fmaf(ry.pb, pB.y, pA.z);                      // c2 + b c5
-                        const float S = fmaf(ry.pa, ta, fmaf(ry.pb, tb, pA.x));
-                        cand = active && (S < 0.0f);
-                    }
-                    // flush when a lane gets a second candidate, and once at the end of the batch
-                    // (the staged records are about to be overwritten)
-                    if (__any_sync(FULL, pend && (cand || c == m))) {
-                        if (pend) {
-                            const PreciseHit h = precise_test(P, tr.rec[pend_c], ry.dlx, ry.dly, ry.dlz, pi, pj);
-                            ST(st_f64 += h.refined);
-                            if (h.hit) {
-                                auto find_farthest = [&]() {
-                                    float mt = -INFINITY;
-                                    int ms = 0;
-#pragma unroll 4
-                                    for (int k = 0; k < K; ++k) {
-                                        const float t = ws.kb_t[k][lane];
-                                        if (t > mt) { mt = t; ms = k; }
-                                    }
-                                    kmax_t = mt;
-                                    kmax_slot = ms;
-                                };
-                                if (cnt < K) {
-                                    const int slot = cnt++;
-                                    ws.kb_t[slot][lane] = h.t1;
-                                    ws.kb_i[slot][lane] = h.s;
-                                    ws.kb_a[slot][lane] = h.alpha;
-                                    if (cnt == K) find_farthest();
-                                } else {
-                                    // full: the candidate replaces the farthest entry if it is nearer.  Whenever
-                                    // two contenders for the last place are within float32 rounding of each other
-                                    // - the candidate and the farthest entry, or the evicted entry and the new
-                                    // farthest one - their float64 entry distances decide (exact_less; rare).
-                                    float ct = h.t1, ca = h.alpha;
-                                    int cs = h.s;
-#pragma unroll 1
-                                    for (;;) {
-                                        bool nearer = ct < kmax_t;
-                                        if (fabsf(ct - kmax_t) <= 2e-6f * kmax_t) {
-                                            nearer = exact_less(P.raw, cam, cs, ws.kb_i[kmax_slot][lane], pi, pj);
-                                            ST(st_f64 += 2);
-                                        }
-                                        if (!nearer) break;
-                                        const float et = kmax_t, ea = ws.kb_a[kmax_slot][lane];
-                                        const int es = ws.kb_i[kmax_slot][lane];
-                                        ws.kb_t[kmax_slot][lane] = ct;
-                                        ws.kb_i[kmax_slot][lane] = cs;
-                                        ws.kb_a[kmax_slot][lane] = ca;
-                                        find_farthest();
-                                        if (!(et - kmax_t <= 2e-6f * et)) break;
-                                        ct = et; cs = es; ca = ea;   // the evicted entry ties with the new farthest
-                                    }
-                                }
-                            }
-                            pend = false;
-                        }
-                        ST(st_ins += 1);
-                    }
-                    if (cand) {
-                        pend = true;
-                        pend_c = c;
-                    }
-                }
-                __syncwarp();
-                // ---- pruning state after the batch: who is full, how far their farthest hit is ----
-                {
-                    const bool full = active && cnt == K;
-                    float cm = full ? kmax_t : -1.0f;
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
-                    if (cm >= 0.0f) {
-                        cm *= 1.0001f;
-                        cut2 = cm * cm;
-                    }
-                    const unsigned om = __ballot_sync(FULL, active && cnt < K);
-                    if (om != open_mask) {
-                        open_mask = om;
-                        if (om != 0) {
-                            int il = cnt < K && active ? pi : 0x7fffffff, ih = cnt < K && active ? pi : -1;
-                            int jl = cnt < K && active ? pj : 0x7fffffff, jh = cnt < K && active ? pj : -1;
-#pragma unroll
-                            for (int o = 16; o > 0; o >>= 1) {
-                                il = min(il, __shfl_xor_sync(FULL, il, o));
-                                ih = max(ih, __shfl_xor_sync(FULL, ih, o));
-                                jl = min(jl, __shfl_xor_sync(FULL, jl, o));
-                                jh = max(jh, __shfl_xor_sync(FULL, jh, o));
-                            }
-                            Frustum fo;
-                            make_frustum(cam, il, ih + 1, jl, jh + 1, fo);
-                            if (lane == 0) tr.open = fo;
-                            open_all = false;
-                        }
-                        __syncwarp();
-                    }
-                }
-            }
-        }
-
-        // ---- order the hits by ascending entry distance: rank counting into the compositing list --
-        // rank_i = #{j : t_j < t_i}; pairs within float32 rounding of each other are ordered by their
-        // float64 entry distances (exact_less).  The traversal scratch is dead from here on.
-        int maxcnt = cnt;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
-        __syncwarp();
-        if (maxcnt > 0) {
-            float tk[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) tk[k] = k < cnt ? ws.kb_t[k][lane] : INFINITY;
-#pragma unroll 1
-            for (int i = 0; i < maxcnt; ++i) {
-                if (i < cnt) {
-                    const float ti_ = ws.kb_t[i][lane];
-                    const float band = 2e-6f * fabsf(ti_);
-                    int rank = 0, nnear = 0;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        rank += tk[j] < ti_;
-                        nnear += fabsf(tk[j] - ti_) <= band;
-                    }
-                    const int id = ws.kb_i[i][lane];
-                    if (nnear > 1) {   // rare: resolve near ties exactly
-                        rank = 0;
-#pragma unroll 1
-                        for (int j = 0; j < cnt; ++j) {
-                            if (j == i) continue;
-                            const float tj_ = ws.kb_t[j][lane];
-                            if (fabsf(tj_ - ti_) <= band) {
-                                rank += exact_less(P.raw, cam, ws.kb_i[j][lane], id, pi, pj);
-                                ST(st_f64 += 2);
-                            } else {
-                                rank += tj_ < ti_;
-                            }
-                        }
-                    }
-                    ws.c.so_i[rank][lane] = id;
-                    ws.c.so_a[rank][lane] = ws.kb_a[i][lane];
-                }
-            }
-        }
-        __syncwarp();
-
-        // ================================ compositing ========================================
-        // accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98), rgb = color +
-        // eval_sh(normalize(dir)) (gaussian.py:199-200).
-        float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
-        int nl = 0;
-        {
-            float Y[15];
-            sh_basis(ry.dnx, ry.dny, ry.dnz, Y);
-            const int nmine = min(cnt, P.depth);
-            const int nloop = min(maxcnt, P.depth);
-#pragma unroll 1
-            for (int k = 0; k < nloop; ++k) {
-                if (k < nmine && T >= P.t_cut) {
-                    const int s = ws.c.so_i[k][lane];
-                    const float alpha = ws.c.so_a[k][lane];
-                    float r, g, b;
-                    eval_colour(P, s, Y, r, g, b);
-                    const float wgt = T * alpha;
-                    cr = fmaf(wgt, r, cr);
-                    cg = fmaf(wgt, g, cg);
-                    cb = fmaf(wgt, b, cb);
-                    T *= 1.0f - alpha;
-                    ++nl;
-                }
-            }
-        }
-        store_tile(P, reinterpret_cast<float*>(&ws.kb_t[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
-        tile_done(P, tile, lane);
-        if (active) {
-            ST(st_rays += 1);
-            ST(st_hit += nl > 0);
-            ST(st_layers += (unsigned)nl);
-        }
-        ST(if (lane == 0) st_tiles += 1);
-    }
-
+}
+template <bool STATS>
+__device__ __forceinline__ void flush_shade_stats(const RenderParams& P, const ShadeStats& S, int lane) {
     if (STATS && P.stats) {
         unsigned long long v[ST_COUNT] = {0};
-        v[ST_RAYS] = st_rays; v[ST_RAYS_HIT] = st_hit; v[ST_LAYERS] = st_layers; v[ST_F64] = st_f64;
-        // warp-uniform counters are taken from lane 0 only
-        if (lane == 0) {
-            v[ST_NODES] = st_nodes;
-            v[ST_CANDS] = st_cands;
-            v[ST_PAIRS] = st_pairs;
-            v[ST_TILES] = st_tiles;
-            v[ST_STEPS] = st_steps;
-            v[ST_INSERTS] = st_ins;
-            v[ST_FALLBACK] = P.use_fallback_list ? st_tiles : 0;
+        v[ST_RAYS] = S.st_rays; v[ST_RAYS_HIT] = S.st_hit; v[ST_LAYERS] = S.st_layers; v[ST_F64] = S.st_f64;
+        if (lane == 0) {   // warp-uniform counters are taken from lane 0 only
+            v[ST_PAIRS] = 32ull * S.st_pairs;
+            v[ST_TILES] = S.st_tiles;
+            v[ST_INSERTS] = S.st_ins;
+            v[11] = S.st_useful;
         }
 #pragma unroll
         for (int k = 0; k < ST_COUNT; ++k) {
@@ -420,7 +62,172 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         }
     }
 }
-#undef ST
+
+// ---- mode 0: the two halves as separate launches -------------------------------------------------------------
+#ifndef K1_CTAS
+#define K1_CTAS 4
+#endif
+#ifndef LISTS_STATIC_SMEM
+#define LISTS_STATIC_SMEM (LISTS_STACK_ENTRIES <= 320)   // 8 warps x (stack + 960 + 256) ints fit the 48 KB static limit
+#endif
+template <bool STATS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(const __grid_constant__ RenderParams P) {
+#if LISTS_STATIC_SMEM
+    __shared__ ListsShared smem[WARPS_PER_CTA];
+    ListsShared& ws = smem[threadIdx.x >> 5];
+#else
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ListsShared& ws = reinterpret_cast<ListsShared*>(smem_raw)[threadIdx.x >> 5];
+#endif
+    const int lane = threadIdx.x & 31;
+    ListsState S;
+    const int ngroups = P.ntiles / TILES_PER_GROUP;
+#pragma unroll 1
+    for (;;) {
+        int group = 0;
+        if (lane == 0) group = (int)atomicAdd(P.counters + CTR_WORK, 1u);
+        group = work_to_id(P, __shfl_sync(FULL, group, 0), P.macro_cols * GROUPS_PER_MACRO, ngroups);
+        if (group >= ngroups) break;
+        lists_group<STATS>(P, ws, S, group, lane);
+    }
+    flush_lists_stats<STATS>(P, S, lane);
+}
+
+#ifndef K2_WARPS
+#define K2_WARPS 10
+#endif
+#ifndef K2_CTAS
+#define K2_CTAS 2
+#endif
+constexpr int SHADE_WARPS = K2_WARPS;   // warps per CTA
+static_assert(sizeof(ShadeShared) * K2_WARPS * K2_CTAS <= 227 * 1024, "shared-memory budget per SM");
+
+template <bool STATS>
+__global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ShadeShared& ws = reinterpret_cast<ShadeShared*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+    ShadeStats S;
+    PeerGrant G;
+    grant_begin(P, G);
+#pragma unroll 1
+    for (;;) {
+        int tile = 0;
+        if (lane == 0) tile = (int)atomicAdd(P.counters + CTR_WORK2, 1u);
+        tile = work_to_id(P, __shfl_sync(FULL, tile, 0), P.macro_cols * TILES_PER_MACRO, P.ntiles);
+        if (tile >= P.ntiles) break;
+        int i0, j0;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
+            tile_done(P, tile, lane);
+            continue;
+        }
+        shade_tile<STATS>(P, ws, S, G, tile, lane);
+    }
+    flush_shade_stats<STATS>(P, S, lane);
+}
+
+// ---- mode 2: the whole frame in one launch -------------------------------------------------------------------
+union __align__(16) FrameShared {
+    ListsShared lists;
+    ShadeShared shade;
+};
+static_assert(sizeof(FrameShared) * K2_WARPS * K2_CTAS <= 227 * 1024, "shared-memory budget per SM");
+
+template <bool STATS>
+__global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_frame(const __grid_constant__ RenderParams P) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    FrameShared& ws = reinterpret_cast<FrameShared*>(smem_raw)[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+    const int ngroups = P.ntiles / TILES_PER_GROUP;
+    ListsState LS;
+    ShadeStats SS;
+    PeerGrant G;
+    grant_begin(P, G);
+    // Every warp claims ONE group, then up to FOUR tiles, and repeats.  Tile claims therefore never run ahead of
+    // four times the group claims: the group of a claimed tile has been claimed by a warp that is resident and
+    // does not wait for anybody, so the acquire below always terminates.  Groups and tiles run out together.
+    bool groups_left = true, tiles_left = true;
+#pragma unroll 1
+    while (groups_left || tiles_left) {
+        if (groups_left) {
+            int group = 0;
+            if (lane == 0) group = (int)atomicAdd(P.counters + CTR_WORK, 1u);
+            group = work_to_id(P, __shfl_sync(FULL, group, 0), P.macro_cols * GROUPS_PER_MACRO, ngroups);
+            if (group >= ngroups) groups_left = false;
+            else lists_group<STATS>(P, ws.lists, LS, group, lane);
+        }
+#pragma unroll 1
+        for (int k = 0; k < TILES_PER_GROUP && tiles_left; ++k) {
+            int tile = 0;
+            if (lane == 0) tile = (int)atomicAdd(P.counters + CTR_WORK2, 1u);
+            tile = work_to_id(P, __shfl_sync(FULL, tile, 0), P.macro_cols * TILES_PER_MACRO, P.ntiles);
+            if (tile >= P.ntiles) {
+                tiles_left = false;
+                break;
+            }
+            int i0, j0;
+            if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
+                tile_done(P, tile, lane);
+                continue;
+            }
+            if (lane == 0) {   // acquire the publication of the tile's group (tile_lists.cuh)
+                const unsigned int* flag = P.ready + tile / TILES_PER_GROUP;
+                unsigned v;
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                while (v != P.seq) {
+                    __nanosleep(200);
+                    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+                }
+            }
+            __syncwarp();
+            shade_tile<STATS>(P, ws.shade, SS, G, tile, lane);
+            __syncwarp();
+        }
+    }
+    flush_lists_stats<STATS>(P, LS, lane);
+    flush_shade_stats<STATS>(P, SS, lane);
+
+    if (cta_is_last(P, CTR_DONE)) {
+        // the frame's lists and shading are complete: pool demand and fallback tiles of this frame
+        const unsigned pool = __ldcg(P.counters + CTR_POOL), fb = __ldcg(P.counters + CTR_FALLBACK);
+        *reinterpret_cast<volatile int*>(P.mirror) = (int)min(pool, 0x7fffffffu);
+        if (fb != 0) *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
+#if RTGS_CDP
+        if (P.tail_launch && fb != 0) {
+            // device-side tail launch: runs when this grid has finished, before anything queued behind it on the
+            // stream; the fused kernel's last CTA completes the frame instead
+            RenderParams Q = P;
+            Q.use_fallback_list = 1;
+            Q.final_kernel = 1;
+            int grid = (int)min((fb + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (unsigned)P.tail_grid);
+            k_render<16, STATS><<<grid, WARPS_PER_CTA * 32, sizeof(fused::WarpShared<16>) * WARPS_PER_CTA,
+                                  cudaStreamTailLaunch>>>(Q);
+        } else
+#endif
+        if (P.final_kernel) {
+            frame_complete(P);
+        }
+    }
+}
+
+// ---- multi-GPU hand-over companions (no collective on the render path: SURVEY.md 8e) -------------------------
+// Wait on a stream until *counter has reached `value` (signed distance, so the 32-bit counter may wrap).
+__global__ void k_wait_counter(const unsigned int* counter, unsigned int value) {
+    unsigned v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    while ((int)(v - value) < 0) {
+        __nanosleep(200);
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+    }
+}
+// Raise *counter to `value` at system scope, with release semantics (everything before it on the stream is complete).
+// A maximum, not a store: releases queued on different streams may execute in either order.
+__global__ void k_set_counter(unsigned int* counter, unsigned int value) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.max.u32 [%0], %1;" ::"l"(counter), "r"(value) : "memory");
+}
 
 // ---- Camera.generate_ray_field (camera.py:57-71): (W,H,8) = origin, direction, start, end -----
 __global__ void k_generate_rays(const CamD cam, float* __restrict__ rays) {
@@ -451,7 +258,7 @@ __global__ void k_trace_closest(const float4* __restrict__ nodes, const float4* 
     const float idx_[3] = {1.0f / rp[3], 1.0f / rp[4], 1.0f / rp[5]};
     double best = INFINITY, best_t2 = INFINITY;
     int best_s = -1;
-    int stack[64];
+    int stack[RTGS_MAX_TREE_DEPTH + 2];   // depth-first, <= 2 pushes per pop: never more than depth + 1 entries
     int sp = 0;
     stack[sp++] = 0;
     auto slab = [&](float mnx, float mny, float mnz, float mxx, float mxy, float mxz) -> float {
@@ -558,30 +365,48 @@ CamD make_camd(const rtgs_camera* cam) {
     return c;
 }
 
-template <int K, bool STATS>
-int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
-    static int blocks_per_sm[16] = {0};
-    const size_t smem = sizeof(WarpShared<K>) * WARPS_PER_CTA;
-    int dev = s->device;
-    if (dev < 0 || dev >= 16) dev = 0;
-    if (blocks_per_sm[dev] == 0) {
-        CUDA_TRY(cudaFuncSetAttribute(k_render<K, STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+int device_slot(const rtgs_scene* s) { return s->device >= 0 && s->device < 16 ? s->device : 0; }
+
+// Occupancy of a persistent kernel on the scene's device (cached per device), with its dynamic shared memory opted in.
+template <typename Kernel>
+int persistent_blocks(rtgs_scene* s, Kernel kernel, int threads, size_t smem, int* cache, const char* name, int* out) {
+    const int dev = device_slot(s);
+    if (cache[dev] == 0) {
+        if (smem > 0) CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int nb = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_render<K, STATS>, WARPS_PER_CTA * 32, smem));
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, threads, smem));
         if (nb < 1) {
-            rtgs_set_error("render kernel does not fit on an SM (smem %zu)", smem);
+            rtgs_set_error("%s does not fit on an SM (smem %zu)", name, smem);
             return RTGS_ERR_CUDA;
         }
-        blocks_per_sm[dev] = nb;
+        cache[dev] = nb;
+        if (getenv("RTGS_DEBUG_OCC")) fprintf(stderr, "rtgs: %s: %d CTAs/SM, %zu B dynamic smem\n", name, nb, smem);
     }
-    int grid = s->sm_count * blocks_per_sm[dev];
+    *out = cache[dev];
+    return RTGS_OK;
+}
+
+template <int K, bool STATS>
+int prepare_render_k(rtgs_scene* s, int* blocks) {
+    static int cache[16] = {0};
+    return persistent_blocks(s, k_render<K, STATS>, WARPS_PER_CTA * 32, sizeof(fused::WarpShared<K>) * WARPS_PER_CTA,
+                             cache, "k_render", blocks);
+}
+
+template <int K, bool STATS>
+int launch_render_k(rtgs_scene* s, const rtgs_scene::FrameScratch& fs, const RenderParams& P, cudaStream_t stream) {
+    int nb = 0;
+    int r = prepare_render_k<K, STATS>(s, &nb);
+    if (r != RTGS_OK) return r;
+    const size_t smem = sizeof(fused::WarpShared<K>) * WARPS_PER_CTA;
+    int grid = s->sm_count * nb;
     const int need = (P.ntiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (grid > need) grid = need;
     if (P.use_fallback_list) {
         // The fallback launch is empty unless the list pool overflowed.  While no finished frame has reported
         // fallback tiles it runs on a quarter of the SMs (a cheaper launch); the first frame that does overflow
         // is still rendered correctly, just with fewer warps on its fallback tiles.
-        const int seen = *reinterpret_cast<volatile int*>(s->band_flags + RTGS_MAX_BANDS + 1);
+        const int seen = *reinterpret_cast<volatile int*>(fs.mirror + 1);
         static const char* e = getenv("RTGS_FB_GRID");
         const int small = e ? atoi(e) : (s->sm_count + 3) / 4;
         if (!seen && grid > small) grid = small;
@@ -592,76 +417,166 @@ int launch_render_k(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
     return RTGS_OK;
 }
 
-// Which kernels render a frame: 0 = k_tile_lists + k_shade_tiles (+ k_render on the fallback list),
-// 1 = the fused k_render alone.  depth > 16 always takes the fused kernel (its k-buffer has 32 entries).
+template <bool STATS>
+int launch_tile_lists(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
+    static int cache[16] = {0};
+    const size_t smem = LISTS_STATIC_SMEM ? 0 : sizeof(ListsShared) * WARPS_PER_CTA;
+    int nb = 0;
+    int r = persistent_blocks(s, k_tile_lists<STATS>, WARPS_PER_CTA * 32, smem, cache, "k_tile_lists", &nb);
+    if (r != RTGS_OK) return r;
+    int grid = s->sm_count * nb;
+    const int need = (P.ntiles / TILES_PER_GROUP + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_tile_lists<STATS><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+template <bool STATS>
+int launch_shade_tiles(rtgs_scene* s, const RenderParams& P, cudaStream_t stream) {
+    static int cache[16] = {0};
+    const size_t smem = sizeof(ShadeShared) * SHADE_WARPS;
+    int nb = 0;
+    int r = persistent_blocks(s, k_shade_tiles<STATS>, SHADE_WARPS * 32, smem, cache, "k_shade_tiles", &nb);
+    if (r != RTGS_OK) return r;
+    int grid = s->sm_count * nb;
+    const int need = (P.ntiles + SHADE_WARPS - 1) / SHADE_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_shade_tiles<STATS><<<grid, SHADE_WARPS * 32, smem, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+template <bool STATS>
+int launch_frame(rtgs_scene* s, RenderParams& P, cudaStream_t stream) {
+    static int cache[16] = {0};
+    const size_t smem = sizeof(FrameShared) * SHADE_WARPS;
+    int nb = 0;
+    int r = persistent_blocks(s, k_frame<STATS>, SHADE_WARPS * 32, smem, cache, "k_frame", &nb);
+    if (r != RTGS_OK) return r;
+    if (P.tail_launch) {   // the device-side launch of the fused kernel needs its shared memory opted in as well
+        int nbk = 0;
+        if ((r = prepare_render_k<16, STATS>(s, &nbk)) != RTGS_OK) return r;
+        P.tail_grid = s->sm_count * nbk;
+    }
+    int grid = s->sm_count * nb;
+    // a warp does one group and four tiles per round: more warps than groups would only spin
+    const int need = (P.ntiles / TILES_PER_GROUP + SHADE_WARPS - 1) / SHADE_WARPS;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    k_frame<STATS><<<grid, SHADE_WARPS * 32, smem, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+// Which kernels render a frame: 2 (default) = k_frame, one launch; 0 = k_tile_lists + k_shade_tiles + k_render on
+// the fallback list; 1 = the fused k_render alone.  depth > 16 always takes the fused kernel (32-entry k-buffer).
 int render_mode(const rtgs_scene* s) {
     if (s->opt_render_mode >= 0) return s->opt_render_mode;
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("RTGS_RENDER_MODE");
-        mode = e ? atoi(e) : 0;
+        mode = e ? atoi(e) : 2;
+        if (mode < 0 || mode > 2) mode = 2;
+    }
+    return mode;
+}
+
+// k_frame's fallback tiles: 1 (default) = its last CTA tail-launches the fused kernel from the device when there
+// are any; 0 = the host queues the fused kernel behind every frame (it returns at once when the list is empty).
+int tail_launch_mode() {
+#if !RTGS_CDP
+    return 0;   // built without relocatable device code: the host queues the fused kernel behind every frame
+#endif
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("RTGS_TAIL_LAUNCH");
+        mode = e ? (atoi(e) != 0) : 1;
     }
     return mode;
 }
 
 // Candidate-list scratch of a scene, sized for the tile count of the largest region rendered so far.
 // The pool starts at 16 chunks (496 candidates) per tile on average - tiles may take any share of it - and
-// doubles whenever the demand reported by the last finished frame (k_tile_lists keeps counting past the end of
-// the pool; the closing k_render launch mirrors the count into mapped host memory) exceeded 70 % of it.  A frame
+// doubles whenever the demand reported by the last finished frame (lists_group keeps counting past the end of
+// the pool; the frame's last CTA mirrors the count into mapped host memory) exceeded 70 % of it.  A frame
 // that overflows is still rendered correctly (fallback list), the next one has the larger pool.
-int ensure_lists(rtgs_scene* s, int ntiles) {
-    int64_t want = s->pool_chunks;
-    if (s->opt_pool_chunks < 0 && s->list_tiles > 0) {
-        const int64_t used = *reinterpret_cast<volatile int*>(s->band_flags + RTGS_MAX_BANDS);
+int ensure_lists(rtgs_scene* s, rtgs_scene::FrameScratch& fs, int ntiles) {
+    int64_t want = fs.pool_chunks;
+    if (s->opt_pool_chunks < 0 && fs.list_tiles > 0) {
+        const int64_t used = *reinterpret_cast<volatile int*>(fs.mirror);
         while (used * 10 > want * 7 && want < (1ll << 26)) want *= 2;
     }
-    if (s->list_tiles >= ntiles && want == s->pool_chunks) return RTGS_OK;
-    const bool grow_only = s->list_tiles >= ntiles;
-    const int tiles = grow_only ? s->list_tiles : ntiles;
-    cudaFree(s->tile_desc); cudaFree(s->list_pool); cudaFree(s->fallback_tiles);
-    s->tile_desc = nullptr; s->list_pool = nullptr; s->fallback_tiles = nullptr;
-    s->list_tiles = 0;
+    if (fs.list_tiles >= ntiles && want == fs.pool_chunks) return RTGS_OK;
+    const bool grow_only = fs.list_tiles >= ntiles;
+    const int tiles = grow_only ? fs.list_tiles : ntiles;
+    cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.ready);
+    fs.tile_desc = nullptr; fs.list_pool = nullptr; fs.fallback_tiles = nullptr; fs.ready = nullptr;
+    fs.list_tiles = 0;
     int64_t chunks = s->opt_pool_chunks >= 0 ? s->opt_pool_chunks : (int64_t)tiles * 16;
     if (grow_only && want > chunks) chunks = want;
     if (chunks > (1ll << 26)) chunks = 1ll << 26;
-    CUDA_TRY(cudaMalloc((void**)&s->tile_desc, (size_t)tiles * sizeof(TileDesc)));
-    CUDA_TRY(cudaMalloc((void**)&s->list_pool, (size_t)(chunks > 0 ? chunks : 1) * CHUNK_INTS * sizeof(int)));
-    CUDA_TRY(cudaMalloc((void**)&s->fallback_tiles, (size_t)tiles * sizeof(int)));
-    s->list_tiles = tiles;
-    s->pool_chunks = (int)chunks;
-    s->band_flags[RTGS_MAX_BANDS] = 0;
+    CUDA_TRY(cudaMalloc((void**)&fs.tile_desc, (size_t)tiles * sizeof(TileDesc)));
+    CUDA_TRY(cudaMalloc((void**)&fs.list_pool, (size_t)(chunks > 0 ? chunks : 1) * CHUNK_INTS * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&fs.fallback_tiles, (size_t)tiles * sizeof(int)));
+    // group publication flags: compared with the frame sequence number, which starts at 1 and never repeats
+    const size_t groups = (size_t)tiles / TILES_PER_GROUP + 1;
+    CUDA_TRY(cudaMalloc((void**)&fs.ready, groups * sizeof(unsigned int)));
+    CUDA_TRY(cudaMemset(fs.ready, 0, groups * sizeof(unsigned int)));
+    fs.list_tiles = tiles;
+    fs.pool_chunks = (int)chunks;
+    fs.mirror[0] = 0;
     return RTGS_OK;
 }
 
 }  // namespace
 
-static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
-                            float t_cut, int accumulate, int full_pitch, float* out_rgb, float* out_T,
-                            cudaStream_t stream, bool want_stats);
+static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const rtgs_camera* cam, int x0, int y0, int w,
+                            int h, int depth, float t_cut, int accumulate, int full_pitch, float* out_rgb,
+                            float* out_T, cudaStream_t stream, bool want_stats);
 
-// A scene's render scratch (work counters, candidate lists, band counters) is shared by all its frames, which is
-// safe in stream order.  A frame launched on ANOTHER stream than the previous one (rtgs_render on the caller's
-// stream, then rtgs_render_host on the library's) first waits for that frame's kernels.
+// A frame's render scratch (work counters, candidate lists) is reused by later frames, which is safe in stream
+// order.  The scene has two scratch sets: a stream keeps the set it used last, a new stream takes the set that has
+// been idle longest and first waits for that set's last frame.  So frames launched alternately on two streams never
+// wait for each other and overlap on the device; a third stream, or statistics / banded delivery (whose counters
+// exist once), are ordered behind what they share.
 int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
                        float t_cut, int accumulate, int full_pitch, float* out_rgb, float* out_T,
                        cudaStream_t stream, bool want_stats) {
-    if (!s->scratch_free) CUDA_TRY(cudaEventCreateWithFlags(&s->scratch_free, cudaEventDisableTiming));
-    if (s->scratch_used && s->scratch_stream != stream) CUDA_TRY(cudaStreamWaitEvent(stream, s->scratch_free, 0));
-    const int r = launch_render_on(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_pitch, out_rgb, out_T, stream,
-                                   want_stats);
+    const bool exclusive = want_stats || s->bands_active > 0;   // uses stats_dev / band_done: one frame at a time
+    int pick = -1;
+    for (int k = 0; k < 2; ++k)
+        if (s->scratch[k].used && s->scratch[k].stream == stream) pick = k;
+    if (pick < 0) pick = (!s->scratch[0].used || (s->scratch[1].used && s->scratch[0].last_use < s->scratch[1].last_use)) ? 0 : 1;
+    if (exclusive) pick = 0;
+    rtgs_scene::FrameScratch& fs = s->scratch[pick];
+    for (int k = 0; k < 2; ++k) {
+        rtgs_scene::FrameScratch& o = s->scratch[k];
+        if (o.used && o.stream != stream && (k == pick || exclusive || s->exclusive_inflight))
+            CUDA_TRY(cudaStreamWaitEvent(stream, o.free_event, 0));
+    }
+    s->exclusive_inflight = exclusive;
+    const int r = launch_render_on(s, fs, cam, x0, y0, w, h, depth, t_cut, accumulate, full_pitch, out_rgb, out_T,
+                                   stream, want_stats);
+    // the hand-over pointers apply to one frame
+    s->sync_arrive = nullptr;
+    s->sync_grant = nullptr;
     // (also after a failed launch sequence: whatever was queued still uses the scratch)
-    if (cudaEventRecord(s->scratch_free, stream) == cudaSuccess) {
-        s->scratch_stream = stream;
-        s->scratch_used = true;
+    if (cudaEventRecord(fs.free_event, stream) == cudaSuccess) {
+        fs.stream = stream;
+        fs.used = true;
+        fs.last_use = ++s->scratch_clock;
     } else {
         cudaGetLastError();
     }
     return r;
 }
 
-static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h, int depth,
-                            float t_cut, int accumulate, int full_pitch, float* out_rgb, float* out_T,
-                            cudaStream_t stream, bool want_stats) {
+static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const rtgs_camera* cam, int x0, int y0, int w,
+                            int h, int depth, float t_cut, int accumulate, int full_pitch, float* out_rgb,
+                            float* out_T, cudaStream_t stream, bool want_stats) {
     RenderParams P;
     P.nodes = s->nodes;
     P.nodes4 = s->nodes4;
@@ -684,7 +599,7 @@ static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y
     P.has_sh = s->has_sh ? 1 : 0;
     P.out_rgb = out_rgb;
     P.out_T = out_T;
-    P.counters = s->counters;
+    P.counters = fs.counters;
     P.stats = want_stats ? s->stats_dev : nullptr;
     P.desc = nullptr;
     P.pool = nullptr;
@@ -695,22 +610,43 @@ static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y
     P.heavy_fused = heavy_fused;
     static const int heavy_limit = getenv("RTGS_HEAVY_LIMIT") ? atoi(getenv("RTGS_HEAVY_LIMIT")) : 1 << 30;
     P.heavy_limit = heavy_limit;
+    {
+        // batch threshold of the traversal stack: the tuned value, capped by what this tree's depth allows
+        static const int tuned = getenv("RTGS_LISTS_SINGLE") ? atoi(getenv("RTGS_LISTS_SINGLE")) : 112;
+        const int bound = lists_single_bound(s->max_depth);
+        P.lists_single = tuned < bound ? tuned : bound;
+        if (P.lists_single < 0) P.lists_single = 0;
+    }
     P.nbands = 0;
     P.band_macro_cols = 1;
     P.macro_rows = mrows;
     P.schedule = s->bands_active > 0 ? s->band_schedule : 0;
     P.band_done = s->band_done;
     P.band_flags = s->band_flags_cur_dev ? s->band_flags_cur_dev : s->band_flags_dev;
-    P.mirror = s->band_flags_dev + RTGS_MAX_BANDS;
+    P.mirror = fs.mirror_dev;
+    P.ready = nullptr;
+    P.seq = 0;
+    P.arrive = s->sync_arrive;
+    P.grant = s->sync_grant;
+    P.grant_value = s->sync_grant_value;
+    P.tail_launch = 0;
+    P.final_kernel = 0;
+    P.self_clean = 0;
+    P.tail_grid = 0;
     if (s->bands_active > 0) {
         P.nbands = s->bands_active;
         P.band_macro_cols = s->band_macro_cols;
         CUDA_TRY(cudaMemsetAsync(s->band_done, 0, RTGS_MAX_BANDS * sizeof(unsigned int), stream));
     }
-    CUDA_TRY(cudaMemsetAsync(s->counters, 0, CTR_COUNT * sizeof(unsigned int), stream));
+    const int mode = depth > 16 ? 1 : render_mode(s);
+    // work counters: k_frame's last CTA leaves them zeroed for the next frame; the other modes (and the first
+    // frame after one of them) reset them here
+    const bool self_clean = mode == 2;
+    if (!self_clean || fs.counters_dirty) CUDA_TRY(cudaMemsetAsync(fs.counters, 0, CTR_COUNT * sizeof(unsigned int), stream));
+    fs.counters_dirty = !self_clean;
     if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), stream));
 
-    // optional per-kernel timing: events e[0..3] of this frame's ring slot bracket the three kernels
+    // optional per-kernel timing: events e[0..3] of this frame's ring slot bracket up to three launches
     cudaEvent_t* ev = nullptr;
     unsigned char* ran = nullptr;
     if (!s->timing_ran.empty()) {
@@ -724,31 +660,54 @@ static int launch_render_on(rtgs_scene* s, const rtgs_camera* cam, int x0, int y
         if (ev) CUDA_TRY(cudaEventRecord(ev[k], stream));
         return RTGS_OK;
     };
-    auto fused = [&](int K) -> int {
-        if (K > 16) return want_stats ? launch_render_k<32, true>(s, P, stream) : launch_render_k<32, false>(s, P, stream);
-        return want_stats ? launch_render_k<16, true>(s, P, stream) : launch_render_k<16, false>(s, P, stream);
+    auto fused_kernel = [&](int K) -> int {
+        if (K > 16) return want_stats ? launch_render_k<32, true>(s, fs, P, stream) : launch_render_k<32, false>(s, fs, P, stream);
+        return want_stats ? launch_render_k<16, true>(s, fs, P, stream) : launch_render_k<16, false>(s, fs, P, stream);
     };
     int r;
-    if (depth > 16 || render_mode(s) == 1) {
+    if (mode == 1) {
         if ((r = mark(0)) != RTGS_OK || (r = mark(1)) != RTGS_OK || (r = mark(2)) != RTGS_OK) return r;
-        if ((r = fused(depth > 16 ? 32 : 16)) != RTGS_OK) return r;
+        P.final_kernel = 1;
+        if ((r = fused_kernel(depth > 16 ? 32 : 16)) != RTGS_OK) return r;
         if (ran) *ran = 4;
         return mark(3);
     }
-    // traversal -> per-tile candidate lists -> shading; tiles whose list did not fit the pool are
-    // rendered by the fused kernel afterwards (it returns at once when there are none)
-    if ((r = ensure_lists(s, P.ntiles)) != RTGS_OK) return r;
-    P.desc = reinterpret_cast<TileDesc*>(s->tile_desc);
-    P.pool = s->list_pool;
-    P.pool_chunks = s->pool_chunks;
-    P.fallback_tiles = s->fallback_tiles;
+    // traversal -> per-tile candidate lists -> shading; tiles whose list did not fit the pool (or whose group holds
+    // too many candidates) are rendered by the fused kernel behind them
+    if ((r = ensure_lists(s, fs, P.ntiles)) != RTGS_OK) return r;
+    P.desc = reinterpret_cast<TileDesc*>(fs.tile_desc);
+    P.pool = fs.list_pool;
+    P.pool_chunks = fs.pool_chunks;
+    P.fallback_tiles = fs.fallback_tiles;
+    if (mode == 2) {
+        P.ready = fs.ready;
+        P.seq = ++fs.frame_seq;
+        // banded host delivery counts tiles per band in both kernels: keep the host-side launch order there
+        const bool tail = tail_launch_mode() != 0;
+        P.tail_launch = tail ? 1 : 0;
+        P.final_kernel = tail ? 1 : 0;
+        P.self_clean = tail ? 1 : 0;
+        if ((r = mark(0)) != RTGS_OK || (r = mark(1)) != RTGS_OK) return r;
+        if ((r = want_stats ? launch_frame<true>(s, P, stream) : launch_frame<false>(s, P, stream)) != RTGS_OK) return r;
+        if ((r = mark(2)) != RTGS_OK) return r;
+        if (ran) *ran = 2;
+        if (!tail) {
+            P.use_fallback_list = 1;
+            P.final_kernel = 1;
+            P.self_clean = 1;
+            if ((r = fused_kernel(16)) != RTGS_OK) return r;
+            if (ran) *ran = 6;
+        }
+        return mark(3);
+    }
     if ((r = mark(0)) != RTGS_OK) return r;
-    if ((r = rtgs_launch_tile_lists(s, P, stream, want_stats)) != RTGS_OK) return r;
+    if ((r = want_stats ? launch_tile_lists<true>(s, P, stream) : launch_tile_lists<false>(s, P, stream)) != RTGS_OK) return r;
     if ((r = mark(1)) != RTGS_OK) return r;
-    if ((r = rtgs_launch_shade_tiles(s, P, stream, want_stats)) != RTGS_OK) return r;
+    if ((r = want_stats ? launch_shade_tiles<true>(s, P, stream) : launch_shade_tiles<false>(s, P, stream)) != RTGS_OK) return r;
     if ((r = mark(2)) != RTGS_OK) return r;
     P.use_fallback_list = 1;
-    if ((r = fused(16)) != RTGS_OK) return r;
+    P.final_kernel = 1;
+    if ((r = fused_kernel(16)) != RTGS_OK) return r;
     if (ran) *ran = 7;
     return mark(3);
 }
@@ -774,6 +733,18 @@ int rtgs_launch_activate_ply(int64_t n, const float* rows_dev, int stride, const
                              float* sh, cudaStream_t stream) {
     k_activate_ply<<<(int)((n + 127) / 128), 128, 0, stream>>>(n, rows_dev, stride, col, scale, sh_layout, pos, rot,
                                                                sca, color, opacity, sh);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+int rtgs_launch_wait_counter(const unsigned int* counter, unsigned int value, cudaStream_t stream) {
+    k_wait_counter<<<1, 1, 0, stream>>>(counter, value);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+int rtgs_launch_set_counter(unsigned int* counter, unsigned int value, cudaStream_t stream) {
+    k_set_counter<<<1, 1, 0, stream>>>(counter, value);
     CUDA_TRY(cudaGetLastError());
     return RTGS_OK;
 }

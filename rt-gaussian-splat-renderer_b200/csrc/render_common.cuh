@@ -1,9 +1,11 @@
-// render_common.cuh — declarations shared by the render kernels (sm_100a):
-//   tile_lists.cu  k_tile_lists   LBVH traversal, one candidate list per 4x8-pixel tile   (scene.py:406-450)
-//   shade.cu       k_shade_tiles  intersection + k-buffer + SH compositing per tile       (gaussian.py:140-230,
+// render_common.cuh — declarations shared by the render kernels (sm_100a), all compiled in render.cu:
+//   tile_lists.cuh lists_group    LBVH traversal, one candidate list per 4x8-pixel tile   (scene.py:406-450)
+//   shade.cuh      shade_tile     intersection + k-buffer + SH compositing per tile       (gaussian.py:140-230,
 //                                                                                          ray_tracer.py:79-104)
-//   render.cu      k_render       the same path fused in one kernel (depth > 16, and tiles whose list did
-//                                 not fit the list pool)
+//   fused.cuh      k_render       the same path per tile with distance pruning (depth > 16, tiles whose list did
+//                                 not fit the list pool, groups whose frustum holds ~1000 Gaussians or more)
+//   render.cu      k_frame        ONE launch per frame: persistent warps alternate between lists_group and
+//                                 shade_tile; k_tile_lists / k_shade_tiles are the same code as two launches
 #pragma once
 #include "common.cuh"
 #include "gsmath.cuh"
@@ -35,6 +37,11 @@ struct TileDesc {
     int count;   // candidates; -1: the list did not fit the pool, the tile is in the fallback list
 };
 
+enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_DONE = 5, CTR_DONE2 = 6,
+       CTR_COUNT = 8 };
+enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
+       ST_FALLBACK, ST_COUNT = 12 };
+
 struct RenderParams {
     const float4* nodes;
     const float4* nodes4;     // two-level nodes (k_tile_lists)
@@ -62,17 +69,91 @@ struct RenderParams {
     int use_fallback_list;    // k_render: take tile ids from fallback_tiles[0 .. counters[2])
     int heavy_fused;          // k_tile_lists: a group whose list overflows shared memory goes to k_render (distance pruning)
     int heavy_limit;          // ... "overflows" = more candidates than this (<= the capacity of the shared-memory list)
+    int lists_single;         // lists_group pops one node per step while its stack holds more entries than this (tile_lists.cuh)
     // band completion (host-pipelined framebuffer copy, rtgs_render_host): the frame is cut into nbands bands of
     // band_macro_cols 32-pixel columns; a band is finished when all its tile ids have been rendered or skipped
     int nbands, band_macro_cols, macro_rows, schedule;
     unsigned int* band_done;  // device counters, one per band
     int* band_flags;          // mapped pinned host memory: set to 1 by the warp that finishes the band
     int* mirror;              // mapped pinned host memory: [0] list-pool demand of the frame, [1] a frame had fallback tiles
+    // group publication (tile_lists.cuh -> shade.cuh inside one launch): ready[group] == seq <=> the descriptors and
+    // list chunks of the group's four tiles are complete for THIS frame (no reset between frames)
+    unsigned int* ready;
+    unsigned int seq;
+    // frame completion and multi-GPU hand-over (render.cu: finish_frame).  All optional (nullptr = off):
+    //   arrive      counter the LAST CTA of the frame's last kernel release-increments at system scope once every store
+    //               of the frame is performed; may live in a peer GPU's memory (tile / view sharding: the
+    //               gathering rank waits for world x frames arrivals - no collective, no extra launch)
+    //   grant       before a warp's first framebuffer store it waits until *grant >= grant_value (signed distance):
+    //               the consumer of a peer-mapped framebuffer has released the buffer this frame is written into
+    unsigned int* arrive;
+    const unsigned int* grant;
+    unsigned int grant_value;
+    int tail_launch;          // k_frame: the last CTA launches the fused kernel for the fallback tiles itself
+                              // (device-side tail launch) instead of the host queueing a third kernel per frame
+    int final_kernel;         // this launch is the frame's last kernel: its last CTA completes the frame (frame_complete)
+    int self_clean;           // ... and zeroes the work counters for the next frame (no memset between frames)
+    int tail_grid;            // CTAs of a device-side k_render launch (2 per SM)
 };
 
-enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_COUNT = 8 };
-enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
-       ST_FALLBACK, ST_COUNT = 12 };
+// System-scope hand-over of a framebuffer that other GPUs read or write (see RenderParams::grant).
+struct PeerGrant {
+    unsigned seen;
+    bool ok;
+};
+__device__ __forceinline__ void grant_begin(const RenderParams& P, PeerGrant& g) {
+    g.ok = P.grant == nullptr;
+    g.seen = 0;
+    // issued at kernel start, consumed before the warp's first store: normally satisfied long before
+    if (!g.ok) asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(g.seen) : "l"(P.grant) : "memory");
+}
+__device__ __forceinline__ void grant_wait(const RenderParams& P, PeerGrant& g) {
+    if (g.ok) return;
+    while ((int)(g.seen - P.grant_value) < 0) {
+        __nanosleep(500);
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(g.seen) : "l"(P.grant) : "memory");
+    }
+    g.ok = true;
+}
+
+// The frame is complete (call from ONE thread, after every CTA of the frame's last kernel has finished its stores):
+// hand-over signal for whoever gathers the frame, then the work counters are zeroed for the next frame.
+__device__ __forceinline__ void frame_complete(const RenderParams& P) {
+    if (P.arrive) {
+        __threadfence_system();
+        asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(P.arrive) : "memory");
+    }
+    if (P.self_clean) {
+#pragma unroll
+        for (int k = 0; k < CTR_COUNT; ++k) P.counters[k] = 0u;
+    }
+}
+
+// End of a kernel: count the finished CTAs; returns true in thread 0 of the CTA that finishes last, with every
+// other CTA's stores ordered before it (fence - atomic - fence; system scope when another GPU will read them).
+__device__ __forceinline__ bool cta_is_last(const RenderParams& P, int ctr) {
+    __syncthreads();
+    if (threadIdx.x != 0) return false;
+    if (P.arrive) __threadfence_system(); else __threadfence();
+    const unsigned prev = atomicAdd(P.counters + ctr, 1u);
+    if (prev + 1u != gridDim.x) return false;
+    __threadfence();
+    return true;
+}
+__device__ __forceinline__ void cta_finish(const RenderParams& P, int ctr) {
+    if (cta_is_last(P, ctr)) frame_complete(P);
+}
+
+// Descriptor of a published tile, read at L2: within one launch the line may have been cached in L1 while a
+// neighbouring descriptor was still unwritten.
+__device__ __forceinline__ TileDesc load_desc(const RenderParams& P, int tile) {
+    const int2 v = __ldcg(reinterpret_cast<const int2*>(P.desc) + tile);
+    TileDesc d;
+    d.head = v.x;
+    d.count = v.y;
+    return d;
+}
+
 
 // A tile id has been rendered (its framebuffer stores are issued) or skipped: count it for its band and, when
 // the band is complete, raise the host-visible flag.  Call with the whole warp converged, after store_tile.
@@ -478,12 +559,9 @@ __device__ __forceinline__ void store_tile(const RenderParams& P, float* ob, int
             else *o = ob[f];
         }
     }
-    __syncwarp();
     if (active && P.out_T) P.out_T[(int64_t)(pi - bi) * pitch + (pj - bj)] = T;
+    __syncwarp();   // every lane's RGB and T stores are ordered before whatever lane 0 releases next (tile_done)
 }
 
 }  // namespace rtgs_dev
 
-// launchers of the two-kernel path (tile_lists.cu, shade.cu); P.counters/desc/pool must be set up
-int rtgs_launch_tile_lists(rtgs_scene* s, const rtgs_dev::RenderParams& P, cudaStream_t stream, bool want_stats);
-int rtgs_launch_shade_tiles(rtgs_scene* s, const rtgs_dev::RenderParams& P, cudaStream_t stream, bool want_stats);

@@ -1,0 +1,392 @@
+// shade.cuh — everything of the render path after the traversal, per 4x8-pixel tile (device code shared by the
+// stand-alone k_shade_tiles kernel and the single-launch frame kernel k_frame, render.cu):
+//   camera ray generation        camera.py:31-71              (registers; rays never stored)
+//   ray-Gaussian intersection    gaussian.py:203-230          (local-frame quadratic)
+//   response + SH colour         gaussian.py:140-201
+//   front-to-back compositing    ray_tracer.py:79-104         (k-buffer of the `depth` nearest entries)
+//
+// A warp owns one tile at a time (lane = pixel) and walks the tile's candidate list, 31 candidates (one
+// 128-byte chunk) per batch:
+//   stage    one lane per candidate, float64: origin shifted to the closest point of the tile's centre
+//            ray -> a 80-byte float32 record + a 6-coefficient quadratic in shared memory;
+//   coarse   every lane evaluates every staged quadratic (broadcast shared-memory reads, 5 FMA) and
+//            keeps a 32-bit mask of the candidates its ray may hit;
+//   precise  warp-wide rounds, each lane takes the next set bit of its mask: exact decision (float32
+//            in the tile-centred frame, float64 from the raw parameters inside the error band), entry
+//            distance, alpha; the hit goes to the lane's K-entry buffer in shared memory (replace-max
+//            once K are held; the nearest hit left outside is remembered, and if it is within float32
+//            rounding of the farthest kept entry the two are compared in float64 after the list).
+// After the list: the lane's entries are ordered by a bitonic network over (entry-distance bits | slot) keys in
+// registers (near ties by their float64 entry distances), composited in that order with the SH basis evaluated
+// once per ray (six 256-bit loads per layer), and stored sector-aligned.
+//
+// Numerics: identical to the fused kernel (fused.cuh) - parity is defined against the float64
+// evaluation of the reference's maths, see DESIGN.md §2.
+//
+// The code is bound by the L1 data pipe (per-lane gathers of SH and staged records), not by latency:
+// 20 warps x 96 registers per SM is the measured optimum, 9.25 KB of shared memory per warp.
+#pragma once
+#include "render_common.cuh"
+
+namespace rtgs_dev {
+
+#ifndef SHADE_POOL_LDG
+#define SHADE_POOL_LDG 0   // experiment: candidate chunks through the read-only (L1) path; only safe with separate launches
+#endif
+#if SHADE_POOL_LDG
+#define POOL_LOAD __ldg
+#else
+#define POOL_LOAD __ldcg
+#endif
+#ifndef SHADE_SLOT_ORDER
+#define SHADE_SLOT_ORDER 0
+#endif
+constexpr int SHADE_K = 16;          // k-buffer entries (depth <= 16)
+constexpr float TIE_BAND = 2e-6f;    // relative: float32 entry distances closer than this are compared in float64
+constexpr int SHADE_BATCH = 32;      // staged candidates per batch (a chunk fills 31)
+constexpr int SHADE_REC_Q = 5;       // quads per staged record (80-byte stride: conflict-free gathers)
+
+struct __align__(16) ShadeShared {
+    float4 rec[SHADE_BATCH][SHADE_REC_Q];  // precise records
+    float4 polyA[SHADE_BATCH];             // coarse quadratics {c0 c1 c2 c3}
+    float2 polyB[SHADE_BATCH];             //                   {c4 c5}
+    float kb_t[SHADE_K][32];               // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
+    int kb_i[SHADE_K][32];
+    float kb_a[SHADE_K][32];
+    float amb[2][32];                      // per lane: id and alpha of the nearest hit that is NOT in the buffer
+};
+
+struct ShadeStats {
+    unsigned long long st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0,
+                       st_ins = 0;
+};
+
+// Bitonic sorting network over the first N (8 or 16) of 16 register-resident keys, ascending.
+template <int N>
+__device__ __forceinline__ void sort_keys(unsigned (&key)[16]) {
+#pragma unroll
+    for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const unsigned a = key[i], b = key[l];
+                    const bool up = (i & k) == 0;
+                    key[i] = up ? min(a, b) : max(a, b);
+                    key[l] = up ? max(a, b) : min(a, b);
+                }
+            }
+        }
+    }
+}
+
+// Could the entry distances behind two sorted keys be within 4e-6 relative of each other?  (The keys
+// carry the distances with 4 truncated bits, hence the wider 6e-6 screen; unused keys are 0xffffffff.)
+__device__ __forceinline__ bool keys_near(unsigned ka, unsigned kb) {
+    const float ta = __uint_as_float(ka & ~15u), tb = __uint_as_float(kb & ~15u);
+    return kb != 0xffffffffu && (tb - ta) <= 6e-6f * tb;
+}
+
+// Shade tile `tile` (a valid id < P.ntiles whose descriptor has been published).
+template <bool STATS>
+__device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& ws, ShadeStats& S, PeerGrant& G, int tile,
+                                           int lane) {
+    constexpr int K = SHADE_K;
+    constexpr int BATCH = SHADE_BATCH;
+    const CamD& cam = P.cam;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
+#define ST(expr) do { if (STATS) { expr; } } while (0)
+    int i0, j0;
+    tile_origin(P, tile, i0, j0);
+    const TileDesc desc = load_desc(P, tile);
+    if (desc.count < 0) return;   // list did not fit the pool: the fused kernel renders this tile
+    const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
+    const bool active = pi < xe && pj < ye;
+
+    int cnt = 0;
+    // The K nearest hits are kept by their float32 entry distances (replace-max once the buffer is full).  Which
+    // of two hits is nearer is only certain beyond float32 rounding (TIE_BAND), so the one place where it
+    // matters - the boundary between the K-th and the (K+1)-th nearest - is re-examined in float64 after the
+    // list: e1_t / ws.amb hold the nearest hit that is NOT in the buffer (a rejected hit or an evicted entry),
+    // bit 8 of kmax_slot says that a second such hit lies within float32 rounding of it.  (Checking every
+    // transient boundary instead sent 8 % of the dense tiles of a surface-like scene to the fused kernel:
+    // a ray with 1000 hits replaces its farthest entry ~60 times.)
+    float e1_t = INFINITY, kmax_t = INFINITY;
+    int kmax_slot = 0;
+    TileRays tr;
+    if (desc.count > 0) {
+        make_tile_rays(cam, i0, j0, pi, pj, active, tr);
+        int left = desc.count;
+        // one coalesced 128-byte read per chunk: lanes 0..30 candidates, lane 31 the next chunk
+        int cur = POOL_LOAD(P.pool + (int64_t)desc.head * CHUNK_INTS + lane);
+#pragma unroll 1
+        while (left > 0) {
+            const int m = (left - 1) % CHUNK_IDS + 1;
+            left -= m;
+            const int s = cur;
+            const int next = __shfl_sync(FULL, cur, CHUNK_INTS - 1);
+            if (left > 0) cur = POOL_LOAD(P.pool + (int64_t)next * CHUNK_INTS + lane);   // prefetch
+            // ---- stage ---------------------------------------------------------------------
+            const int m4 = (m + 3) & ~3;
+            if (lane < m) {
+                float4 rec[5];
+                float poly[6];
+                stage_candidate(P, tr, s, rec, poly);
+#pragma unroll
+                for (int k = 0; k < 5; ++k) ws.rec[lane][k] = rec[k];
+                ws.polyA[lane] = make_float4(poly[0], poly[1], poly[2], poly[3]);
+                ws.polyB[lane] = make_float2(poly[4], poly[5]);
+            } else if (lane < m4) {   // pad to a multiple of 4: never a candidate
+                ws.polyA[lane] = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+                ws.polyB[lane] = make_float2(0.0f, 0.0f);
+            }
+            __syncwarp();
+            ST(S.st_pairs += (unsigned)m);
+            // ---- coarse: mask of the staged candidates this ray may hit ---------------------
+            unsigned mask = 0;
+#pragma unroll 1
+            for (int c = 0; c < m4; c += 4) {
+                unsigned nib = 0;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 pA = ws.polyA[c + u];
+                    const float2 pB = ws.polyB[c + u];
+                    const float ta = fmaf(tr.pa, pA.w, fmaf(tr.pb, pB.x, pA.y));   // c1 + a c3 + b c4
+                    const float tb = fmaf(tr.pb, pB.y, pA.z);                      // c2 + b c5
+                    const float S = fmaf(tr.pa, ta, fmaf(tr.pb, tb, pA.x));
+                    if (S < 0.0f) nib |= 1u << u;
+                }
+                mask |= nib << c;
+            }
+            if (!active) mask = 0;
+            ST(S.st_useful += (unsigned)__popc(__reduce_or_sync(FULL, mask)));
+            // ---- precise: warp-wide rounds, one candidate per lane and round -----------------
+#pragma unroll 1
+            while (__any_sync(FULL, mask != 0)) {
+                if (mask != 0) {
+                    const int c = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const PreciseHit h = precise_test(P, ws.rec[c], tr.dlx, tr.dly, tr.dlz, pi, pj);
+                    ST(S.st_f64 += h.refined);
+                    if (h.hit) {
+                        float xt = h.t1, xa = h.alpha;   // the hit that stays outside the buffer (full buffer)
+                        int xi = h.s;
+                        int slot = -1;
+                        if (cnt < K) {
+                            slot = cnt++;
+                        } else if (h.t1 < kmax_t) {   // full: replace the farthest entry, which goes outside
+                            slot = kmax_slot & 15;
+                            xt = kmax_t;
+                            xi = ws.kb_i[slot][lane];
+                            xa = ws.kb_a[slot][lane];
+                        }
+                        const bool full = cnt == K;
+                        if (slot >= 0) {
+                            ws.kb_t[slot][lane] = h.t1;
+                            ws.kb_i[slot][lane] = h.s;
+                            ws.kb_a[slot][lane] = h.alpha;
+                            if (full) {   // track the farthest entry (exact float32 maximum)
+                                float mt = -INFINITY;
+                                int ms = 0;
+#pragma unroll
+                                for (int k = 0; k < K; ++k) {
+                                    const float t = ws.kb_t[k][lane];
+                                    if (t > mt) { mt = t; ms = k; }
+                                }
+                                kmax_slot = ms | (kmax_slot & 0x100);
+                                if (kmax_t == INFINITY) xt = INFINITY;   // the buffer has just filled: nothing is outside yet
+                                kmax_t = mt;
+                            }
+                        }
+                        if (full && xt < INFINITY) {
+                            if (xt < e1_t) {
+                                kmax_slot = (e1_t - xt <= TIE_BAND * xt) ? (kmax_slot | 0x100) : (kmax_slot & ~0x100);
+                                e1_t = xt;
+                                ws.amb[0][lane] = __int_as_float(xi);
+                                ws.amb[1][lane] = xa;
+                            } else if (xt - e1_t <= TIE_BAND * e1_t) {
+                                kmax_slot |= 0x100;
+                            }
+                        }
+                    }
+                }
+                ST(S.st_ins += 1);
+            }
+            __syncwarp();
+        }
+    }
+
+    // ---- the K-th / (K+1)-th boundary (rare): is the nearest outside hit within float32 rounding of the
+    // farthest entry?  Then their float64 entry distances decide, repeatedly while the loser ties again.
+    const bool amb = e1_t - kmax_t <= TIE_BAND * kmax_t;   // false while either is inf
+    if (__any_sync(FULL, amb)) {
+        if (__any_sync(FULL, amb && (kmax_slot & 0x100))) {
+            // three contenders within rounding: k_render (launched next on the stream) renders the tile and
+            // resolves them on the spot; nothing of it has been written yet, so `accumulate` outputs stay correct
+            if (lane == 0) {
+                P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
+                *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
+            }
+            return;
+        }
+        if (amb) {
+            float ct = e1_t, ca = ws.amb[1][lane];
+            int ci = __float_as_int(ws.amb[0][lane]);
+            float mt = kmax_t;
+            int ms = kmax_slot & 15;
+#pragma unroll 1
+            for (int it = 0; it < 4; ++it) {
+                if (!(ct - mt <= TIE_BAND * mt)) break;
+                ST(S.st_f64 += 2);
+                if (!exact_less(P.raw, cam, ci, ws.kb_i[ms][lane], pi, pj)) break;
+                // the outside hit is nearer: it takes the slot, the former farthest entry is the contender now
+                const float ot = mt, oa = ws.kb_a[ms][lane];
+                const int oi = ws.kb_i[ms][lane];
+                ws.kb_t[ms][lane] = ct;
+                ws.kb_i[ms][lane] = ci;
+                ws.kb_a[ms][lane] = ca;
+                ct = ot; ci = oi; ca = oa;
+                mt = -INFINITY;
+#pragma unroll 1
+                for (int k = 0; k < K; ++k) {
+                    const float t = ws.kb_t[k][lane];
+                    if (t > mt) { mt = t; ms = k; }
+                }
+            }
+        }
+    }
+
+    // ---- order the hits by ascending entry distance -------------------------------------------
+    // Keys = entry-distance bits (positive floats order like their bit patterns) with the slot in the
+    // 4 low bits, sorted in registers by a bitonic network; perm holds the slot of every rank, 4 bits
+    // each.  Neighbours within float32 rounding (and the 4 truncated bits) of each other are then
+    // ordered by their float64 entry distances (rare).
+    unsigned long long perm = 0;
+    int maxcnt = cnt;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
+    if (maxcnt > 0) {
+        unsigned key[K];
+        bool near = false;
+        if (maxcnt <= 8) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
+            sort_keys<8>(key);
+            unsigned lo = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) lo |= (key[r] & 15u) << (4 * r);
+            perm = lo;
+#pragma unroll
+            for (int r = 0; r + 1 < 8; ++r) near = near || keys_near(key[r], key[r + 1]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < K; ++k)
+                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
+            sort_keys<16>(key);
+            unsigned lo = 0, hi = 0;
+#pragma unroll
+            for (int r = 0; r < 8; ++r) {
+                lo |= (key[r] & 15u) << (4 * r);
+                hi |= (key[r + 8] & 15u) << (4 * r);
+            }
+            perm = ((unsigned long long)hi << 32) | lo;
+#pragma unroll
+            for (int r = 0; r + 1 < K; ++r) near = near || keys_near(key[r], key[r + 1]);
+        }
+        if (near) {
+            float tp = ws.kb_t[(int)(perm & 15u)][lane];
+#pragma unroll 1
+            for (int k = 1; k < cnt; ++k) {
+                const int sk = (int)((perm >> (4 * k)) & 15u);
+                const float tk = ws.kb_t[sk][lane];
+                if (fabsf(tk - tp) <= 4e-6f * fabsf(tk)) {
+                    // insertion among the near-tied predecessors
+                    int j = k;
+                    while (j > 0) {
+                        const int sa = (int)((perm >> (4 * (j - 1))) & 15u), sb = (int)((perm >> (4 * j)) & 15u);
+                        const float ta = ws.kb_t[sa][lane], tb = ws.kb_t[sb][lane];
+                        if (fabsf(tb - ta) > 4e-6f * fabsf(tb)) break;
+                        ST(S.st_f64 += 2);
+                        if (!exact_less(P.raw, cam, ws.kb_i[sb][lane], ws.kb_i[sa][lane], pi, pj)) break;
+                        const unsigned long long ma = 15ull << (4 * (j - 1)), mb = 15ull << (4 * j);
+                        perm = (perm & ~(ma | mb)) | ((unsigned long long)sb << (4 * (j - 1))) |
+                               ((unsigned long long)sa << (4 * j));
+                        --j;
+                    }
+                }
+                tp = ws.kb_t[(int)((perm >> (4 * k)) & 15u)][lane];
+            }
+        }
+    }
+
+    // ---- compositing: accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98) ---------
+    float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
+    int nl = 0;
+    if (maxcnt > 0) {
+        float Y[15];
+        sh_basis(tr.dnx, tr.dny, tr.dnz, Y);
+        const int nmine = min(cnt, P.depth);
+#if SHADE_SLOT_ORDER
+        // Weights first: w_k = T_k alpha_k depends on the alphas and their depth order only, so the ordered pass
+        // touches no colour data; the colour sum  accum = sum_k w_k rgb_k  is then taken in SLOT order.  Slots fill
+        // in list order, which all rays of the tile share, so lanes that hold the same Gaussian tend to reach it
+        // in the same iteration and share its SH record (one L1 wavefront set instead of several).
+#pragma unroll 1
+        for (int k = 0; k < cnt; ++k) {
+            const int slot = (int)((perm >> (4 * k)) & 15u);
+            const float alpha = ws.kb_a[slot][lane];
+            const bool use = k < nmine && T >= P.t_cut;
+            ws.kb_a[slot][lane] = use ? T * alpha : 0.0f;
+            if (use) {
+                T *= 1.0f - alpha;
+                ++nl;
+            }
+        }
+#pragma unroll 1
+        for (int slot = 0; slot < maxcnt; ++slot) {
+            const float wgt = slot < cnt ? ws.kb_a[slot][lane] : 0.0f;
+            if (wgt != 0.0f) {
+                float r, g, b;
+                eval_colour(P, ws.kb_i[slot][lane], Y, r, g, b);
+                cr = fmaf(wgt, r, cr);
+                cg = fmaf(wgt, g, cg);
+                cb = fmaf(wgt, b, cb);
+            }
+        }
+#else
+        const int nloop = min(maxcnt, P.depth);
+#pragma unroll 1
+        for (int k = 0; k < nloop; ++k) {
+            if (k < nmine && T >= P.t_cut) {
+                const int slot = (int)((perm >> (4 * k)) & 15u);
+                const int s = ws.kb_i[slot][lane];
+                const float alpha = ws.kb_a[slot][lane];
+                float r, g, b;
+                eval_colour(P, s, Y, r, g, b);
+                const float wgt = T * alpha;
+                cr = fmaf(wgt, r, cr);
+                cg = fmaf(wgt, g, cg);
+                cb = fmaf(wgt, b, cb);
+                T *= 1.0f - alpha;
+                ++nl;
+            }
+        }
+#endif
+    }
+    grant_wait(P, G);
+    store_tile(P, reinterpret_cast<float*>(&ws.rec[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
+    tile_done(P, tile, lane);
+    if (active) {
+        ST(S.st_rays += 1);
+        ST(S.st_hit += nl > 0);
+        ST(S.st_layers += (unsigned)nl);
+    }
+    ST(if (lane == 0) S.st_tiles += 1);
+
+#undef ST
+}
+
+}  // namespace rtgs_dev

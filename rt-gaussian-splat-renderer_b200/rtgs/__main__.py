@@ -47,7 +47,12 @@ def build_parser() -> argparse.ArgumentParser:
     p.add_argument("--views", type=int, default=0, help="orbit sweep: N views theta_k = 2 pi k / N (0 = single pose)")
     p.add_argument("--out", type=pathlib.Path, default=pathlib.Path("rtgs_out"))
     p.add_argument("--format", choices=("png", "npy", "both"), default="png")
-    p.add_argument("--t-cut", type=float, default=1e-4, help="transmittance early-termination threshold (0 = off)")
+    p.add_argument("--t-cut", type=float, default=1e-4,
+                   help="transmittance early-termination threshold (0 = off, the reference's behaviour: it has no "
+                        "early-out; 1e-4 changes a pixel by < 1e-4)")
+    p.add_argument("--sh-layout", choices=("channel_major", "interleaved"), default="channel_major",
+                   help="how f_rest_* map to the SH triples (Scene.load_file): channel_major = the 3DGS file layout "
+                        "(default), interleaved = the flat reinterpretation the reference-run goldens contain")
     p.add_argument("--device", type=int, default=None)
     return p
 
@@ -99,7 +104,7 @@ def main(argv=None) -> int:
             logger.info("wrote %s", args.export_ply)
         scene.from_arrays(a["pos"], a["rot"], a["scale"], a["color"], a["opacity"], a["sh"])
     elif args.open is not None:
-        scene.load_file(args.open, args.scale)
+        scene.load_file(args.open, args.scale, sh_layout=args.sh_layout)
     else:
         print("rtgs: one of -o/--open or --synthetic is required", file=sys.stderr)
         return 2

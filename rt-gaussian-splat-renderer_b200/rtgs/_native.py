@@ -56,6 +56,12 @@ SIGNATURES = {
                               C.c_int32, C.c_float, C.c_int32, C.c_int32, _vp, _vp, _vp,
                               C.POINTER(rtgs_render_stats)]),
     "rtgs_scene_set_option": (C.c_int, [_vp, C.c_int32, C.c_int64]),
+    "rtgs_scene_get_option": (C.c_int, [_vp, C.c_int32, C.POINTER(C.c_int64)]),
+    "rtgs_scene_set_frame_sync": (C.c_int, [_vp, _vp, _vp, C.c_uint32]),
+    "rtgs_stream_wait_counter": (C.c_int, [C.c_int, _vp, C.c_uint32, _vp]),
+    "rtgs_stream_set_counter": (C.c_int, [C.c_int, _vp, C.c_uint32, _vp]),
+    "rtgs_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "rtgs_host_unregister": (C.c_int, [_vp]),
     "rtgs_scene_read_kernel_times": (C.c_int, [_vp, C.c_int32, _vp]),
     "rtgs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rtgs_host_free": (C.c_int, [_vp]),
@@ -74,8 +80,12 @@ SIGNATURES = {
     "rtgs_scene_destroy": (C.c_int, [_vp]),
 }
 
-OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING, OPT_STRIPE, OPT_MORTON_BITS = 0, 1, 2, 3, 4
-KERNEL_NAMES = ("k_tile_lists", "k_shade_tiles", "k_render")
+OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING, OPT_STRIPE, OPT_MORTON_BITS, OPT_TREE_DEPTH = 0, 1, 2, 3, 4, 5
+#: the (up to) three launches of a frame, by render mode (rtgs_scene_read_kernel_times); None = no launch
+KERNEL_NAMES_BY_MODE = {0: ("k_tile_lists", "k_shade_tiles", "k_render"),
+                        1: (None, None, "k_render"),
+                        2: (None, "k_frame", "k_render")}
+KERNEL_NAMES = KERNEL_NAMES_BY_MODE[0]
 
 _lib = None
 

@@ -88,14 +88,25 @@ class Scene:
 
         The activations are the reference's NumPy float32 expressions (scene.py:101-114) unless
         ``activate_on_device`` selects the fused CUDA ingest (rtgs_scene_create_from_ply_rows).
-        sh_layout: "channel_major" (sh_k[c] = f_rest_{15c+k}: the intent of ``reshape((-1,3,15))``,
-        scene.py:106-107) or "taichi_as_executed" (sh_k[c] = f_rest_{3k+c}); SURVEY.md §7 hard part 7.
+        sh_layout - how the 45 ``f_rest_*`` columns become the 15 RGB triples ``sh_10 .. sh_36``.  The reference
+        reshapes them to (N,3,15) and copies that array into an (N,15) field of vec3 without a transpose
+        (scene.py:106-107,122,127); what real Taichi 1.7.3 stores then cannot be established offline, so the
+        layouts are named for what they DO, not for what Taichi is believed to do:
+          "channel_major"  sh_k[c] = f_rest_{15c+k}: the standard 3DGS file layout, the evident intent of
+                           ``reshape((-1,3,15))``; the default here;
+          "interleaved"    sh_k[c] = f_rest_{3k+c}: the flat C-order reinterpretation of that (N,3,15) buffer as
+                           (N,15,3), which is what ``oracle/taichi_shim`` executes and therefore what the committed
+                           reference-run goldens contain.  (SURVEY.md §7 hard part 7 derives yet another candidate
+                           for real Taichi, flat[45i+15k+c] with out-of-row reads; none of the three is verified.)
+        ``"taichi_as_executed"`` is accepted as a deprecated alias of "interleaved".
         """
         path = pathlib.Path(path)
         cols = read_ply(path.resolve())
         num_points = len(cols["x"])
         logger.info(f"Point cloud loaded from {path} with {num_points} points.")
-        if sh_layout not in ("channel_major", "taichi_as_executed"):
+        if sh_layout == "taichi_as_executed":
+            sh_layout = "interleaved"
+        if sh_layout not in ("channel_major", "interleaved"):
             raise ValueError(sh_layout)
         if activate_on_device:
             return self._load_rows_on_device(cols, scale, sh_layout)
@@ -209,12 +220,38 @@ class Scene:
     def num_gaussians(self) -> int:
         return self._n
 
+    _OPTIONS = {"render_mode": _native.OPT_RENDER_MODE, "list_pool_chunks": _native.OPT_LIST_POOL_CHUNKS,
+                "kernel_timing": _native.OPT_KERNEL_TIMING, "stripe": _native.OPT_STRIPE,
+                "morton_bits": _native.OPT_MORTON_BITS, "tree_depth": _native.OPT_TREE_DEPTH}
+
     def set_option(self, name: str, value: int) -> "Scene":
-        """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 0 = tile lists + shading kernels (default),
-        1 = the fused kernel alone; ``list_pool_chunks`` = capacity of the candidate-list pool (-1 = default)."""
-        opt = {"render_mode": _native.OPT_RENDER_MODE, "list_pool_chunks": _native.OPT_LIST_POOL_CHUNKS,
-               "kernel_timing": _native.OPT_KERNEL_TIMING, "stripe": _native.OPT_STRIPE}[name]
-        _native.check(_native.load().rtgs_scene_set_option(self.handle, opt, int(value)))
+        """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 2 = the whole frame in one launch (k_frame,
+        default), 0 = tile lists + shading as separate kernels, 1 = the fused kernel alone; ``list_pool_chunks`` =
+        capacity of the candidate-list pool (-1 = default)."""
+        _native.check(_native.load().rtgs_scene_set_option(self.handle, self._OPTIONS[name], int(value)))
+        return self
+
+    def get_option(self, name: str) -> int:
+        """Current value of an option (rtgs_scene_get_option); ``tree_depth`` (read-only) is the depth of the
+        deepest LBVH leaf."""
+        v = C.c_int64()
+        _native.check(_native.load().rtgs_scene_get_option(self.handle, self._OPTIONS[name], C.byref(v)))
+        return int(v.value)
+
+    @property
+    def render_mode(self) -> int:
+        return self.get_option("render_mode")
+
+    @property
+    def kernel_names(self):
+        """Names of the frame's (up to) three launches in the current render mode (None = no launch)."""
+        return _native.KERNEL_NAMES_BY_MODE[self.render_mode]
+
+    def set_frame_sync(self, arrive: int = 0, grant: int = 0, grant_value: int = 0) -> "Scene":
+        """Multi-GPU hand-over of the NEXT frame (rtgs_scene_set_frame_sync): device addresses of 32-bit counters,
+        0 = none.  Used by ``rtgs.sharding.PeerFrame``."""
+        _native.check(_native.load().rtgs_scene_set_frame_sync(self.handle, arrive or None, grant or None,
+                                                               int(grant_value) & 0xffffffff))
         return self
 
     def set_stripe(self, world: int = 1, rank: int = 0) -> "Scene":
@@ -223,7 +260,7 @@ class Scene:
         return self.set_option("stripe", (int(world) << 32) | int(rank))
 
     def read_kernel_times(self, frames: int):
-        """(frames, 3) float32 milliseconds of k_tile_lists, k_shade_tiles, k_render for the last `frames` renders
+        """(frames, 3) float32 milliseconds of the frame's launches (``kernel_names``) for the last `frames` renders
         (needs ``set_option("kernel_timing", n)`` with n >= frames beforehand).  Synchronises the device."""
         out = np.zeros((int(frames), len(_native.KERNEL_NAMES)), np.float32)
         _native.check(_native.load().rtgs_scene_read_kernel_times(self.handle, int(frames), out.ctypes.data))

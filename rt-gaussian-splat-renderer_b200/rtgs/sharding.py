@@ -98,31 +98,51 @@ class StripeGather:
 
 
 class PeerFrame:
-    """One (W,H,3) float32 framebuffer in rank 0's device memory that every rank's render kernels store their
-    stripes into directly over NVLink (CUDA IPC + peer access).  ``tensor`` is a torch view of that
-    memory on the local device: pass it as ``out`` of a full-frame ``RayTracer.render_device`` after
-    ``Scene.set_stripe(world, rank)``.  ``finish(dist)`` is a stream-ordered barrier: once it has completed on
-    rank 0's stream, every rank's stores have landed (a kernel's stores are performed when it completes)."""
+    """Framebuffers in rank 0's device memory that every rank's render kernels store into directly over NVLink
+    (CUDA IPC + peer access), handed over with two device-side counters - no collective, no host
+    synchronisation, no extra kernel on the producing ranks:
+
+    * ``slots`` images of (W,H,3) float32 per buffer: 1 for tile sharding (every rank stores its stripes of the one
+      frame, ``Scene.set_stripe(world, rank)``), ``world`` for view sharding (rank r stores its whole frame into
+      slot r), ``buffers`` deep so that the producers may run ahead of the consumer;
+    * ``arrive[b]``: the last CTA of a rank's frame increments it once all the frame's stores are performed
+      (release, system scope; csrc/render_common.cuh: frame_complete).  Rank 0 waits on its stream until the buffer
+      has ``world`` arrivals per use (``wait()``: a one-thread kernel, rtgs_stream_wait_counter);
+    * ``consumed``: rank 0 stores the number of frames it has finished with (``release()``); a producer's warps
+      check it before their first store into a buffer that is being reused (RenderParams::grant).
+
+    Per frame, every rank calls ``begin()`` (returns the tensor to pass as ``out`` of a full-frame
+    ``RayTracer.render_device``) and renders; rank 0 then calls ``wait()``, consumes ``frame()`` on the same
+    stream and calls ``release()``."""
 
     class _Raw:
         def __init__(self, ptr, shape):
             self.__cuda_array_interface__ = {"shape": shape, "typestr": "<f4", "data": (int(ptr), False), "version": 3}
 
-    def __init__(self, W: int, H: int, rank: int, world: int, device: int, dist=None):
+    CTRL_BYTES = 1024   # arrive[b] at 128 b, consumed at 128 * buffers
+
+    def __init__(self, W: int, H: int, rank: int, world: int, device: int, dist=None, slots: int = 1,
+                 buffers: int = 2):
         import ctypes as C
 
         import torch
 
         from . import _native
         lib = _native.load()
+        assert 1 <= buffers <= 4 and slots >= 1
         self.rank, self.world, self.device = rank, world, device
+        self.W, self.H, self.slots, self.buffers = W, H, slots, buffers
         self._lib, self._owner_ptr, self._peer_ptr = lib, None, None
-        nbytes = W * H * 3 * 4
+        self.image_bytes = W * H * 3 * 4
+        nbytes = self.CTRL_BYTES + buffers * slots * self.image_bytes
         handle = torch.zeros(64, dtype=torch.uint8)
         p = C.c_void_p()
         if rank == 0:
             _native.check(lib.rtgs_device_alloc(device, nbytes, C.byref(p)))
             self._owner_ptr = p.value
+            ctrl = torch.as_tensor(PeerFrame._Raw(p.value, (self.CTRL_BYTES // 4,)), device=torch.device("cuda", device))
+            ctrl.zero_()
+            torch.cuda.synchronize(device)
             buf = (C.c_ubyte * 64)()
             _native.check(lib.rtgs_ipc_export(device, p, buf))
             handle = torch.tensor(list(buf), dtype=torch.uint8)
@@ -134,15 +154,59 @@ class PeerFrame:
             buf = (C.c_ubyte * 64)(*handle.tolist())
             _native.check(lib.rtgs_ipc_open(device, buf, C.byref(p)))
             self._peer_ptr = p.value
-        self.tensor = torch.as_tensor(PeerFrame._Raw(p.value, (W, H, 3)), device=torch.device("cuda", device))
-        self._token = torch.zeros(1, device=torch.device("cuda", device))
+        self.base = p.value
+        dev = torch.device("cuda", device)
+        self._images = [[torch.as_tensor(PeerFrame._Raw(self.base + self.CTRL_BYTES + (b * slots + k) * self.image_bytes,
+                                                        (W, H, 3)), device=dev) for k in range(slots)]
+                        for b in range(buffers)]
+        self.frames = 0          # frames begun on this rank
+        self.released = 0        # rank 0: frames released
 
-    def finish(self, dist):
-        if self.world > 1:
-            dist.all_reduce(self._token)      # stream-ordered, no host synchronisation
+    # -- addresses of the counters (device pointers valid on this rank)
+    def _arrive(self, b):
+        return self.base + 128 * b
+
+    @property
+    def _consumed(self):
+        return self.base + 128 * self.buffers
+
+    def begin(self, scene, slot: int = 0):
+        """Start this rank's next frame: arm the scene's hand-over counters and return the (W,H,3) tensor to render
+        into (rank 0's memory, peer-mapped here)."""
+        self.frames += 1
+        f = self.frames
+        b = f % self.buffers
+        scene.set_frame_sync(arrive=self._arrive(b), grant=self._consumed if f > self.buffers else 0,
+                             grant_value=f - self.buffers)
+        return self._images[b][slot]
+
+    def frame(self, slot: int = 0):
+        """The tensor of the frame begun last (on rank 0: complete after ``wait()``)."""
+        return self._images[self.frames % self.buffers][slot]
+
+    def wait(self, stream=None):
+        """Rank 0: make `stream` (default: torch's current stream) wait until every rank's part of the frame begun
+        last has landed."""
+        import torch
+        assert self.rank == 0
+        f = self.frames
+        b = f % self.buffers
+        uses = len(range(b if b else self.buffers, f + 1, self.buffers))   # frames that have used buffer b, this one included
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        from . import _native
+        _native.check(self._lib.rtgs_stream_wait_counter(self.device, self._arrive(b), self.world * uses, st))
+
+    def release(self, stream=None):
+        """Rank 0: the consumer is done with the frame begun last (stream-ordered)."""
+        import torch
+        assert self.rank == 0
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        from . import _native
+        self.released = self.frames
+        _native.check(self._lib.rtgs_stream_set_counter(self.device, self._consumed, self.released, st))
 
     def close(self):
-        self.tensor = None
+        self._images = None
         if self._peer_ptr:
             self._lib.rtgs_ipc_close(self.device, self._peer_ptr)
             self._peer_ptr = None

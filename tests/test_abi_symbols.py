@@ -27,7 +27,7 @@ def test_library_exports_every_declared_symbol(lib):
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/rtgs_b200.h but not exported"
     assert sorted(_native.SIGNATURES) == names, "ctypes SIGNATURES out of sync with the header"
-    assert lib.rtgs_abi_version() == 2
+    assert lib.rtgs_abi_version() == 3
 
 
 def test_errors_are_reported_not_thrown(lib):

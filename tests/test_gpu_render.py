@@ -164,7 +164,10 @@ def test_extreme_shapes_needles_pancakes_and_screen_filling_gaussians():
         scene.set_option("render_mode", 1)
         fused, _ = _render(scene, cam)
         scene.set_option("render_mode", 0)
+        split, _ = _render(scene, cam)
+        scene.set_option("render_mode", 2)
         assert np.abs(fused - img).max() <= 1e-5
+        assert np.array_equal(split, img)      # the frame kernel and the two separate launches run the same code per tile
 
 
 def test_stripe_sharding_is_bit_identical():
@@ -199,7 +202,8 @@ def test_stripe_sharding_is_bit_identical():
 def test_peer_frame_owner_side():
     """PeerFrame on the owning rank: the library-allocated image is exportable (CUDA IPC handle) and a render into
     its torch view equals the ordinary render.  (Opening the handle needs a second process and GPU: that path is
-    exercised by `bench.py --gpus N --sharding tiles`.)"""
+    exercised by `bench.py --gpus N`.)  The hand-over counters work on one GPU as well: every frame signals `arrive`
+    from its last CTA, a stream-ordered wait kernel sees it, `release` feeds the producers' grant."""
     import ctypes as C
     import torch
     from rtgs import _native
@@ -210,13 +214,26 @@ def test_peer_frame_owner_side():
     cam, _ = make_camera(0.5, 1.2, 2.4, 96, 64)
     rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
     want = rt.render_device(16).clone()
-    pf = PeerFrame(96, 64, 0, 1, torch.cuda.current_device())
+    dev = torch.cuda.current_device()
+    pf = PeerFrame(96, 64, 0, 1, dev, buffers=2)
     buf = (C.c_ubyte * 64)()
-    _native.check(_native.load().rtgs_ipc_export(torch.cuda.current_device(), C.c_void_p(pf.tensor.data_ptr()), buf))
+    _native.check(_native.load().rtgs_ipc_export(dev, C.c_void_p(pf.base), buf))
     assert any(buf)
-    rt.render_device(16, out=pf.tensor)
-    pf.finish(None)
-    assert torch.equal(pf.tensor, want)
+    ctrl = torch.as_tensor(PeerFrame._Raw(pf.base, (PeerFrame.CTRL_BYTES // 4,)), device=torch.device("cuda", dev)).view(torch.int32)
+    for mode in (2, 0, 1):
+        scene.set_option("render_mode", mode)
+        for _ in range(5):                          # more frames than buffers: arrive / wait / release / grant cycle
+            out = pf.begin(scene)
+            rt.render_device(16, out=out)
+            pf.wait()                               # a one-thread kernel that spins until the frame's last CTA has signalled
+            assert torch.equal(pf.frame(), want)
+            pf.release()
+    torch.cuda.synchronize()
+    frames = pf.frames
+    assert frames == 15
+    arrive = [int(ctrl[32 * b]) for b in range(2)]
+    assert sum(arrive) == frames and int(ctrl[32 * 2]) == frames, (arrive, int(ctrl[64]))
+    scene.set_option("render_mode", 2)
     pf.close()
 
 
@@ -233,24 +250,29 @@ def test_render_paths_agree_and_pool_overflow_falls_back():
     a = rt.render(16)
     rt.render_device(16, collect_stats=True)
     assert rt.last_stats["fallback_tiles"] == 0
+    a = a.copy()
     scene.set_option("render_mode", 1)
-    b = rt.render(16)
-    scene.set_option("render_mode", 0)
-    scene.set_option("list_pool_chunks", 48)       # 3 slabs of 16 chunks for ~850 tiles
-    c = rt.render(16)
-    rt.render_device(16, collect_stats=True)
-    st = rt.last_stats
-    assert 0 < st["fallback_tiles"] <= st["tiles"]
-    assert st["rays"] == 200 * 136
-    scene.set_option("list_pool_chunks", 0)        # no pool at all: every non-empty tile falls back
-    d = rt.render(16)
-    scene.set_option("list_pool_chunks", -1)
-    e = rt.render(16)
-    for name, img in (("lists", a), ("fused", b), ("small pool", c), ("no pool", d)):
+    b = rt.render(16).copy()
+    imgs = [("frame kernel", a), ("fused", b)]
+    for mode in (2, 0):                            # one launch (fallback tiles: device-side tail launch) / three launches
+        scene.set_option("render_mode", mode)
+        scene.set_option("list_pool_chunks", 48)       # 3 slabs of 16 chunks for ~850 tiles
+        c = rt.render(16).copy()
+        rt.render_device(16, collect_stats=True)
+        st = rt.last_stats
+        assert 0 < st["fallback_tiles"] <= st["tiles"]
+        assert st["rays"] == 200 * 136
+        scene.set_option("list_pool_chunks", 0)        # no pool at all: every non-empty tile falls back
+        d = rt.render(16).copy()
+        scene.set_option("list_pool_chunks", -1)
+        e = rt.render(16).copy()
+        imgs += [(f"small pool (mode {mode})", c), (f"no pool (mode {mode})", d)]
+        assert np.array_equal(a, e), mode
+    scene.set_option("render_mode", 2)
+    for name, img in imgs:
         mx, ps, _ = compare(img, ref, TOL)
         print(f"{name}: max-abs={mx:.2e} psnr={ps:.1f}")
         assert mx <= TOL and ps >= 60.0, name
-    assert np.array_equal(a, e)
 
 
 def test_early_termination_bound():
@@ -295,7 +317,7 @@ def test_sample_state_machine():
 
 def test_overflowing_groups_take_the_pruning_kernel():
     """A wall of large splats: every 8x16-pixel group frustum holds more candidates than its shared-memory list, so
-    k_tile_lists hands the tiles to k_render, which traverses near first and prunes by distance once the hit buffers
+    the traversal (lists_group) hands the tiles to k_render, which traverses near first and prunes by distance once the hit buffers
     are full (most Gaussians of the wall are never tested).  Image within tolerance of the brute-force oracle for
     depth 16 and 32, default route and fused-only route."""
     rng = np.random.default_rng(77)
@@ -310,16 +332,16 @@ def test_overflowing_groups_take_the_pruning_kernel():
     for depth in (16, 32):
         ref = O.render(gs, ocam, depth=depth)
         assert np.minimum(ref["nhit"], depth).mean() > 0.9 * depth      # the buffers do fill
-        for mode in (0, 1):
+        for mode in (2, 0, 1):
             scene.set_option("render_mode", mode)
             img = rt.render(depth).copy()
             mx, ps, bad = compare(img, ref["rgb"], TOL)
             assert mx <= TOL and ps >= 60.0, (depth, mode, mx, ps)
             rt.render_device(depth, collect_stats=True)
             st = rt.last_stats
-            if mode == 0 and depth == 16:
+            if mode != 1 and depth == 16:
                 assert st["fallback_tiles"] > 0.5 * (96 // 4) * (64 // 8)      # the groups overflowed
-    scene.set_option("render_mode", 0)
+    scene.set_option("render_mode", 2)
 
 
 def test_pipelined_sweep_is_bit_identical_to_synchronous_renders():
@@ -401,6 +423,6 @@ def test_device_ply_ingest_matches_host_loader(test_ply):
     for k in ("scale", "color", "opacity"):
         assert np.allclose(a[k], b[k], rtol=3e-7, atol=0), k       # expf vs numpy exp: <= 2 ulp
     assert np.array_equal(a["sh"], b["sh"])
-    c = Scene().load_file(test_ply, 30.0, sh_layout="taichi_as_executed", activate_on_device=True).read_gaussians()
-    d = Scene().load_file(test_ply, 30.0, sh_layout="taichi_as_executed").read_gaussians()
+    c = Scene().load_file(test_ply, 30.0, sh_layout="interleaved", activate_on_device=True).read_gaussians()
+    d = Scene().load_file(test_ply, 30.0, sh_layout="interleaved").read_gaussians()
     assert np.array_equal(c["sh"], d["sh"])

@@ -131,7 +131,7 @@ def test_activation_of_test_ply(test_ply):
     assert np.allclose(np.linalg.norm(a["rot"], axis=1), 1, atol=1e-6)
     assert np.allclose(a["scale"], np.exp(np.stack([cols[f"scale_{i}"] for i in range(3)], -1)) * 30, rtol=1e-6)
     assert np.array_equal(a["sh"][:, 2, 1], cols["f_rest_17"])          # channel-major: sh_k[c] = f_rest_{15c+k}
-    b = O.activate(cols, scale=30.0, sh_layout="taichi_as_executed")
+    b = O.activate(cols, scale=30.0, sh_layout="interleaved")
     assert np.array_equal(b["sh"][:, 2, 1], cols["f_rest_7"])           # flat[3k + c]
 
 
