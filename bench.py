@@ -75,11 +75,24 @@ def parse_args():
     return ap.parse_args()
 
 
-def make_views(W, H):
+def make_views(W, H, n_views=N_VIEWS, phi=np.pi / 2):
     from rtgs.orbit import focal_from_fov, orbit_pose
     from rtgs.synthetic import FOV_DEG, ORBIT_R
     f = focal_from_fov(H, FOV_DEG)
-    return f, [orbit_pose(2 * np.pi * k / N_VIEWS, np.pi / 2, ORBIT_R) for k in range(N_VIEWS)]
+    return f, [orbit_pose(2 * np.pi * k / n_views, phi, ORBIT_R) for k in range(n_views)]
+
+
+def load_config(name, h_target=None):
+    """(arrays, n, seed, sh_degree, (W, H), n_views, phi, description) of a bench configuration."""
+    from rtgs.synthetic import CONFIGS, SURFACE_CONFIGS, make_scene, make_surface_scene
+    if name in SURFACE_CONFIGS:
+        n, seed, res, nv, phi = SURFACE_CONFIGS[name]
+        return (make_surface_scene(n, seed), n, seed, 3, res, nv, phi,
+                f"synthetic {n} Gaussians on surfaces (6 shells + a floor, flat splats, log-normal sizes sigma 1, 40 huge "
+                f"translucent blobs, 6 stray points 800 radii out), SH degree 3, seed {seed}")
+    n, seed, deg, res = CONFIGS[name]
+    arrays = make_scene(n, seed, deg) if h_target is None else make_scene(n, seed, deg, h_target)
+    return arrays, n, seed, deg, res, N_VIEWS, np.pi / 2, f"synthetic {n} random Gaussians, SH degree {deg}, seed {seed}"
 
 
 class ClockSampler:
@@ -169,7 +182,7 @@ def cpu_leg(cfg_name, scene_arrays, W, H, focal, views, steps, warmup, stride):
     pix = ref_cpu.all_pixels(W, H, stride)
     times = []
     for s in range(warmup + steps):
-        pos, rot = views[s % N_VIEWS]
+        pos, rot = views[s % len(views)]
         cam = O.CameraParams(np.asarray(pos), np.asarray(rot), W, H, (focal, focal))
         t0 = time.perf_counter()
         cs.render(cam, DEPTH, pixels=pix, precision="float", threads=threads)
@@ -388,9 +401,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
     from rtgs.synthetic import CONFIGS, make_scene
-    n_g, seed, sh_deg, (W, H) = CONFIGS[args.config]
-    config = {"workload": f"synthetic {n_g} random Gaussians, SH degree {sh_deg}, seed {seed}, {W}x{H}, fov 60, "
-                          f"orbit r=2.2, depth {DEPTH}, t_cut {T_CUT}; 64-view orbit, view (step*N+rank)%64",
+    arrays, n_g, seed, sh_deg, (W, H), n_views, orbit_phi, what = load_config(args.config, args.h_target)
+    config = {"workload": f"{what}, {W}x{H}, fov 60, orbit r=2.2, depth {DEPTH}, t_cut {T_CUT}; "
+                          f"{n_views}-view orbit, view (step*N+rank)%{n_views}",
               "gaussians": n_g, "sh_degree": sh_deg, "resolution": [W, H], "depth": DEPTH,
               "sharding": "camera views (scene replicated, no collective; at N > 1 every rank's kernels store their "
                           "frame into GPU 0's memory over NVLink and GPU 0 waits for the arrival counters)",
@@ -400,8 +413,7 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        arrays = make_scene(n_g, seed, sh_deg)
-        focal, views = make_views(W, H)
+        focal, views = make_views(W, H, n_views, orbit_phi)
         # bounded sample: every 4th column and row (1/16 of the rays) keeps 100 steps within ~1 minute of CPU time
         stride = args.cpu_stride or (4 if W * H <= 1920 * 1080 else 8)
         r = cpu_leg(args.config, arrays, W, H, focal, views, args.steps, args.warmup, stride)
@@ -431,7 +443,6 @@ def main():
     from rtgs.ray_tracer import RayTracer
     from rtgs.scene import Scene
 
-    arrays = make_scene(n_g, seed, sh_deg) if args.h_target is None else make_scene(n_g, seed, sh_deg, args.h_target)
     if args.h_target is not None:
         config["workload"] += f" [diagnostic: h_target {args.h_target}]"
     if args.outliers > 0:
@@ -440,7 +451,7 @@ def main():
         config["workload"] += f" [diagnostic: {args.outliers} outliers at ~4000 scene radii]"
     if args.morton_bits == 63:
         config["workload"] += " [LBVH with 63-bit Morton codes]"
-    focal, views = make_views(W, H)
+    focal, views = make_views(W, H, n_views, orbit_phi)
     t0 = time.perf_counter()
     scene = Scene(device=local_rank, morton_bits=args.morton_bits or "auto").from_arrays(
         arrays["pos"], arrays["rot"], arrays["scale"], arrays["color"], arrays["opacity"], arrays["sh"])
@@ -462,7 +473,7 @@ def main():
         peer = PeerFrame(W, H, rank, world, local_rank, dist, slots=world, buffers=2)
 
     def set_view(step):
-        v = (step * world + rank) % N_VIEWS
+        v = (step * world + rank) % n_views
         cam.position, cam.rotation = views[v]
         return v
 
@@ -482,7 +493,7 @@ def main():
 
     # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views (whole frames)
     agg = {}
-    for s in range(min(args.steps, N_VIEWS)):
+    for s in range(min(args.steps, n_views)):
         set_view(s)
         rt.render_device(DEPTH, out=out, collect_stats=True)
         for k, v in rt.last_stats.items():
@@ -504,7 +515,7 @@ def main():
             got = [peer.frame(r).clone() for r in range(world)]
             gathered_ok = True
             for r in range(world):
-                cam.position, cam.rotation = views[r % N_VIEWS]
+                cam.position, cam.rotation = views[r % n_views]
                 gathered_ok = gathered_ok and bool(torch.equal(rt.render_device(DEPTH, out=out), got[r]))
             torch.cuda.synchronize()
         barrier()

@@ -139,11 +139,13 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam,
                 float* out_rgb, float* out_T, void* stream, rtgs_render_stats* stats);
 
 /* Tuning knobs of one scene's render path (no reference counterpart; defaults need no call).
- *  RTGS_OPT_RENDER_MODE      2 (default): k_frame - traversal and shading of the frame in ONE launch (persistent
- *                            warps alternate between the two; the fused kernel is tail-launched from the device
- *                            only when some tile's candidate list did not fit the pool); 0: the same code as
- *                            separate launches k_tile_lists + k_shade_tiles + k_render; 1: the fused kernel
- *                            alone.  depth > 16 always uses the fused kernel.
+ *  RTGS_OPT_RENDER_MODE      0 (default): k_tile_lists (traversal, one candidate list per 4x8-pixel tile) +
+ *                            k_shade_tiles (intersection, k-buffer, compositing) + the fused kernel k_render for the
+ *                            tiles whose list did not fit the pool; 2: k_frame - the same traversal and shading
+ *                            code in ONE launch (persistent warps alternate between the two; lowest latency for
+ *                            a single frame that is spread over four or more GPUs); 1: the fused kernel alone.
+ *                            depth > 16 always uses the fused kernel.  Frames launched alternately on two streams
+ *                            use separate scratch and overlap on the device in every mode.
  *  RTGS_OPT_LIST_POOL_CHUNKS capacity of the candidate-list pool in 128-byte chunks (31 candidates each);
  *                            -1 (default) = 16 chunks per 4x8-pixel tile of the rendered region, doubled whenever a
  *                            finished frame used more than 70 % of it.  A small pool is

@@ -486,12 +486,12 @@ int rtgs_scene_get_option(const rtgs_scene* s, int32_t option, int64_t* value) {
     RTGS_CHECK_ARG(s != nullptr && value != nullptr);
     switch (option) {
         case RTGS_OPT_RENDER_MODE: {
-            // the mode a depth <= 16 frame renders in: the per-scene option, else RTGS_RENDER_MODE, else 2
+            // the mode a depth <= 16 frame renders in: the per-scene option, else RTGS_RENDER_MODE, else 0
             int m = s->opt_render_mode;
             if (m < 0) {
                 const char* e = getenv("RTGS_RENDER_MODE");
-                m = e ? atoi(e) : 2;
-                if (m < 0 || m > 2) m = 2;
+                m = e ? atoi(e) : 0;
+                if (m < 0 || m > 2) m = 0;
             }
             *value = m;
             return RTGS_OK;

@@ -471,15 +471,16 @@ int launch_frame(rtgs_scene* s, RenderParams& P, cudaStream_t stream) {
     return RTGS_OK;
 }
 
-// Which kernels render a frame: 2 (default) = k_frame, one launch; 0 = k_tile_lists + k_shade_tiles + k_render on
-// the fallback list; 1 = the fused k_render alone.  depth > 16 always takes the fused kernel (32-entry k-buffer).
+// Which kernels render a frame: 0 (default) = k_tile_lists + k_shade_tiles + k_render on the fallback list; 2 =
+// k_frame, one launch (lowest latency of a single frame that is spread over >= 4 GPUs); 1 = the fused k_render
+// alone.  depth > 16 always takes the fused kernel (32-entry k-buffer).
 int render_mode(const rtgs_scene* s) {
     if (s->opt_render_mode >= 0) return s->opt_render_mode;
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("RTGS_RENDER_MODE");
-        mode = e ? atoi(e) : 2;
-        if (mode < 0 || mode > 2) mode = 2;
+        mode = e ? atoi(e) : 0;
+        if (mode < 0 || mode > 2) mode = 0;
     }
     return mode;
 }

@@ -225,9 +225,9 @@ class Scene:
                 "morton_bits": _native.OPT_MORTON_BITS, "tree_depth": _native.OPT_TREE_DEPTH}
 
     def set_option(self, name: str, value: int) -> "Scene":
-        """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 2 = the whole frame in one launch (k_frame,
-        default), 0 = tile lists + shading as separate kernels, 1 = the fused kernel alone; ``list_pool_chunks`` =
-        capacity of the candidate-list pool (-1 = default)."""
+        """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 0 = tile lists + shading kernels (default),
+        2 = the whole frame in one launch (k_frame), 1 = the fused kernel alone; ``list_pool_chunks`` = capacity of
+        the candidate-list pool (-1 = default)."""
         _native.check(_native.load().rtgs_scene_set_option(self.handle, self._OPTIONS[name], int(value)))
         return self
 

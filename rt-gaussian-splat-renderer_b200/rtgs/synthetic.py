@@ -19,6 +19,12 @@ CONFIGS = {
     "1m_deg0_1080p": (1_000_000, 1002, 0, (1920, 1080)),   # same geometry without SH (diagnostic)
     "3m_deg3_2160p": (3_000_000, 1003, 3, (3840, 2160)),
 }
+# Scenes shaped like a trained capture rather than a uniform cloud (the reference's own target
+# workload is truck.ply, docs/source/get-started.md:64-74): see make_surface_scene.
+SURFACE_CONFIGS = {
+    # name: (N, seed, (W, H), orbit views, orbit phi)
+    "surface_1m_1080p": (1_000_000, 4242, (1920, 1080), 16, float(np.pi / 2 - 0.3)),
+}
 ORBIT_R = 2.2
 FOV_DEG = 60.0
 H_TARGET = 16.0
@@ -68,3 +74,37 @@ def export_ply(path, arrays: dict) -> None:
         for i in range(45):
             cols[f"f_rest_{i}"] = rest[:, i]
     write_gs_ply(path, cols)
+
+
+def make_surface_scene(n: int, seed: int = 4242) -> dict:
+    """Gaussians on SURFACES - six spherical shells and a floor - flat (one axis 10x thinner), with heavy-tailed sizes
+    (log-normal, sigma 1), forty huge translucent blobs and six stray points 800 scene radii out: the features of a
+    trained 3DGS capture that a uniform cloud lacks (tiles that look along the floor hold thousands of splats; the
+    stray points defeat 10-bit-per-axis Morton codes).  SH degree 3.  Post-activation arrays like ``make_scene``."""
+    f32 = np.float32
+    rng = np.random.default_rng(seed)
+    pos = np.empty((n, 3), f32)
+    k = rng.integers(0, 7, n)
+    c = rng.uniform(-0.6, 0.6, (6, 3))
+    r = rng.uniform(0.15, 0.45, 6)
+    u = rng.normal(size=(n, 3))
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    shell = k < 6
+    pos[shell] = (c[k[shell]] + r[k[shell], None] * u[shell] * (1 + 0.01 * rng.normal(size=(shell.sum(), 1)))).astype(f32)
+    pos[~shell] = np.stack([rng.uniform(-1, 1, (~shell).sum()), rng.uniform(-1, 1, (~shell).sum()),
+                            -0.8 + 0.005 * rng.normal(size=(~shell).sum())], axis=1).astype(f32)
+    quat = rng.normal(size=(n, 4))
+    quat /= np.linalg.norm(quat, axis=1, keepdims=True)
+    base = 2.0 * np.sqrt(16.0 / (3 * np.pi * n)) * 2.0
+    ls = rng.normal(np.log(base), 1.0, (n, 3))            # heavy tail (sigma 1.0 instead of 0.5)
+    ls[:, 2] -= np.log(10.0)                               # flat splats
+    scale = np.exp(ls).astype(f32)
+    big = rng.choice(n, 40, replace=False)
+    scale[big] = rng.uniform(0.2, 0.6, (40, 3)).astype(f32)   # huge blobs
+    stray = rng.choice(n, 6, replace=False)
+    pos[stray] = (rng.uniform(-1, 1, (6, 3)) * 800.0).astype(f32)
+    opacity = (1 / (1 + np.exp(-rng.normal(0.5, 2.0, n)))).astype(f32)
+    opacity[big] = 0.05
+    color = (1 / (1 + np.exp(-rng.normal(0, 1, (n, 3))))).astype(f32)
+    sh = rng.normal(0, 0.15, (n, 15, 3)).astype(f32)
+    return dict(pos=pos, rot=quat.astype(f32), scale=scale, color=color, opacity=opacity, sh=sh)

@@ -45,7 +45,7 @@ def test_sixteen_thousand_coincident_centres_render_and_hit():
         mx, ps, bad = compare(img, ref["rgb"], TOL)
         print(f"mode {mode}: max-abs {mx:.2e} psnr {ps:.1f}")
         assert mx <= TOL and ps >= 60.0, mode
-    scene.set_option("render_mode", 2)
+    scene.set_option("render_mode", 0)
     # closest hit through the same deep tree (k_trace_closest: per-ray stack of depth + 2 entries)
     rays = cam.cam_ray_field.to_numpy().reshape(-1, 8)[::7]
     hit = scene.hit(rays)

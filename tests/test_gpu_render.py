@@ -163,11 +163,11 @@ def test_extreme_shapes_needles_pancakes_and_screen_filling_gaussians():
         assert mx <= TOL and ps >= 60.0
         scene.set_option("render_mode", 1)
         fused, _ = _render(scene, cam)
-        scene.set_option("render_mode", 0)
-        split, _ = _render(scene, cam)
         scene.set_option("render_mode", 2)
+        one, _ = _render(scene, cam)
+        scene.set_option("render_mode", 0)
         assert np.abs(fused - img).max() <= 1e-5
-        assert np.array_equal(split, img)      # the frame kernel and the two separate launches run the same code per tile
+        assert np.array_equal(one, img)        # the frame kernel and the two separate launches run the same code per tile
 
 
 def test_stripe_sharding_is_bit_identical():
@@ -233,7 +233,7 @@ def test_peer_frame_owner_side():
     assert frames == 15
     arrive = [int(ctrl[32 * b]) for b in range(2)]
     assert sum(arrive) == frames and int(ctrl[32 * 2]) == frames, (arrive, int(ctrl[64]))
-    scene.set_option("render_mode", 2)
+    scene.set_option("render_mode", 0)
     pf.close()
 
 
@@ -253,8 +253,8 @@ def test_render_paths_agree_and_pool_overflow_falls_back():
     a = a.copy()
     scene.set_option("render_mode", 1)
     b = rt.render(16).copy()
-    imgs = [("frame kernel", a), ("fused", b)]
-    for mode in (2, 0):                            # one launch (fallback tiles: device-side tail launch) / three launches
+    imgs = [("lists + shading", a), ("fused", b)]
+    for mode in (0, 2):                            # one launch (fallback tiles: device-side tail launch) / three launches
         scene.set_option("render_mode", mode)
         scene.set_option("list_pool_chunks", 48)       # 3 slabs of 16 chunks for ~850 tiles
         c = rt.render(16).copy()
@@ -268,7 +268,7 @@ def test_render_paths_agree_and_pool_overflow_falls_back():
         e = rt.render(16).copy()
         imgs += [(f"small pool (mode {mode})", c), (f"no pool (mode {mode})", d)]
         assert np.array_equal(a, e), mode
-    scene.set_option("render_mode", 2)
+    scene.set_option("render_mode", 0)
     for name, img in imgs:
         mx, ps, _ = compare(img, ref, TOL)
         print(f"{name}: max-abs={mx:.2e} psnr={ps:.1f}")
@@ -341,7 +341,7 @@ def test_overflowing_groups_take_the_pruning_kernel():
             st = rt.last_stats
             if mode != 1 and depth == 16:
                 assert st["fallback_tiles"] > 0.5 * (96 // 4) * (64 // 8)      # the groups overflowed
-    scene.set_option("render_mode", 2)
+    scene.set_option("render_mode", 0)
 
 
 def test_pipelined_sweep_is_bit_identical_to_synchronous_renders():
