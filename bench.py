@@ -340,30 +340,54 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
         scene.set_stripe(world, rank)
     barrier()
 
-    # ---- end to end: every frame delivered to pinned host memory on rank 0 (one DMA of the gathered frame)
-    host = [torch.empty((W, H, 3), dtype=torch.float32, pin_memory=True) for _ in range(2)] if rank == 0 else None
+    # ---- end to end: every frame delivered to HOST memory.  Each rank copies its own stripes into one shared,
+    # page-locked host image over its own PCIe link (rtgs.sharding.HostFrame); rank 0's host thread collects every
+    # frame inside the timed region.  Nothing is gathered on a device, no collective.
+    from rtgs.sharding import HostFrame
+    hf = HostFrame(W, H, rank, world, local_rank, dist, buffers=3)
+    dev = [torch.empty((W, H, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
 
-    def e2e_step(s, _):
-        rt.render_device(DEPTH, out=peer.begin(scene))
+    def e2e_loop(n):
+        last = None
+        for s in range(n):
+            set_view(s)
+            with ts.stream(s):
+                rt.render_device(DEPTH, out=dev[s % 2])
+                hf.deliver(dev[s % 2])
+            if rank == 0 and s >= 1:
+                last = hf.wait()
+                hf.release()
         if rank == 0:
-            peer.wait()
-            host[s % 2].copy_(peer.frame(), non_blocking=True)
-            peer.release()
+            last = hf.wait()
+            hf.release()
+        return last
 
-    for s in range(2):
-        set_view(s)
-        e2e_step(s, None)
+    e2e_loop(3)
     torch.cuda.synchronize()
     barrier()
     t0 = time.perf_counter()
-    for s in range(steps):
-        set_view(s)
-        with ts.stream(s):
-            e2e_step(s, None)
+    e2e_loop(steps)
     torch.cuda.synchronize()
     barrier()
     e2e_ms = 1e3 * (time.perf_counter() - t0) / steps
     (e2e_ms,) = allmax(dist, torch, [e2e_ms])
+    # untimed check of the host path: one frame through it == rank 0's own full render
+    host_verified = None
+    set_view(0)
+    rt.render_device(DEPTH, out=dev[0])
+    hf.deliver(dev[0])
+    if rank == 0:
+        got = np.array(hf.wait(), copy=True)
+        hf.release()
+        scene.set_stripe()
+        set_view(0)
+        full = rt.render_device(DEPTH, out=out_local)
+        torch.cuda.synchronize()
+        host_verified = bool(np.array_equal(full.cpu().numpy(), got))
+        scene.set_stripe(world, rank)
+    torch.cuda.synchronize()
+    barrier()
+    hf.close()
     scene.set_stripe()
     scene.set_option("render_mode", modes[0])
     peer.close()
@@ -389,7 +413,9 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
            "single_gpu_by_mode": {str(m): {"ms_per_frame_latency": v[0], "ms_per_frame_two_streams": v[1]}
                                   for m, v in single.items()},
            "e2e": {"ms_per_frame": e2e_ms, "mrays": W * H / e2e_ms / 1e3, "d2h_bytes_per_frame": W * H * 12,
-                   "api": "stripes stored into rank 0's frame over NVLink, then one DMA to pinned host memory per frame"},
+                   "verified_bit_identical": host_verified,
+                   "api": "rtgs.sharding.HostFrame: every rank DMAs its own stripes into one shared page-locked host "
+                          "image over its own PCIe link, flags in the same shared memory; rank 0 collects every frame"},
            "gather": "peer stores + device-side arrive/grant counters (no collective)"}
     return res
 

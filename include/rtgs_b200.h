@@ -227,6 +227,17 @@ int rtgs_stream_set_counter(int device, uint32_t* counter, uint32_t value, void*
  * deliver their stripes of one frame into (each over its own PCIe link).  Portable across devices. */
 int rtgs_host_register(void* p, size_t bytes);
 int rtgs_host_unregister(void* p);
+/* Device alias of a pinned / registered host address (for flags a stream-ordered kernel stores into host memory). */
+int rtgs_host_device_pointer(void* host, void** dev);
+/* Queue a one-thread kernel that release-stores `value` to *counter at system scope (a plain store: for flags in
+ * mapped host memory, one writer per flag). */
+int rtgs_stream_store_u32(int device, uint32_t* counter, uint32_t value, void* stream);
+/* Tile sharding, host delivery: copy this rank's 32-column stripes (stripe k belongs to rank k % world, the
+ * RTGS_OPT_STRIPE partition) of a (W,H,3) float32 DEVICE image to the same positions of a (W,H,3) pinned HOST image:
+ * one strided DMA for all full stripes (+ one for a ragged last stripe).  With every rank delivering its own stripes
+ * into one shared, registered host image the frame crosses PCIe on all the GPUs' links in parallel. */
+int rtgs_copy_stripes_d2h(int device, float* host_rgb, const float* dev_rgb, int32_t W, int32_t H,
+                          int32_t world, int32_t rank, void* stream);
 
 /* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
  * RayTracer makes: camera in, image out): `host_rgb` ((w,h,3) float32) and optionally
@@ -249,6 +260,20 @@ int rtgs_render_host_submit(rtgs_scene* s, const rtgs_camera* cam,
                             int32_t x0, int32_t y0, int32_t w, int32_t h,
                             int32_t depth, float t_cut, float* host_rgb, float* host_T);
 int rtgs_render_host_collect(rtgs_scene* s);
+
+/* rtgs_render_host_submit with a COMPACT host image (opt-in; the float32 call above is the parity path).  The
+ * frame is rendered in float32 as always and converted on the device before the DMA:
+ *   RTGS_PIXELS_F32    (w,h,3) float32, 12 B/pixel - identical to rtgs_render_host_submit
+ *   RTGS_PIXELS_F16    (w,h,3) IEEE half, round to nearest even, 6 B/pixel
+ *   RTGS_PIXELS_RGBA8  (w,h,4) bytes, each channel clip(x,0,1)*255 rounded to nearest, alpha 255, 4 B/pixel - what the
+ *                      reference's viewer shows (ti.GUI.set_image clips to 8 bits, __main__.py:249-252)
+ * For viewer loops and sweeps on several GPUs of one host, whose summed device-to-host traffic otherwise exceeds
+ * what the host can absorb (profiles/README.md: ~100 GB/s in total on the 8-GPU box).  Collected with
+ * rtgs_render_host_collect like any submitted frame. */
+typedef enum rtgs_pixel_format { RTGS_PIXELS_F32 = 0, RTGS_PIXELS_F16 = 1, RTGS_PIXELS_RGBA8 = 2 } rtgs_pixel_format;
+int rtgs_render_host_submit_packed(rtgs_scene* s, const rtgs_camera* cam,
+                                   int32_t x0, int32_t y0, int32_t w, int32_t h,
+                                   int32_t depth, float t_cut, void* host_pixels, int32_t format);
 
 /* Camera.generate_ray_field — camera.py:57-71.  rays: device, (W,H,8) float32
  * = origin xyz, direction xyz, start, end (ray.py:4-18). */

@@ -52,13 +52,13 @@ void free_scene(rtgs_scene* s) {
     cudaFree(s->morton64);
     cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
     for (auto& fs : s->scratch) {
-        cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.ready);
+        cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.fallback_tiles2); cudaFree(fs.ready);
         cudaFree(fs.counters);
         if (fs.free_event) cudaEventDestroy(fs.free_event);
     }
     cudaFree(s->stats_dev);
     for (auto& hs : s->host_slot) {
-        cudaFree(hs.stage_rgb); cudaFree(hs.stage_T);
+        cudaFree(hs.stage_rgb); cudaFree(hs.stage_T); cudaFree(hs.stage_packed);
         if (hs.done) cudaEventDestroy(hs.done);
         if (hs.copied) cudaEventDestroy(hs.copied);
     }
@@ -117,8 +117,8 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
         fs.mirror_dev = s->band_flags_dev + off;
         fs.mirror[0] = 0;   // pool demand of the last finished frame (render.cu: ensure_lists)
         fs.mirror[1] = 0;   // some finished frame had fallback tiles (render.cu: launch_render_k)
-        TRY(dev_alloc(&fs.counters, 8));
-        CUDA_TRY(cudaMemset(fs.counters, 0, 8 * sizeof(unsigned int)));   // k_frame leaves them zeroed frame after frame
+        TRY(dev_alloc(&fs.counters, 16));      // CTR_COUNT (render_common.cuh)
+        CUDA_TRY(cudaMemset(fs.counters, 0, 16 * sizeof(unsigned int)));   // k_frame leaves them zeroed frame after frame
         CUDA_TRY(cudaEventCreateWithFlags(&fs.free_event, cudaEventDisableTiming));
     }
     TRY(dev_alloc(&s->pos, n * 3));
@@ -440,8 +440,8 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             s->opt_pool_chunks = value;
             // dropped here, re-created with the new capacity by the next render
             for (auto& fs : s->scratch) {
-                cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.ready);
-                fs.tile_desc = nullptr; fs.list_pool = nullptr; fs.fallback_tiles = nullptr; fs.ready = nullptr;
+                cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.fallback_tiles2); cudaFree(fs.ready);
+                fs.tile_desc = nullptr; fs.list_pool = nullptr; fs.fallback_tiles = nullptr; fs.fallback_tiles2 = nullptr; fs.ready = nullptr;
                 fs.list_tiles = 0;
                 fs.pool_chunks = 0;
             }
@@ -549,6 +549,53 @@ int rtgs_host_register(void* p, size_t bytes) {
 
 int rtgs_host_unregister(void* p) {
     if (p) CUDA_TRY(cudaHostUnregister(p));
+    return RTGS_OK;
+}
+
+int rtgs_host_device_pointer(void* host, void** dev) {
+    RTGS_CHECK_ARG(host != nullptr && dev != nullptr);
+    *dev = nullptr;
+    CUDA_TRY(cudaHostGetDevicePointer(dev, host, 0));
+    return RTGS_OK;
+}
+
+int rtgs_stream_store_u32(int device, uint32_t* counter, uint32_t value, void* stream) {
+    RTGS_CHECK_ARG(counter != nullptr);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    return rtgs_launch_store_u32(counter, value, (cudaStream_t)stream);
+}
+
+int rtgs_copy_stripes_d2h(int device, float* host_rgb, const float* dev_rgb, int32_t W, int32_t H, int32_t world,
+                          int32_t rank, void* stream) {
+    RTGS_CHECK_ARG(host_rgb != nullptr && dev_rgb != nullptr);
+    RTGS_CHECK_ARG(W > 0 && H > 0 && world >= 1 && rank >= 0 && rank < world);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    // stripe k = pixel columns [32 k, 32 k + 32): 32 * H * 3 contiguous floats of the i-major image; rank owns
+    // k = rank, rank + world, ...  All full stripes of the rank move as ONE strided copy (rows = stripes).
+    const size_t stripe = (size_t)32 * H * 3 * sizeof(float);
+    const int nstripes = (W + 31) / 32;
+    const int full = W / 32;                                  // stripes of full width
+    const int mine_full = rank < full ? (full - rank + world - 1) / world : 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const char* src = reinterpret_cast<const char*>(dev_rgb) + (size_t)rank * stripe;
+    char* dst = reinterpret_cast<char*>(host_rgb) + (size_t)rank * stripe;
+    if (mine_full > 0)
+        CUDA_TRY(cudaMemcpy2DAsync(dst, stripe * world, src, stripe * world, stripe, (size_t)mine_full,
+                                   cudaMemcpyDeviceToHost, st));
+    if (nstripes > full && (nstripes - 1) % world == rank) {   // the ragged last stripe
+        const size_t off = (size_t)(nstripes - 1) * stripe;
+        const size_t bytes = (size_t)(W - 32 * full) * H * 3 * sizeof(float);
+        CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(host_rgb) + off, reinterpret_cast<const char*>(dev_rgb) + off,
+                                 bytes, cudaMemcpyDeviceToHost, st));
+    }
     return RTGS_OK;
 }
 
@@ -752,6 +799,46 @@ int rtgs_render_host_submit(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, i
     static const bool banded = getenv("RTGS_SUBMIT_BANDED") != nullptr;   // experiment: band pipeline here too
     if (banded) return submit_banded(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, host_T);
     return submit_whole(s, cam, x0, y0, w, h, depth, t_cut, host_rgb, host_T);
+}
+
+int rtgs_render_host_submit_packed(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, int32_t w, int32_t h,
+                                   int32_t depth, float t_cut, void* host_pixels, int32_t format) {
+    if (format == RTGS_PIXELS_F32)
+        return rtgs_render_host_submit(s, cam, x0, y0, w, h, depth, t_cut, (float*)host_pixels, nullptr);
+    RTGS_CHECK_ARG(format == RTGS_PIXELS_F16 || format == RTGS_PIXELS_RGBA8);
+    TRY(check_host_render_args(s, cam, x0, y0, w, h, depth, t_cut, (const float*)host_pixels,
+                               "rtgs_render_host_submit_packed"));
+    if (s->host_inflight >= 2) {
+        rtgs_set_error("rtgs_render_host_submit_packed: two frames are in flight already; call rtgs_render_host_collect");
+        return RTGS_ERR_STATE;
+    }
+    DeviceGuard g(s->device);
+    if (!pinned_device_ptr(host_pixels)) {
+        rtgs_set_error("rtgs_render_host_submit_packed: the destination must be pinned host memory (rtgs_host_alloc)");
+        return RTGS_ERR_INVALID;
+    }
+    rtgs_scene::HostSlot& hs = s->host_slot[s->host_head];
+    const size_t px = (size_t)w * h;
+    TRY(ensure_stage(hs, px));
+    if (hs.stage_packed_pixels < px) {
+        cudaFree(hs.stage_packed);
+        hs.stage_packed = nullptr;
+        hs.stage_packed_pixels = 0;
+        CUDA_TRY(cudaMalloc(&hs.stage_packed, px * 8));
+        hs.stage_packed_pixels = px;
+    }
+    cudaStream_t rs = s->host_head == 0 ? s->own_stream : s->own_stream2;
+    TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, 0, 0, hs.stage_rgb, nullptr, rs, false));
+    TRY(rtgs_launch_pack_pixels(hs.stage_rgb, hs.stage_packed, (int64_t)px, format, rs));
+    CUDA_TRY(cudaEventRecord(hs.done, rs));
+    CUDA_TRY(cudaStreamWaitEvent(s->copy_stream, hs.done, 0));
+    const size_t bytes = px * (format == RTGS_PIXELS_F16 ? 6 : 4);
+    CUDA_TRY(cudaMemcpyAsync(host_pixels, hs.stage_packed, bytes, cudaMemcpyDeviceToHost, s->copy_stream));
+    CUDA_TRY(cudaEventRecord(hs.copied, s->copy_stream));
+    hs.nb = 0;   // a whole-frame slot for _collect
+    s->host_head ^= 1;
+    ++s->host_inflight;
+    return RTGS_OK;
 }
 
 int rtgs_render_host_collect(rtgs_scene* s) {

@@ -99,6 +99,7 @@ struct rtgs_scene {
         void* tile_desc = nullptr;            // candidate lists (render_common.cuh), sized on first use
         int* list_pool = nullptr;
         int* fallback_tiles = nullptr;
+        int* fallback_tiles2 = nullptr;
         unsigned int* ready = nullptr;        // per traversal group: sequence number of the frame whose lists are complete
         unsigned int frame_seq = 0;           // frames launched through k_frame so far (ready[] is compared with it)
         bool counters_dirty = false;          // the last frame did not zero the work counters itself
@@ -128,6 +129,8 @@ struct rtgs_scene {
         float* stage_rgb = nullptr;
         float* stage_T = nullptr;
         size_t stage_pixels = 0;
+        void* stage_packed = nullptr;         // compact delivery (RTGS_PIXELS_F16 / _RGBA8): the converted image
+        size_t stage_packed_pixels = 0;
         int* flags = nullptr;                 // this slot's part of band_flags (host / device alias)
         int* flags_dev = nullptr;
         cudaEvent_t done = nullptr;           // recorded behind the frame's last kernel
@@ -169,6 +172,8 @@ int rtgs_launch_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays, i
                               float* t12, cudaStream_t stream);
 int rtgs_launch_wait_counter(const unsigned int* counter, unsigned int value, cudaStream_t stream);
 int rtgs_launch_set_counter(unsigned int* counter, unsigned int value, cudaStream_t stream);
+int rtgs_launch_store_u32(unsigned int* counter, unsigned int value, cudaStream_t stream);
+int rtgs_launch_pack_pixels(const float* rgb, void* out, int64_t npix, int format, cudaStream_t stream);
 int rtgs_launch_activate_ply(int64_t n, const float* rows_dev, int stride, const int32_t* col,
                              float scale, int sh_layout, float* pos, float* rot, float* sca,
                              float* color, float* opacity, float* sh, cudaStream_t stream);

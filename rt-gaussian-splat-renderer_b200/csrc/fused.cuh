@@ -33,7 +33,7 @@
 // small band of the sqrt(3)-sigma surface, an entry distance within a band of 0, and adjacent
 // k-buffer entries closer than a few ulp are re-evaluated in float64 from the raw parameters.
 #pragma once
-#include "render_common.cuh"
+#include "kbuffer.cuh"
 
 namespace rtgs_dev {
 namespace fused {
@@ -53,7 +53,7 @@ constexpr int REC_Q = 5;                 // quads per staged record (80-byte str
 struct __align__(16) TraversalScratch {
     float4 rec[BATCH][REC_Q];   // precise records (render_common.cuh: stage_candidate)
     float4 polyA[BATCH];        // coarse quadratics {c0 c1 c2 c3}
-    float2 polyB[BATCH];        //                   {c4 c5}
+    float4 polyB[BATCH];        //                   {c4 c5 t_lo -}: t_lo = no ray of the tile enters the candidate before it
     int stack[STACK_CAP];
     int cq[CQ_CAP];
     Frustum open;               // pyramid of the rays that still lack hits (distance pruning, below)
@@ -84,10 +84,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     const unsigned lt_mask = (1u << lane) - 1u;
     const CamD& cam = P.cam;
     const int xe = P.x0 + P.w, ye = P.y0 + P.h;
-    // work items: every tile id, or (fallback mode) the tiles k_tile_lists could not store a list for
-    const int nwork = P.use_fallback_list ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : P.ntiles;
+    // work items: every tile id, or (fallback mode) the tiles the traversal and / or the shading handed over
+    const int n1 = (P.use_fallback_list & 1) ? (int)min(P.counters[CTR_FALLBACK], (unsigned)P.ntiles) : 0;
+    const int n2 = (P.use_fallback_list & 2) ? (int)min(P.counters[CTR_FALLBACK2], (unsigned)P.ntiles) : 0;
+    unsigned int* const cursor = P.counters + (P.use_fallback_list == 2 ? CTR_WORK4 : CTR_WORK3);
+    if (P.early_trigger) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (P.use_fallback_list && blockIdx.x == 0 && threadIdx.x == 0) {
+    if ((P.use_fallback_list & 1) && blockIdx.x == 0 && threadIdx.x == 0) {
         // pool demand of this frame (for the host's sizing) and whether any frame so far needed the fallback
         *reinterpret_cast<volatile int*>(P.mirror) = (int)min(P.counters[CTR_POOL], 0x7fffffffu);
         if (P.counters[CTR_FALLBACK] != 0) *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
@@ -103,9 +106,8 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     for (;;) {
         int tile = 0;
         if (lane == 0) {
-            tile = (int)atomicAdd(P.counters + CTR_WORK3, 1u);
-            if (P.use_fallback_list && tile < nwork) tile = P.fallback_tiles[tile];
-            else if (P.use_fallback_list) tile = P.ntiles;
+            tile = (int)atomicAdd(cursor, 1u);
+            if (P.use_fallback_list) tile = tile < n1 ? P.fallback_tiles[tile] : (tile - n1 < n2 ? P.fallback_tiles2[tile - n1] : P.ntiles);
             else tile = work_to_id(P, tile, P.macro_cols * TILES_PER_MACRO, P.ntiles);
         }
         tile = __shfl_sync(FULL, tile, 0);
@@ -128,10 +130,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         float kmax_t = INFINITY;
         int kmax_slot = 0;
 
-        // one pending candidate per lane; the precise test and the hit-only work (entry distance,
-        // alpha, float64 refinement, buffer append) run in warp-wide rounds
-        bool pend = false;
-        int pend_c = 0;
+        // Transmittance exhaustion (t_cut > 0, K = 16): once the hits a ray holds bring its transmittance below
+        // t_cut, nothing behind the hit that does so is ever composited (ray_tracer.py:96-98 with the early-out), and
+        // hits found later can only lower the transmittance further.  d_T is that hit's entry distance (with a margin);
+        // the ray is then CLOSED at min(d_T, farthest of K kept hits) exactly like a ray whose buffer is full.
+        float d_T = INFINITY;
+        bool kb_dirty = false;         // the lane's buffer changed since d_T was last evaluated
 
         // Distance pruning - the K-nearest form of the reference's "skip a node whose entry distance exceeds the best
         // hit so far" (scene.py:417-419).  A ray that holds K hits needs nothing farther than its farthest one, so a
@@ -205,105 +209,140 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             while (ncq >= BATCH || (top == 0 && ncq > 0)) {
                 const int m = min(BATCH, ncq);
                 ncq -= m;
+                const int m4 = (m + 3) & ~3;
                 if (lane < m) {
                     float4 rec[5];
                     float poly[6];
-                    stage_candidate(P, ry, tr.cq[ncq + lane], rec, poly);
+                    stage_candidate<true>(P, ry, tr.cq[ncq + lane], rec, poly);
 #pragma unroll
                     for (int k = 0; k < 5; ++k) tr.rec[lane][k] = rec[k];
                     tr.polyA[lane] = make_float4(poly[0], poly[1], poly[2], poly[3]);
-                    tr.polyB[lane] = make_float2(poly[4], poly[5]);
+                    tr.polyB[lane] = make_float4(poly[4], poly[5], rec[4].w, 0.0f);
+                } else if (lane < m4) {   // pad to a multiple of 4: never a candidate
+                    tr.polyA[lane] = make_float4(1.0f, 0.0f, 0.0f, 0.0f);
+                    tr.polyB[lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
                 }
                 __syncwarp();
                 ST(st_cands += (unsigned)m);
                 ST(st_pairs += 32ull * (unsigned)m);
+                // ---- coarse: mask of the staged candidates this ray may hit (as in shade.cuh) ----------
+                // a closed ray takes nothing that certainly begins behind its cut (margin: near ties at the K-th
+                // place are decided in float64 by the insertion code, so they must reach it)
+                const float my_cut = fminf(cnt == K ? kmax_t : INFINITY, d_T) * 1.000004f;
+                unsigned mask = 0;
 #pragma unroll 1
-                for (int c = 0; c <= m; ++c) {
-                    bool cand = false;
-                    if (c < m) {
-                        const float4 pA = tr.polyA[c];
-                        const float2 pB = tr.polyB[c];
+                for (int c = 0; c < m4; c += 4) {
+                    unsigned nib = 0;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 pA = tr.polyA[c + u];
+                        const float4 pB = tr.polyB[c + u];
                         const float ta = fmaf(ry.pa, pA.w, fmaf(ry.pb, pB.x, pA.y));   // c1 + a c3 + b c4
                         const float tb = fmaf(ry.pb, pB.y, pA.z);                      // c2 + b c5
                         const float S = fmaf(ry.pa, ta, fmaf(ry.pb, tb, pA.x));
-                        cand = active && (S < 0.0f);
+                        if (S < 0.0f && pB.z <= my_cut) nib |= 1u << u;
                     }
-                    // flush when a lane gets a second candidate, and once at the end of the batch
-                    // (the staged records are about to be overwritten)
-                    if (__any_sync(FULL, pend && (cand || c == m))) {
-                        if (pend) {
-                            const PreciseHit h = precise_test(P, tr.rec[pend_c], ry.dlx, ry.dly, ry.dlz, pi, pj);
-                            ST(st_f64 += h.refined);
-                            if (h.hit) {
-                                auto find_farthest = [&]() {
-                                    float mt = -INFINITY;
-                                    int ms = 0;
-#pragma unroll 4
-                                    for (int k = 0; k < K; ++k) {
-                                        const float t = ws.kb_t[k][lane];
-                                        if (t > mt) { mt = t; ms = k; }
-                                    }
-                                    kmax_t = mt;
-                                    kmax_slot = ms;
-                                };
-                                if (cnt < K) {
-                                    const int slot = cnt++;
-                                    ws.kb_t[slot][lane] = h.t1;
-                                    ws.kb_i[slot][lane] = h.s;
-                                    ws.kb_a[slot][lane] = h.alpha;
-                                    if (cnt == K) find_farthest();
-                                } else {
-                                    // full: the candidate replaces the farthest entry if it is nearer.  Whenever
-                                    // two contenders for the last place are within float32 rounding of each other
-                                    // - the candidate and the farthest entry, or the evicted entry and the new
-                                    // farthest one - their float64 entry distances decide (exact_less; rare).
-                                    float ct = h.t1, ca = h.alpha;
-                                    int cs = h.s;
+                    mask |= nib << c;
+                }
+                if (!active) mask = 0;
+                // ---- precise: warp-wide rounds, one candidate per lane and round ----------------------
 #pragma unroll 1
-                                    for (;;) {
-                                        bool nearer = ct < kmax_t;
-                                        if (fabsf(ct - kmax_t) <= 2e-6f * kmax_t) {
-                                            nearer = exact_less(P.raw, cam, cs, ws.kb_i[kmax_slot][lane], pi, pj);
-                                            ST(st_f64 += 2);
-                                        }
-                                        if (!nearer) break;
-                                        const float et = kmax_t, ea = ws.kb_a[kmax_slot][lane];
-                                        const int es = ws.kb_i[kmax_slot][lane];
-                                        ws.kb_t[kmax_slot][lane] = ct;
-                                        ws.kb_i[kmax_slot][lane] = cs;
-                                        ws.kb_a[kmax_slot][lane] = ca;
-                                        find_farthest();
-                                        if (!(et - kmax_t <= 2e-6f * et)) break;
-                                        ct = et; cs = es; ca = ea;   // the evicted entry ties with the new farthest
+                while (__any_sync(FULL, mask != 0)) {
+                    if (mask != 0) {
+                        const int c = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const PreciseHit h = precise_test(P, tr.rec[c], ry.dlx, ry.dly, ry.dlz, pi, pj);
+                        ST(st_f64 += h.refined);
+                        if (h.hit && h.t1 <= d_T) {
+                            kb_dirty = true;
+                            auto find_farthest = [&]() {
+                                float mt = -INFINITY;
+                                int ms = 0;
+#pragma unroll 4
+                                for (int k = 0; k < K; ++k) {
+                                    const float t = ws.kb_t[k][lane];
+                                    if (t > mt) { mt = t; ms = k; }
+                                }
+                                kmax_t = mt;
+                                kmax_slot = ms;
+                            };
+                            if (cnt < K) {
+                                const int slot = cnt++;
+                                ws.kb_t[slot][lane] = h.t1;
+                                ws.kb_i[slot][lane] = h.s;
+                                ws.kb_a[slot][lane] = h.alpha;
+                                if (cnt == K) find_farthest();
+                            } else {
+                                // full: the candidate replaces the farthest entry if it is nearer.  Whenever
+                                // two contenders for the last place are within float32 rounding of each other
+                                // - the candidate and the farthest entry, or the evicted entry and the new
+                                // farthest one - their float64 entry distances decide (exact_less; rare).
+                                float ct = h.t1, ca = h.alpha;
+                                int cs = h.s;
+#pragma unroll 1
+                                for (;;) {
+                                    bool nearer = ct < kmax_t;
+                                    if (fabsf(ct - kmax_t) <= 2e-6f * kmax_t) {
+                                        nearer = exact_less(P.raw, cam, cs, ws.kb_i[kmax_slot][lane], pi, pj);
+                                        ST(st_f64 += 2);
                                     }
+                                    if (!nearer) break;
+                                    const float et = kmax_t, ea = ws.kb_a[kmax_slot][lane];
+                                    const int es = ws.kb_i[kmax_slot][lane];
+                                    ws.kb_t[kmax_slot][lane] = ct;
+                                    ws.kb_i[kmax_slot][lane] = cs;
+                                    ws.kb_a[kmax_slot][lane] = ca;
+                                    find_farthest();
+                                    if (!(et - kmax_t <= 2e-6f * et)) break;
+                                    ct = et; cs = es; ca = ea;   // the evicted entry ties with the new farthest
                                 }
                             }
-                            pend = false;
                         }
-                        ST(st_ins += 1);
                     }
-                    if (cand) {
-                        pend = true;
-                        pend_c = c;
-                    }
+                    ST(st_ins += 1);
                 }
                 __syncwarp();
-                // ---- pruning state after the batch: who is full, how far their farthest hit is ----
+                // ---- pruning state after the batch: which rays are closed, and how far they still look ----
                 {
-                    const bool full = active && cnt == K;
-                    float cm = full ? kmax_t : -1.0f;
+                    if constexpr (K == 16) {
+                        if (P.t_cut > 0.0f && __any_sync(FULL, kb_dirty)) {
+                            // order the lane's hits (truncated keys are enough: the margin below covers near ties)
+                            // and multiply the transmittance through
+                            unsigned key[16];
+#pragma unroll
+                            for (int k = 0; k < 16; ++k)
+                                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
+                            sort_keys<16>(key);
+                            const float lim = 0.99f * P.t_cut;
+                            float Tacc = 1.0f, d = INFINITY;
+#pragma unroll
+                            for (int r = 0; r < 16; ++r) {
+                                if (r < cnt && d == INFINITY) {
+                                    const int slot = (int)(key[r] & 15u);
+                                    Tacc *= 1.0f - ws.kb_a[slot][lane];
+                                    if (Tacc < lim) d = ws.kb_t[slot][lane];
+                                }
+                            }
+                            d_T = d * 1.0001f;     // (inf stays inf)
+                            kb_dirty = false;
+                        }
+                    }
+                    const float c_ray = fminf(cnt == K ? kmax_t : INFINITY, d_T);
+                    const bool closed = active && c_ray < INFINITY;
+                    float cm = closed ? c_ray : -1.0f;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
                     if (cm >= 0.0f) {
                         cm *= 1.0001f;
                         cut2 = cm * cm;
                     }
-                    const unsigned om = __ballot_sync(FULL, active && cnt < K);
+                    const bool open = active && !closed;
+                    const unsigned om = __ballot_sync(FULL, open);
                     if (om != open_mask) {
                         open_mask = om;
                         if (om != 0) {
-                            int il = cnt < K && active ? pi : 0x7fffffff, ih = cnt < K && active ? pi : -1;
-                            int jl = cnt < K && active ? pj : 0x7fffffff, jh = cnt < K && active ? pj : -1;
+                            int il = open ? pi : 0x7fffffff, ih = open ? pi : -1;
+                            int jl = open ? pj : 0x7fffffff, jh = open ? pj : -1;
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) {
                                 il = min(il, __shfl_xor_sync(FULL, il, o));
@@ -322,56 +361,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             }
         }
 
-        // ---- order the hits by ascending entry distance: rank counting into the compositing list --
-        // rank_i = #{j : t_j < t_i}; pairs within float32 rounding of each other are ordered by their
-        // float64 entry distances (exact_less).  The traversal scratch is dead from here on.
         int maxcnt = cnt;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
         __syncwarp();
-        if (maxcnt > 0) {
-            float tk[K];
-#pragma unroll
-            for (int k = 0; k < K; ++k) tk[k] = k < cnt ? ws.kb_t[k][lane] : INFINITY;
-#pragma unroll 1
-            for (int i = 0; i < maxcnt; ++i) {
-                if (i < cnt) {
-                    const float ti_ = ws.kb_t[i][lane];
-                    const float band = 2e-6f * fabsf(ti_);
-                    int rank = 0, nnear = 0;
-#pragma unroll
-                    for (int j = 0; j < K; ++j) {
-                        rank += tk[j] < ti_;
-                        nnear += fabsf(tk[j] - ti_) <= band;
-                    }
-                    const int id = ws.kb_i[i][lane];
-                    if (nnear > 1) {   // rare: resolve near ties exactly
-                        rank = 0;
-#pragma unroll 1
-                        for (int j = 0; j < cnt; ++j) {
-                            if (j == i) continue;
-                            const float tj_ = ws.kb_t[j][lane];
-                            if (fabsf(tj_ - ti_) <= band) {
-                                rank += exact_less(P.raw, cam, ws.kb_i[j][lane], id, pi, pj);
-                                ST(st_f64 += 2);
-                            } else {
-                                rank += tj_ < ti_;
-                            }
-                        }
-                    }
-                    ws.c.so_i[rank][lane] = id;
-                    ws.c.so_a[rank][lane] = ws.kb_a[i][lane];
-                }
-            }
-        }
-        __syncwarp();
-
-        // ================================ compositing ========================================
-        // accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98), rgb = color +
-        // eval_sh(normalize(dir)) (gaussian.py:199-200).
         float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;
         int nl = 0;
-        {
+        if constexpr (K == 16) {
+            // ---- order the hits (bitonic network over register keys, near ties by float64: kbuffer.cuh) and composite
+            // accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98), rgb = color + eval_sh(normalize(dir))
+            unsigned long long n_exact = 0;
+            const unsigned long long perm = order_hits16(P, ws.kb_t, ws.kb_i, cnt, maxcnt, lane, pi, pj, n_exact);
+            ST(st_f64 += n_exact);
             float Y[15];
             sh_basis(ry.dnx, ry.dny, ry.dnz, Y);
             const int nmine = min(cnt, P.depth);
@@ -379,8 +380,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
 #pragma unroll 1
             for (int k = 0; k < nloop; ++k) {
                 if (k < nmine && T >= P.t_cut) {
-                    const int s = ws.c.so_i[k][lane];
-                    const float alpha = ws.c.so_a[k][lane];
+                    const int slot = (int)((perm >> (4 * k)) & 15u);
+                    const int s = ws.kb_i[slot][lane];
+                    const float alpha = ws.kb_a[slot][lane];
                     float r, g, b;
                     eval_colour(P, s, Y, r, g, b);
                     const float wgt = T * alpha;
@@ -389,6 +391,70 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                     cb = fmaf(wgt, b, cb);
                     T *= 1.0f - alpha;
                     ++nl;
+                }
+            }
+            __syncwarp();
+        } else {
+            // ---- K = 32: rank counting into the compositing list.  rank_i = #{j : t_j < t_i}; pairs within float32
+            // rounding of each other are ordered by their float64 entry distances (exact_less).
+            if (maxcnt > 0) {
+                float tk[K];
+#pragma unroll
+                for (int k = 0; k < K; ++k) tk[k] = k < cnt ? ws.kb_t[k][lane] : INFINITY;
+#pragma unroll 1
+                for (int i = 0; i < maxcnt; ++i) {
+                    if (i < cnt) {
+                        const float ti_ = ws.kb_t[i][lane];
+                        const float band = 2e-6f * fabsf(ti_);
+                        int rank = 0, nnear = 0;
+#pragma unroll
+                        for (int j = 0; j < K; ++j) {
+                            rank += tk[j] < ti_;
+                            nnear += fabsf(tk[j] - ti_) <= band;
+                        }
+                        const int id = ws.kb_i[i][lane];
+                        if (nnear > 1) {   // rare: resolve near ties exactly
+                            rank = 0;
+#pragma unroll 1
+                            for (int j = 0; j < cnt; ++j) {
+                                if (j == i) continue;
+                                const float tj_ = ws.kb_t[j][lane];
+                                if (fabsf(tj_ - ti_) <= band) {
+                                    rank += exact_less(P.raw, cam, ws.kb_i[j][lane], id, pi, pj);
+                                    ST(st_f64 += 2);
+                                } else {
+                                    rank += tj_ < ti_;
+                                }
+                            }
+                        }
+                        ws.c.so_i[rank][lane] = id;
+                        ws.c.so_a[rank][lane] = ws.kb_a[i][lane];
+                    }
+                }
+            }
+            __syncwarp();
+            // ================================ compositing ========================================
+            // accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98), rgb = color +
+            // eval_sh(normalize(dir)) (gaussian.py:199-200).
+            {
+                float Y[15];
+                sh_basis(ry.dnx, ry.dny, ry.dnz, Y);
+                const int nmine = min(cnt, P.depth);
+                const int nloop = min(maxcnt, P.depth);
+#pragma unroll 1
+                for (int k = 0; k < nloop; ++k) {
+                    if (k < nmine && T >= P.t_cut) {
+                        const int s = ws.c.so_i[k][lane];
+                        const float alpha = ws.c.so_a[k][lane];
+                        float r, g, b;
+                        eval_colour(P, s, Y, r, g, b);
+                        const float wgt = T * alpha;
+                        cr = fmaf(wgt, r, cr);
+                        cg = fmaf(wgt, g, cg);
+                        cb = fmaf(wgt, b, cb);
+                        T *= 1.0f - alpha;
+                        ++nl;
+                    }
                 }
             }
         }
@@ -424,7 +490,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             if (lane == 0 && x) atomicAdd(P.stats + k, x);
         }
     }
-    if (P.final_kernel) cta_finish(P, CTR_DONE2);
+    if (P.final_kernel) cta_finish(P, P.use_fallback_list == 1 ? CTR_DONE3 : CTR_DONE2);
 }
 #undef ST
 

@@ -37,8 +37,12 @@ struct TileDesc {
     int count;   // candidates; -1: the list did not fit the pool, the tile is in the fallback list
 };
 
+// CTR_FALLBACK / CTR_WORK3: tiles the traversal hands to k_render (list pool exhausted, or a group whose frustum holds
+// too many candidates) and the cursor of the launch that renders them; CTR_FALLBACK2 / CTR_WORK4: tiles the shading
+// hands over (three hits within rounding at the K-th place) and their cursor.  Two lists, because the first one is
+// complete BEFORE the shading starts and its tiles are rendered concurrently with it (render.cu).
 enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_DONE = 5, CTR_DONE2 = 6,
-       CTR_COUNT = 8 };
+       CTR_FALLBACK2 = 7, CTR_WORK4 = 8, CTR_DONE3 = 9, CTR_COUNT = 16 };
 enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
        ST_FALLBACK, ST_COUNT = 12 };
 
@@ -65,8 +69,12 @@ struct RenderParams {
     TileDesc* desc;           // ntiles
     int* pool;                // pool_chunks * CHUNK_INTS
     int pool_chunks;
-    int* fallback_tiles;      // ntiles
-    int use_fallback_list;    // k_render: take tile ids from fallback_tiles[0 .. counters[2])
+    int* fallback_tiles;      // ntiles: tiles handed over by the traversal (lists_group)
+    int* fallback_tiles2;     // ntiles: tiles handed over by the shading (shade_tile)
+    int use_fallback_list;    // k_render: 0 = every tile of the region; bit 0 = the tiles of fallback_tiles, bit 1 =
+                              // those of fallback_tiles2 (both: the first list, then the second)
+    int early_trigger;        // k_render: let the next kernel on the stream start at once (programmatic dependent
+                              // launch): the shading that follows does not depend on this launch
     int heavy_fused;          // k_tile_lists: a group whose list overflows shared memory goes to k_render (distance pruning)
     int heavy_limit;          // ... "overflows" = more candidates than this (<= the capacity of the shared-memory list)
     int lists_single;         // lists_group pops one node per step while its stack holds more entries than this (tile_lists.cuh)
@@ -408,11 +416,12 @@ __device__ __forceinline__ void make_tile_rays(const CamD& cam, int i0, int j0, 
 
 // Per-(tile, candidate) staging in float64 by one lane: the precise record (origin shifted to the
 // closest point of the tile-centre ray) and the coarse quadratic.
-//   rec: {W00 W01 W02 W10} {W11 W12 W20 W21} {W22 e0.xyz} {g0.xyz t_c} {opacity, s, band, -}
+//   rec: {W00 W01 W02 W10} {W11 W12 W20 W21} {W22 e0.xyz} {g0.xyz t_c} {opacity, s, band, t_lo}
 //   poly: S(a,b) = c0 + a (c1 + a c3 + b c4) + b (c2 + b c5) < 0  <=>  possibly q < 3 + band
 // With o' = W (o - p) = -W v and G(a,b) = W D(a,b) = G0 + a Gx + b Gy:
 //   q(a,b) = |o' x G|^2 / |G|^2 = N/Dn,  m = o' x G = M0 + a Mx + b My,
 //   S = N - (3 + band) Dn - margin, margin bounding the float32 evaluation error.
+template <bool WITH_T_LO = false>
 __device__ __forceinline__ void stage_candidate(const RenderParams& P, const TileRays& tr, int s, float4 (&rec)[5],
                                                 float (&poly)[6]) {
     const CamD& cam = P.cam;
@@ -437,7 +446,15 @@ __device__ __forceinline__ void stage_candidate(const RenderParams& P, const Til
     rec[1] = g2;
     rec[2] = make_float4(g3.x, (float)e0.x, (float)e0.y, (float)e0.z);
     rec[3] = make_float4((float)gd.x, (float)gd.y, (float)gd.z, (float)tc);
-    rec[4] = make_float4(g0.w, __int_as_float(s), band, 0.0f);
+    // lower bound of the entry distance for every ray of the tile: t1 = tc + tau with
+    // |tau| <= (|e| + sqrt 3) / |W d|, |e| <= eb (above) and |W d| >= |W d0| - |W| |delta|max
+    // (only the fused kernel uses it: it prunes per ray by distance)
+    float t_lo = -INFINITY;
+    if (WITH_T_LO) {
+        const float gn = (float)sqrt(d3dot(gd, gd)) - wn * tr.dl_max;
+        if (gn > 0.0f) t_lo = __double2float_rd(tc - (double)((eb + 1.7320509f) / gn) * 1.000001);
+    }
+    rec[4] = make_float4(g0.w, __int_as_float(s), band, t_lo);
     const d3 op = Wmul(d3make(-v.x, -v.y, -v.z));
     const d3 G0 = Wmul(tr.D0);
     const d3 Gx = Wmul(d3make(cam.R[0], cam.R[3], cam.R[6]));

@@ -26,7 +26,7 @@
 // The code is bound by the L1 data pipe (per-lane gathers of SH and staged records), not by latency:
 // 20 warps x 96 registers per SM is the measured optimum, 9.25 KB of shared memory per warp.
 #pragma once
-#include "render_common.cuh"
+#include "kbuffer.cuh"
 
 namespace rtgs_dev {
 
@@ -60,34 +60,6 @@ struct ShadeStats {
     unsigned long long st_useful = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0, st_rays = 0, st_tiles = 0,
                        st_ins = 0;
 };
-
-// Bitonic sorting network over the first N (8 or 16) of 16 register-resident keys, ascending.
-template <int N>
-__device__ __forceinline__ void sort_keys(unsigned (&key)[16]) {
-#pragma unroll
-    for (int k = 2; k <= N; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-#pragma unroll
-            for (int i = 0; i < N; ++i) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const unsigned a = key[i], b = key[l];
-                    const bool up = (i & k) == 0;
-                    key[i] = up ? min(a, b) : max(a, b);
-                    key[l] = up ? max(a, b) : min(a, b);
-                }
-            }
-        }
-    }
-}
-
-// Could the entry distances behind two sorted keys be within 4e-6 relative of each other?  (The keys
-// carry the distances with 4 truncated bits, hence the wider 6e-6 screen; unused keys are 0xffffffff.)
-__device__ __forceinline__ bool keys_near(unsigned ka, unsigned kb) {
-    const float ta = __uint_as_float(ka & ~15u), tb = __uint_as_float(kb & ~15u);
-    return kb != 0xffffffffu && (tb - ta) <= 6e-6f * tb;
-}
 
 // Shade tile `tile` (a valid id < P.ntiles whose descriptor has been published).
 template <bool STATS>
@@ -226,7 +198,7 @@ __device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& w
             // three contenders within rounding: k_render (launched next on the stream) renders the tile and
             // resolves them on the spot; nothing of it has been written yet, so `accumulate` outputs stay correct
             if (lane == 0) {
-                P.fallback_tiles[atomicAdd(P.counters + CTR_FALLBACK, 1u)] = tile;
+                P.fallback_tiles2[atomicAdd(P.counters + CTR_FALLBACK2, 1u)] = tile;
                 *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
             }
             return;
@@ -258,69 +230,13 @@ __device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& w
         }
     }
 
-    // ---- order the hits by ascending entry distance -------------------------------------------
-    // Keys = entry-distance bits (positive floats order like their bit patterns) with the slot in the
-    // 4 low bits, sorted in registers by a bitonic network; perm holds the slot of every rank, 4 bits
-    // each.  Neighbours within float32 rounding (and the 4 truncated bits) of each other are then
-    // ordered by their float64 entry distances (rare).
-    unsigned long long perm = 0;
+    // ---- order the hits by ascending entry distance (kbuffer.cuh) ---------------------------------
     int maxcnt = cnt;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxcnt = max(maxcnt, __shfl_xor_sync(FULL, maxcnt, o));
-    if (maxcnt > 0) {
-        unsigned key[K];
-        bool near = false;
-        if (maxcnt <= 8) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
-            sort_keys<8>(key);
-            unsigned lo = 0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) lo |= (key[r] & 15u) << (4 * r);
-            perm = lo;
-#pragma unroll
-            for (int r = 0; r + 1 < 8; ++r) near = near || keys_near(key[r], key[r + 1]);
-        } else {
-#pragma unroll
-            for (int k = 0; k < K; ++k)
-                key[k] = k < cnt ? ((__float_as_uint(ws.kb_t[k][lane]) & ~15u) | (unsigned)k) : 0xffffffffu;
-            sort_keys<16>(key);
-            unsigned lo = 0, hi = 0;
-#pragma unroll
-            for (int r = 0; r < 8; ++r) {
-                lo |= (key[r] & 15u) << (4 * r);
-                hi |= (key[r + 8] & 15u) << (4 * r);
-            }
-            perm = ((unsigned long long)hi << 32) | lo;
-#pragma unroll
-            for (int r = 0; r + 1 < K; ++r) near = near || keys_near(key[r], key[r + 1]);
-        }
-        if (near) {
-            float tp = ws.kb_t[(int)(perm & 15u)][lane];
-#pragma unroll 1
-            for (int k = 1; k < cnt; ++k) {
-                const int sk = (int)((perm >> (4 * k)) & 15u);
-                const float tk = ws.kb_t[sk][lane];
-                if (fabsf(tk - tp) <= 4e-6f * fabsf(tk)) {
-                    // insertion among the near-tied predecessors
-                    int j = k;
-                    while (j > 0) {
-                        const int sa = (int)((perm >> (4 * (j - 1))) & 15u), sb = (int)((perm >> (4 * j)) & 15u);
-                        const float ta = ws.kb_t[sa][lane], tb = ws.kb_t[sb][lane];
-                        if (fabsf(tb - ta) > 4e-6f * fabsf(tb)) break;
-                        ST(S.st_f64 += 2);
-                        if (!exact_less(P.raw, cam, ws.kb_i[sb][lane], ws.kb_i[sa][lane], pi, pj)) break;
-                        const unsigned long long ma = 15ull << (4 * (j - 1)), mb = 15ull << (4 * j);
-                        perm = (perm & ~(ma | mb)) | ((unsigned long long)sb << (4 * (j - 1))) |
-                               ((unsigned long long)sa << (4 * j));
-                        --j;
-                    }
-                }
-                tp = ws.kb_t[(int)((perm >> (4 * k)) & 15u)][lane];
-            }
-        }
-    }
+    unsigned long long n_exact = 0;
+    const unsigned long long perm = order_hits16(P, ws.kb_t, ws.kb_i, cnt, maxcnt, lane, pi, pj, n_exact);
+    ST(S.st_f64 += n_exact);
 
     // ---- compositing: accum += T * alpha * rgb ; T *= 1 - alpha   (ray_tracer.py:96-98) ---------
     float T = 1.0f, cr = 0.0f, cg = 0.0f, cb = 0.0f;

@@ -62,6 +62,9 @@ SIGNATURES = {
     "rtgs_stream_set_counter": (C.c_int, [C.c_int, _vp, C.c_uint32, _vp]),
     "rtgs_host_register": (C.c_int, [_vp, C.c_size_t]),
     "rtgs_host_unregister": (C.c_int, [_vp]),
+    "rtgs_host_device_pointer": (C.c_int, [_vp, C.POINTER(_vp)]),
+    "rtgs_stream_store_u32": (C.c_int, [C.c_int, _vp, C.c_uint32, _vp]),
+    "rtgs_copy_stripes_d2h": (C.c_int, [C.c_int, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
     "rtgs_scene_read_kernel_times": (C.c_int, [_vp, C.c_int32, _vp]),
     "rtgs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rtgs_host_free": (C.c_int, [_vp]),
@@ -75,6 +78,8 @@ SIGNATURES = {
     "rtgs_render_host_submit": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_int32, C.c_float, _vp, _vp]),
     "rtgs_render_host_collect": (C.c_int, [_vp]),
+    "rtgs_render_host_submit_packed": (C.c_int, [_vp, C.POINTER(rtgs_camera), C.c_int32, C.c_int32, C.c_int32,
+                                                 C.c_int32, C.c_int32, C.c_float, _vp, C.c_int32]),
     "rtgs_generate_rays": (C.c_int, [C.POINTER(rtgs_camera), C.c_int, _vp, _vp]),
     "rtgs_trace_closest": (C.c_int, [_vp, C.c_int64, _vp, _vp, _vp, _vp]),
     "rtgs_scene_destroy": (C.c_int, [_vp]),
@@ -86,6 +91,8 @@ KERNEL_NAMES_BY_MODE = {0: ("k_tile_lists", "k_shade_tiles", "k_render"),
                         1: (None, None, "k_render"),
                         2: (None, "k_frame", "k_render")}
 KERNEL_NAMES = KERNEL_NAMES_BY_MODE[0]
+#: rtgs_pixel_format: name -> (enum value, numpy dtype, channels)
+PIXEL_FORMATS = {"f32": (0, "float32", 3), "f16": (1, "float16", 3), "rgba8": (2, "uint8", 4)}
 
 _lib = None
 

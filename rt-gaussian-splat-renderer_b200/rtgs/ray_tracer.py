@@ -138,7 +138,7 @@ class RayTracer:
                                                       out.ctypes.data, None))
         return out
 
-    def render_async(self, depth: int = 16, tile=None):
+    def render_async(self, depth: int = 16, tile=None, fmt: str = "f32"):
         """``render()`` without the wait: queue the frame of the CURRENT camera pose and return a
         ``PendingFrame``; its ``result()`` is the (w,h,3) host image.  Two frames may be in flight per
         scene, so in a sweep frame f+1 renders while the tail of frame f crosses PCIe::
@@ -153,13 +153,19 @@ class RayTracer:
             use(prev.result())
 
         The image lands in one of three pinned buffers owned by this RayTracer, used in turn: a result
-        stays valid until the third ``render_async`` after its own."""
+        stays valid until the third ``render_async`` after its own.
+
+        ``fmt`` selects an opt-in COMPACT host image (rtgs_render_host_submit_packed): "f32" (default, the parity
+        path, (w,h,3) float32), "f16" ((w,h,3) float16, half the bytes) or "rgba8" ((w,h,4) uint8, clipped to [0,1]
+        and rounded like the reference's display, a third of the bytes).  The frame is always rendered in float32;
+        only what crosses PCIe changes - for viewer loops and for sweeps on many GPUs of one host."""
         W, H = self.buf_size.x, self.buf_size.y
         x0, y0, w, h = (0, 0, W, H) if tile is None else tile
+        fmt_id, dtype, ch = _native.PIXEL_FORMATS[fmt]
         ring = self._async_ring
-        if not ring or ring[0].shape != (w, h, 3):
+        if not ring or ring[0].shape != (w, h, ch) or ring[0].dtype != np.dtype(dtype):
             self.scene.drain_pending()
-            ring = self._async_ring = [_native.PinnedBuffer((w, h, 3)) for _ in range(3)]
+            ring = self._async_ring = [_native.PinnedBuffer((w, h, ch), dtype) for _ in range(3)]
             self._async_next = 0
         buf = ring[self._async_next]
         self._async_next = (self._async_next + 1) % len(ring)
@@ -168,8 +174,12 @@ class RayTracer:
         while len(pending) >= 2:          # the library holds two frames at most
             pending[0].result()
         cam = self.camera.native()
-        _native.check(_native.load().rtgs_render_host_submit(self.scene.handle, cam, x0, y0, w, h, int(depth),
-                                                             self.t_cut, out.ctypes.data, None))
+        if fmt_id == 0:
+            _native.check(_native.load().rtgs_render_host_submit(self.scene.handle, cam, x0, y0, w, h, int(depth),
+                                                                 self.t_cut, out.ctypes.data, None))
+        else:
+            _native.check(_native.load().rtgs_render_host_submit_packed(self.scene.handle, cam, x0, y0, w, h,
+                                                                        int(depth), self.t_cut, out.ctypes.data, fmt_id))
         frame = PendingFrame(self.scene, out)
         pending.append(frame)
         return frame

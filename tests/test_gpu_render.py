@@ -426,3 +426,91 @@ def test_device_ply_ingest_matches_host_loader(test_ply):
     c = Scene().load_file(test_ply, 30.0, sh_layout="interleaved", activate_on_device=True).read_gaussians()
     d = Scene().load_file(test_ply, 30.0, sh_layout="interleaved").read_gaussians()
     assert np.array_equal(c["sh"], d["sh"])
+
+
+def test_stripe_delivery_to_host_assembles_the_frame():
+    """Tile sharding, host delivery: every rank renders its 32-column stripes into a local device image and copies
+    exactly those stripes into ONE page-locked host image (rtgs_copy_stripes_d2h: one strided DMA, plus the ragged
+    last stripe); the host image assembled from 3 'ranks' equals the single full render bit for bit, and a rank never
+    touches a foreign stripe.  Then the same through rtgs.sharding.HostFrame (shared-memory image + host flags)."""
+    import ctypes as C
+    import torch
+    from rtgs import _native
+    from rtgs.ray_tracer import RayTracer
+    from rtgs.sharding import HostFrame, stripe_columns
+    lib = _native.load()
+    gs = random_set(3000, seed=14, mean_scale=0.03)
+    scene = make_scene(gs)
+    W, H = 200, 72                                # 6 full stripes + one of 8 columns
+    cam, _ = make_camera(0.9, 1.2, 2.4, W, H)
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    want = rt.render_device(16).cpu().numpy()
+    dev = torch.cuda.current_device()
+    stream = torch.cuda.current_stream().cuda_stream
+    host = _native.PinnedBuffer((W, H, 3))
+    img = host.view()
+    img[:] = -7.0
+    for world in (3, 1, 8):
+        img[:] = -7.0
+        for r in range(world):
+            scene.set_stripe(world, r)
+            part = torch.full((W, H, 3), -9.0, dtype=torch.float32, device="cuda")
+            rt.render_device(16, out=part)
+            _native.check(lib.rtgs_copy_stripes_d2h(dev, host.ptr, part.data_ptr(), W, H, world, r, stream))
+            torch.cuda.synchronize()
+            done = np.concatenate([stripe_columns(W, q, world) for q in range(r + 1)])
+            rest = np.setdiff1d(np.arange(W), done)
+            assert np.array_equal(img[done], want[done]) and (img[rest] == -7.0).all(), (world, r)
+        assert np.array_equal(img, want)
+    scene.set_stripe()
+    # HostFrame with one rank: deliver / wait / release over more frames than buffers
+    hf = HostFrame(W, H, 0, 1, dev, None, buffers=2)
+    full = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
+    for k in range(5):
+        rt.render_device(16, out=full)
+        hf.deliver(full)
+        got = hf.wait()
+        assert np.array_equal(got, want), k
+        hf.release()
+    hf.close()
+
+
+def test_compact_host_delivery_matches_the_float32_frame():
+    """Opt-in compact delivery (rtgs_render_host_submit_packed): the frame is rendered in float32 as always and
+    converted on the device; "f16" equals numpy's round-to-nearest-even cast of the float32 image, "rgba8" equals the
+    clip / scale / round of the reference's display path (alpha 255).  The float32 path is untouched."""
+    from rtgs.ray_tracer import RayTracer
+    gs = random_set(2500, seed=15, mean_scale=0.05)
+    gs.color[:200] = 3.0                          # some colours beyond 1: the 8-bit format must clip
+    scene = make_scene(gs)
+    cam, _ = make_camera(0.3, 1.1, 2.4, 104, 57)    # odd pixel count: the half2 tail path
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    f32 = rt.render(16).copy()
+    a = rt.render_async(16, fmt="f16").result().copy()
+    b = rt.render_async(16, fmt="rgba8").result().copy()
+    c = rt.render_async(16).result().copy()
+    assert a.dtype == np.float16 and a.shape == (104, 57, 3) and np.array_equal(a, f32.astype(np.float16))
+    want8 = (np.clip(f32, 0.0, 1.0) * np.float32(255.0) + np.float32(0.5)).astype(np.uint8)
+    assert b.dtype == np.uint8 and b.shape == (104, 57, 4)
+    assert np.array_equal(b[..., :3], want8) and (b[..., 3] == 255).all() and (f32.max() > 1.0)
+    assert np.array_equal(c, f32)
+    # pipelined, mixed with float32 frames of another pose
+    from rtgs.orbit import orbit_pose
+    frames = []
+    for k, fmt in enumerate(("rgba8", "f32", "f16", "rgba8")):
+        cam.position, cam.rotation = orbit_pose(0.3 + 0.2 * k, 1.1, 2.4)
+        frames.append((fmt, np.asarray(rt.render(16)).copy()))
+    pend = []
+    for k, (fmt, ref) in enumerate(frames):
+        cam.position, cam.rotation = orbit_pose(0.3 + 0.2 * k, 1.1, 2.4)
+        pend.append((fmt, ref, rt.render_async(16, fmt=fmt)))
+        if len(pend) == 2:
+            fmt0, ref0, p0 = pend.pop(0)
+            got = p0.result()
+            if fmt0 == "f32":
+                assert np.array_equal(got, ref0)
+            elif fmt0 == "f16":
+                assert np.array_equal(got, ref0.astype(np.float16))
+            else:
+                assert np.array_equal(got[..., :3], (np.clip(ref0, 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8))
+    pend[0][2].result()
