@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""bench.py — Mrays/s of the fused per-ray render path (BASELINE.json metric).
+"""bench.py — Mrays/s of the per-ray render path (BASELINE.json metric).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
 
@@ -7,21 +7,30 @@ Workload (config 3 of BASELINE.json, the one the metric is quoted on): synthetic
 Gaussians, SH degree 3, seed 1002, 1920x1080, vertical fov 60 deg, orbit radius 2.2, depth 16.
 A "step" = ONE full 1080p frame (ray generation + LBVH traversal + intersection + 16-nearest
 k-buffer + SH compositing + framebuffer write) of one view of the 64-view orbit (config 5); the
-step s on rank r renders view (s*N + r) mod 64, view 0 being config 3's camera.  Multi-GPU is
-view-sharded with the scene replicated on every GPU and no collective on the data path, so
-per-GPU work is fixed as N grows ("scaling": "weak").  One ray = one finished pixel.
+step s on rank r renders view (s*N + r) mod 64, view 0 being config 3's camera.  One ray = one finished pixel.
 
-value  = whole-job Mrays/s with everything resident in HBM (device-timed, CUDA events, max over ranks)
+Multi-GPU (one process per GPU, scene replicated, NO collective on the data path):
+  views  (value, e2e; "scaling": "weak")  rank r renders its views; at N > 1 every rank's kernels store their frame
+         straight into GPU 0's memory over NVLink (rtgs.sharding.PeerFrame) and GPU 0 waits for the device-side
+         arrival counters, so a step ends with all N frames resident on GPU 0
+  tiles  ("tiles": BASELINE config 3; "tiles_config4": config 4 at 8 GPUs) every frame is cut into 32-column stripes
+         dealt round-robin; strong scaling of one frame, speed-up against rank 0 rendering the whole frame alone in
+         the same process, bit-identity checked, slowest kernel named per rank
+
+value  = whole-job Mrays/s with everything resident in HBM: K steps alternating on two CUDA streams (two frames in
+         flight per GPU, the way the sweep API runs), CUDA events around both, max over ranks;
+         serial_value = the same K steps on one stream (this loop also carries the per-kernel events)
 e2e    = the same through the public API with HOST buffers: the orbit sweep as a user writes it with
          RayTracer.render_async()/result() (camera struct in, image delivered to pinned host memory, every step,
-         inside the timed region; two frames in flight so that step s+1 renders while the tail of step s crosses
-         PCIe); e2e.sync_value = the same loop with the blocking RayTracer.render()
+         inside the timed region; two frames in flight) or the blocking RayTracer.render() loop, whichever is faster
+         (both reported); e2e.compact = the opt-in 8-bit delivery
 roofline = the dominant kernel, k_shade_tiles (intersection + k-buffer + SH compositing): algorithmic bytes per
          ray (16 + kbar*(64 + 192[sh]), all of them consumed by this kernel) x rays per launch /
          its mean duration, measured with CUDA events the library records around each kernel on the render
-         stream during the timed region, against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
+         stream during the serial timed loop, against the measured HBM copy bandwidth in MEASURED_PEAKS.json;
          "kernels" lists every kernel of the step with its mean time and share
-cpu_baseline = oracle/ref_cpu.cpp (reference-shaped C++/OpenMP port, float32) on a pixel subsample
+cpu_baseline = oracle/ref_cpu.cpp (reference-shaped C++/OpenMP port, float32, every core this process may use)
+         on a pixel subsample
 """
 from __future__ import annotations
 
@@ -319,7 +328,7 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
         per_rank = allgather(dist, torch, kt.tolist(), world)
         per_mode[mode] = {"ms_per_frame": lat, "ms_per_frame_two_streams": pipe, "kernel_names": list(scene.kernel_names),
                           "kernels_ms_per_rank": [[round(v, 5) for v in r] for r in per_rank]}
-    best = min(per_mode, key=lambda m: per_mode[m]["ms_per_frame_two_streams"])
+    best = min(per_mode, key=lambda m: min(per_mode[m]["ms_per_frame_two_streams"], per_mode[m]["ms_per_frame"]))
     scene.set_option("render_mode", best)
 
     # ---- untimed check: the assembled frame == rank 0's own full-frame render, bit for bit
@@ -397,12 +406,15 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
     k = b["kernels_ms_per_rank"]
     kmax = [max(r[i] for r in k) for i in range(3)]
     dom = int(np.argmax(kmax))
+    tput = min(b["ms_per_frame_two_streams"], b["ms_per_frame"])     # frames per second of a sweep: the better schedule
     res = {"resolution": [W, H], "frames": steps, "render_mode": best,
-           "ms_per_frame": b["ms_per_frame_two_streams"], "mrays": W * H / b["ms_per_frame_two_streams"] / 1e3,
-           "ms_per_frame_latency": b["ms_per_frame"],
+           "ms_per_frame": tput, "mrays": W * H / tput / 1e3,
+           "schedule": "two streams (two frames in flight per GPU)" if b["ms_per_frame_two_streams"] <= b["ms_per_frame"]
+                       else "one stream (one frame in flight per GPU)",
+           "ms_per_frame_latency": min(v["ms_per_frame"] for v in per_mode.values()),
            "ms_per_frame_1gpu": t1_pipe, "ms_per_frame_1gpu_latency": t1_lat,
-           "speedup_vs_n1": t1_pipe / b["ms_per_frame_two_streams"],
-           "speedup_vs_n1_latency": t1_lat / b["ms_per_frame"],
+           "speedup_vs_n1": t1_pipe / tput,
+           "speedup_vs_n1_latency": t1_lat / min(v["ms_per_frame"] for v in per_mode.values()),
            "verified_bit_identical": verified,
            "limiting_kernel": {"name": b["kernel_names"][dom], "slowest_rank_ms": kmax[dom],
                                "per_rank_ms": [r[dom] for r in k],
@@ -519,11 +531,14 @@ def main():
 
     # stats pass (untimed): kbar, hit fraction, traversal counters for the timed views (whole frames)
     agg = {}
+    stack_hw = [0, 0, 0]
     for s in range(min(args.steps, n_views)):
         set_view(s)
         rt.render_device(DEPTH, out=out, collect_stats=True)
         for k, v in rt.last_stats.items():
             agg[k] = agg.get(k, 0) + v
+        stack_hw = [max(a, rt.last_stats[k]) for a, k in zip(stack_hw, ("max_lists_stack", "max_fused_stack", "max_group_list"))]
+    tree_depth = scene.get_option("tree_depth")
     kbar = agg["layers"] / agg["rays"]
     bytes_ray = 16 + kbar * (64 + (192 if sh_deg > 0 else 0))
 
@@ -563,10 +578,29 @@ def main():
         launches += launches_per_frame
     e_end.record()
     barrier()
-    total_ms = e_beg.elapsed_time(e_end)
+    serial_ms = e_beg.elapsed_time(e_end)
     kern_ms = [a.elapsed_time(b) for a, b in ev]
     per_kernel = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)   # ms of the frame's launches
     scene.set_option("kernel_timing", 0)
+
+    # The throughput figure: the same K steps with frames alternating on two streams.  Frames on different streams
+    # use separate frame scratch in the library (csrc/render.cu), so the head of step s+1 (its traversal kernel)
+    # fills the SMs that the tail of step s leaves idle - the way the sweep API (render_async) runs.  Device-timed
+    # with events on the default stream around both streams' work.
+    ts = TwoStreams(torch)
+    for s in range(args.warmup):
+        set_view(s)
+        with ts.stream(s):
+            render_step()
+    barrier()
+    e0 = ts.begin()
+    for s in range(args.steps):
+        set_view(s)
+        with ts.stream(s):
+            render_step()
+    e1 = ts.end()
+    barrier()
+    total_ms = e0.elapsed_time(e1)
 
     # end-to-end: public API call with host buffers (camera in, image out on the host), every rank its own frames
     def blocking(n):
@@ -574,14 +608,14 @@ def main():
             set_view(s)
             rt.render(DEPTH)
 
-    def pipelined(n):
+    def pipelined(n, fmt="f32"):
         # the sweep API: every step still uploads its camera and delivers its image to pinned host memory, but
         # two frames are in flight (RayTracer.render_async), so step s+1 renders while step s is copied out.
         # Every image is collected inside the timed region.
         prev = None
         for s in range(n):
             set_view(s)
-            cur = rt.render_async(DEPTH)
+            cur = rt.render_async(DEPTH, fmt=fmt)
             if prev is not None:
                 prev.result()
             prev = cur
@@ -597,6 +631,8 @@ def main():
 
     e2e_sync_s = wall(blocking, args.steps)
     e2e_pipe_s = wall(pipelined, args.steps)
+    # opt-in compact delivery (the frame is still rendered in float32; 4 instead of 12 bytes per pixel cross PCIe)
+    e2e_rgba8_s = wall(lambda n: pipelined(n, "rgba8"), args.steps)
     # the sampler has been running through all timed loops (device-timed steps and both end-to-end loops)
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
@@ -607,8 +643,8 @@ def main():
     e2e_kernels = scene.read_kernel_times(timed_frames).astype(np.float64).mean(axis=0)
     scene.set_option("kernel_timing", 0)
 
-    total_ms, e2e_pipe_s, e2e_sync_s, kern_mean, *pk = allmax(
-        dist, torch, [total_ms, e2e_pipe_s, e2e_sync_s, float(np.mean(kern_ms)), *per_kernel.tolist()])
+    total_ms, serial_ms, e2e_pipe_s, e2e_sync_s, e2e_rgba8_s, kern_mean, *pk = allmax(
+        dist, torch, [total_ms, serial_ms, e2e_pipe_s, e2e_sync_s, e2e_rgba8_s, float(np.mean(kern_ms)), *per_kernel.tolist()])
     per_kernel = np.asarray(pk)
 
     # ------------------------------------------------------------------ strong scaling: tile-sharded frames
@@ -650,6 +686,9 @@ def main():
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak",
+            "timing": "K steps alternating on two CUDA streams (two frames in flight per GPU), CUDA events on the "
+                      "default stream around both, max over ranks; serial_* = the same K steps on one stream",
+            "serial_value": rays_step * args.steps / (serial_ms * 1e-3) / 1e6, "serial_ms_per_step": serial_ms / args.steps,
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_val, "unit": "Mrays/s", "h2d_bytes_per_step": 44 * world,
                     "d2h_bytes_per_step": W * H * 3 * 4 * world,
@@ -660,6 +699,11 @@ def main():
                     "pipelined_value": rays_step * args.steps / e2e_pipe_s / 1e6,
                     "sync_value": rays_step * args.steps / e2e_sync_s / 1e6,
                     "sync_api": "RayTracer.render() per step (blocking)",
+                    "compact": {"format": "rgba8", "value": rays_step * args.steps / e2e_rgba8_s / 1e6,
+                                "d2h_bytes_per_step": W * H * 4 * world,
+                                "api": "RayTracer.render_async(fmt='rgba8'): same float32 render, the image is clipped "
+                                       "and rounded to 8 bits per channel on the device before the DMA (opt-in; "
+                                       "not the parity path, not the headline)"},
                     "kernels_ms": [round(float(v), 5) for v in e2e_kernels]},
             "gpu_launches": launches,
             "render_mode": base_mode,
@@ -679,7 +723,9 @@ def main():
                             "traversal_steps_per_tile": agg["traversal_steps"] / max(agg["tiles"], 1),
                             "insert_rounds_per_tile": agg["insert_rounds"] / max(agg["tiles"], 1),
                             "useful_candidates_per_tile": agg["useful_candidates"] / max(agg["tiles"], 1),
-                            "fallback_tiles": agg["fallback_tiles"]},
+                            "fallback_tiles": agg["fallback_tiles"],
+                            "stack_high_water": {"lists": stack_hw[0], "fused": stack_hw[1], "group_list": stack_hw[2],
+                                                 "capacity": [256, 512, 960], "tree_depth": tree_depth}},
             "bvh_build_ms": bvh_build_ms,            # device time of the LBVH build kernels
             "morton_bits": morton_bits,
             "scene_load_ms": build_ms,               # wall: upload of the arrays + build (+ CUDA start-up on first use)

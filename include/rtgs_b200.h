@@ -64,6 +64,12 @@ typedef struct rtgs_render_stats {
     uint64_t insert_rounds;      /* warp-wide k-buffer insertion rounds */
     uint64_t fallback_tiles;     /* tiles rendered by the fused kernel because their list did not fit the pool */
     uint64_t useful_candidates;  /* staged candidates that passed the coarse test for at least one ray */
+    /* high-water marks of the render (maxima over all warps): the traversal stacks are bounded by construction
+     * (256 entries in the list traversal, 512 in the fused kernel, for trees up to 96 levels deep);
+     * these let a test assert the bounds on the device */
+    uint64_t max_lists_stack;    /* deepest stack of the list traversal (entries) */
+    uint64_t max_fused_stack;    /* deepest stack of the fused kernel (entries) */
+    uint64_t max_group_list;     /* longest shared-memory candidate list of an 8x16-pixel group (<= 960) */
 } rtgs_render_stats;
 
 const char* rtgs_last_error(void);

@@ -9,7 +9,7 @@ Modules
 -------
 ref_numpy   float64 brute-force image oracle (no BVH) + loader activations + orbit camera.
 lbvh_ref    integer Morton-30 / sort-key / Karras-hierarchy specification in NumPy.
-scenes      synthetic scene generator + binary PLY reader/writer used by tests and bench.
+ref_cpu     ctypes wrapper of ref_cpu.cpp.
 ref_cpu.cpp C++/OpenMP restatement with the reference's algorithm shape (K closest-hit
             restarts over a BVH); float = timed CPU baseline, double = large-scene oracle.
 taichi_shim a pure-Python stand-in for the subset of Taichi the reference uses, so that the

@@ -138,7 +138,7 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->leafbox, n * 2));
     TRY(dev_alloc(&s->nodes4, s->num_nodes * 8));
-    TRY(dev_alloc(&s->stats_dev, 12));
+    TRY(dev_alloc(&s->stats_dev, 16));
     return RTGS_OK;
 }
 
@@ -417,12 +417,13 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
     TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_image_pitch, out_rgb, out_T, st,
                            stats != nullptr));
     if (stats) {
-        unsigned long long hs[12];
+        unsigned long long hs[16];
         CUDA_TRY(cudaMemcpyAsync(hs, s->stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
         stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
         stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->fallback_tiles = hs[10]; stats->useful_candidates = hs[11];
+        stats->max_lists_stack = hs[12]; stats->max_fused_stack = hs[13]; stats->max_group_list = hs[14];
     }
     return RTGS_OK;
 }

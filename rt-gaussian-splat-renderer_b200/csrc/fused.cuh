@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     grant_begin(P, grant);
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
+    unsigned st_max_stack = 0;
 #define ST(expr) do { if (STATS) { expr; } } while (0)
 
 #pragma unroll 1
@@ -202,6 +203,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 const int ncqa = ncq + __popc(mL0);
                 if (h1 && c1 < 0) tr.cq[ncqa + __popc(mL1 & lt_mask)] = ~c1;
                 ncq = ncqa + __popc(mL1);
+                ST(st_max_stack = max(st_max_stack, (unsigned)top));
                 __syncwarp();
             }
             // -------- candidate batch: stage (one lane each, float64) then test (all lanes) --
@@ -489,6 +491,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
             for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
             if (lane == 0 && x) atomicAdd(P.stats + k, x);
         }
+        if (lane == 0) atomicMax(P.stats + ST_MAX_FUSED_STACK, (unsigned long long)st_max_stack);
     }
     if (P.final_kernel) cta_finish(P, P.use_fallback_list == 1 ? CTR_DONE3 : CTR_DONE2);
 }

@@ -66,6 +66,8 @@ __device__ __forceinline__ void flush_lists_stats(const RenderParams& P, const L
         if (S.st_nodes) atomicAdd(P.stats + ST_NODES, S.st_nodes);
         if (S.st_steps) atomicAdd(P.stats + ST_STEPS, S.st_steps);
         if (S.st_cands) atomicAdd(P.stats + ST_CANDS, S.st_cands);
+        atomicMax(P.stats + ST_MAX_LISTS_STACK, (unsigned long long)S.st_max_stack);
+        atomicMax(P.stats + ST_MAX_GROUP_LIST, (unsigned long long)S.st_max_list);
     }
 }
 template <bool STATS>
@@ -691,7 +693,7 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
     const bool self_clean = mode == 2;
     if (!self_clean || fs.counters_dirty) CUDA_TRY(cudaMemsetAsync(fs.counters, 0, CTR_COUNT * sizeof(unsigned int), stream));
     fs.counters_dirty = !self_clean;
-    if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), stream));
+    if (want_stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_TOTAL * sizeof(unsigned long long), stream));
 
     // optional per-kernel timing: events e[0..3] of this frame's ring slot bracket up to three launches
     cudaEvent_t* ev = nullptr;
@@ -775,7 +777,7 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
     P.final_kernel = 1;
     static const bool stats_fallback_only = getenv("RTGS_STATS_FALLBACK_ONLY") != nullptr;   // diagnostic
     if (want_stats && stats_fallback_only)
-        CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_COUNT * sizeof(unsigned long long), stream));
+        CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, ST_TOTAL * sizeof(unsigned long long), stream));
     if ((r = fused_kernel(16)) != RTGS_OK) return r;
     if (ran) *ran = 7;
     return mark(3);

@@ -44,7 +44,11 @@ struct TileDesc {
 enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_DONE = 5, CTR_DONE2 = 6,
        CTR_FALLBACK2 = 7, CTR_WORK4 = 8, CTR_DONE3 = 9, CTR_COUNT = 16 };
 enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
-       ST_FALLBACK, ST_COUNT = 12 };
+       ST_FALLBACK, ST_USEFUL, ST_COUNT = 12,
+       // high-water marks (maxima, not sums; statistics builds only): deepest traversal stacks and the fullest group
+       // list seen - the stack bounds of tile_lists.cuh / fused.cuh checked on the device (compute-sanitizer is not
+       // available on the GPU pool, so the deep-tree tests assert these instead)
+       ST_MAX_LISTS_STACK = 12, ST_MAX_FUSED_STACK = 13, ST_MAX_GROUP_LIST = 14, ST_TOTAL = 16 };
 
 struct RenderParams {
     const float4* nodes;
@@ -138,11 +142,13 @@ __device__ __forceinline__ void frame_complete(const RenderParams& P) {
 }
 
 // End of a kernel: count the finished CTAs; returns true in thread 0 of the CTA that finishes last, with every
-// other CTA's stores ordered before it (fence - atomic - fence; system scope when another GPU will read them).
+// other CTA's stores ordered before it: each CTA's fence + atomic (device scope) synchronises with the last CTA's
+// atomic + fence, and causality order is transitive across scopes, so only the ONE system-scope release in
+// frame_complete is needed to publish all of them to another GPU (a system fence per CTA cost ~10 us per frame).
 __device__ __forceinline__ bool cta_is_last(const RenderParams& P, int ctr) {
     __syncthreads();
     if (threadIdx.x != 0) return false;
-    if (P.arrive) __threadfence_system(); else __threadfence();
+    __threadfence();
     const unsigned prev = atomicAdd(P.counters + ctr, 1u);
     if (prev + 1u != gridDim.x) return false;
     __threadfence();

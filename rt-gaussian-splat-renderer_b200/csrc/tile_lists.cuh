@@ -64,6 +64,7 @@ struct __align__(16) ListsShared {
 struct ListsState {
     int slab_next = 0, slab_end = 0;
     unsigned long long st_nodes = 0, st_steps = 0, st_cands = 0;
+    unsigned st_max_stack = 0, st_max_list = 0;     // high-water marks (statistics builds)
 };
 
 template <bool STATS>
@@ -196,6 +197,8 @@ __device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& 
                 break;
             }
             traverse_step(ws.stack, top, ws.glist, ng, fg);
+            ST(S.st_max_stack = max(S.st_max_stack, (unsigned)top));
+            ST(S.st_max_list = max(S.st_max_list, (unsigned)ng));
         }
     }
 
@@ -300,6 +303,7 @@ __device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& 
 #pragma unroll 1
             while (top > 0 && ok) {
                 traverse_step(ws.glist, top, ws.cq, ncq, fr);
+                ST(S.st_max_stack = max(S.st_max_stack, (unsigned)top));
 #pragma unroll 1
                 while (ncq >= CHUNK_IDS && ok) ok = write_chunk(ws.cq, CHUNK_IDS, ncq, head, count);
             }

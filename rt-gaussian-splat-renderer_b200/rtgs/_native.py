@@ -27,7 +27,8 @@ class rtgs_camera(C.Structure):
 class rtgs_render_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "rays_hit", "layers", "nodes_tested", "candidates",
                                           "pair_tests", "f64_refinements", "tiles", "traversal_steps",
-                                          "insert_rounds", "fallback_tiles", "useful_candidates")]
+                                          "insert_rounds", "fallback_tiles", "useful_candidates",
+                                          "max_lists_stack", "max_fused_stack", "max_group_list")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

@@ -5,6 +5,7 @@ writes profiles/TAG_ncu_summary.json, profiles/TAG_<kernel>_per_line.txt, profil
 import csv, io, json, re, subprocess, sys
 from pathlib import Path
 tag, rep, launches = sys.argv[1:4]
+opts = set(sys.argv[4:])     # "notraffic": keep render_kernel_traffic.json; "nolines": no per-line files; "merge": add to an existing summary
 root = Path(__file__).resolve().parent.parent
 prof = root / "profiles"
 METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_sector_hit_rate.pct",
@@ -42,15 +43,22 @@ for r in data:
         return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
     traffic[name] = {"dram_bytes_per_launch": mb("dram__bytes_read.sum") + mb("dram__bytes_write.sum"),
                      "source": f"profiles/{tag}_ncu_summary.json (ncu --set full --clock-control none, one launch)"}
-(prof / f"{tag}_ncu_summary.json").write_text(json.dumps(summary, indent=1))
-(prof / "render_kernel_traffic.json").write_text(json.dumps(traffic, indent=1))
+sp = prof / f"{tag}_ncu_summary.json"
+if "merge" in opts and sp.exists():
+    old = json.loads(sp.read_text())
+    old.update(summary)
+    summary = old
+sp.write_text(json.dumps(summary, indent=1))
+if "notraffic" not in opts:
+    (prof / "render_kernel_traffic.json").write_text(json.dumps(traffic, indent=1))
 # per-line
-for li, r in enumerate(data):
+for li, r in enumerate(data if "nolines" not in opts else []):
     name = re.sub(r"^void |\(.*$|<unnamed>::|<.*$", "", r[kcol])
     txt = subprocess.run([sys.executable, str(root / "scratch" / "ncu_lines.py"), rep, str(li), "45"], capture_output=True, text=True).stdout
     mem = subprocess.run([sys.executable, str(root / "scratch" / "ncu_mem.py"), rep, str(li), "20"], capture_output=True, text=True).stdout
     (prof / f"{tag}_{name}_per_line.txt").write_text("== instructions / stall samples per source line ==\n" + txt + "\n== memory traffic per source line ==\n" + mem)
 # launch list: keep our kernels only
-keep = [l for l in open(launches) if not l.startswith("==")]
-(prof / f"{tag}_launches.csv").write_text("".join(keep))
+if launches != "-":
+    keep = [l for l in open(launches) if not l.startswith("==")]
+    (prof / f"{tag}_launches.csv").write_text("".join(keep))
 print("wrote", sorted(p.name for p in prof.glob(tag + "*")), "render_kernel_traffic.json")

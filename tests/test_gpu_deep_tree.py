@@ -46,6 +46,17 @@ def test_sixteen_thousand_coincident_centres_render_and_hit():
         print(f"mode {mode}: max-abs {mx:.2e} psnr {ps:.1f}")
         assert mx <= TOL and ps >= 60.0, mode
     scene.set_option("render_mode", 0)
+    # the stack bounds, checked on the device (compute-sanitizer is not available on the GPU pool): high-water marks of
+    # the list traversal (256-entry stack, 960-entry group list) and of the fused kernel (512-entry stack)
+    rt.render_device(16, collect_stats=True)
+    st = rt.last_stats
+    print("high water: lists stack", st["max_lists_stack"], "group list", st["max_group_list"], "fused stack", st["max_fused_stack"])
+    assert 0 < st["max_lists_stack"] <= 256 and st["max_group_list"] <= 960 and st["max_fused_stack"] <= 512
+    assert st["fallback_tiles"] > 0                      # the pile overflows the group lists: the fused kernel ran
+    scene.set_option("render_mode", 1)
+    rt.render_device(16, collect_stats=True)
+    assert 0 < rt.last_stats["max_fused_stack"] <= 512
+    scene.set_option("render_mode", 0)
     # closest hit through the same deep tree (k_trace_closest: per-ray stack of depth + 2 entries)
     rays = cam.cam_ray_field.to_numpy().reshape(-1, 8)[::7]
     hit = scene.hit(rays)
@@ -78,6 +89,14 @@ def test_a_million_coincident_centres_stay_within_the_stack_bound():
         assert np.isfinite(imgs[mode]).all()
     assert np.array_equal(imgs[0], imgs[2])
     assert np.abs(imgs[1] - imgs[0]).max() <= 1e-5
+    for mode in (0, 1):
+        scene.set_option("render_mode", mode)
+        rt.render_device(16, collect_stats=True)
+        st = rt.last_stats
+        print(f"mode {mode} high water: lists stack {st['max_lists_stack']} group list {st['max_group_list']} "
+              f"fused stack {st['max_fused_stack']}")
+        assert st["max_lists_stack"] <= 256 and st["max_group_list"] <= 960 and 0 < st["max_fused_stack"] <= 512
+    scene.set_option("render_mode", 0)
     rays = cam.cam_ray_field.to_numpy().reshape(-1, 8)
     hit = scene.hit(rays)
     assert (hit.gaussian_idx >= 0).any()
