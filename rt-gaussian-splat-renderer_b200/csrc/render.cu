@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
         if (lane == 0) group = (int)atomicAdd(P.counters + CTR_WORK, 1u);
         group = work_to_id(P, __shfl_sync(FULL, group, 0), P.macro_cols * GROUPS_PER_MACRO, ngroups);
         if (group >= ngroups) break;
-        lists_group<STATS>(P, ws, S, group, lane);
+        int gi0, gj0;
+        if (!group_origin(P, group, gi0, gj0) || gi0 >= P.x0 + P.w || gj0 >= P.y0 + P.h) continue;
+        lists_group<STATS>(P, ws, S, group, gi0, gj0, lane);
     }
     flush_lists_stats<STATS>(P, S, lane);
 }
@@ -183,8 +185,10 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_frame(const __gri
             int group = 0;
             if (lane == 0) group = (int)atomicAdd(P.counters + CTR_WORK, 1u);
             group = work_to_id(P, __shfl_sync(FULL, group, 0), P.macro_cols * GROUPS_PER_MACRO, ngroups);
+            int gi0, gj0;
             if (group >= ngroups) groups_left = false;
-            else lists_group<STATS>(P, ws.lists, LS, group, lane);
+            else if (group_origin(P, group, gi0, gj0) && gi0 < xe && gj0 < ye)
+                lists_group<STATS>(P, ws.lists, LS, group, gi0, gj0, lane);
         }
 #pragma unroll 1
         for (int k = 0; k < TILES_PER_GROUP && tiles_left; ++k) {

@@ -67,14 +67,15 @@ struct ListsState {
     unsigned st_max_stack = 0, st_max_list = 0;     // high-water marks (statistics builds)
 };
 
+// `group` is a group of this launch whose pixel origin (gi0, gj0) lies inside the rendered region (the caller has
+// checked group_origin: nobody waits for any other group).
 template <bool STATS>
-__device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& ws, ListsState& S, int group, int lane) {
+__device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& ws, ListsState& S, int group, int gi0,
+                                            int gj0, int lane) {
     const unsigned lt_mask = (1u << lane) - 1u;
     const CamD& cam = P.cam;
     const int xe = P.x0 + P.w, ye = P.y0 + P.h;
 #define ST(expr) do { if (STATS) { expr; } } while (0)
-    int gi0, gj0;
-    if (!group_origin(P, group, gi0, gj0) || gi0 >= xe || gj0 >= ye) return;   // nobody waits for such a group
 
     // one traversal step, two tree levels deep (see the header comment)
     auto traverse_step = [&](int* stk, int& top, int* dst, int& nd, const Frustum& fr) {
