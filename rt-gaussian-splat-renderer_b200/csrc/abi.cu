@@ -50,6 +50,8 @@ void free_scene(rtgs_scene* s) {
     cudaFree(s->pos); cudaFree(s->rot); cudaFree(s->scale); cudaFree(s->color); cudaFree(s->opacity);
     cudaFree(s->sh); cudaFree(s->morton); cudaFree(s->sorted_idx); cudaFree(s->child); cudaFree(s->parent);
     cudaFree(s->morton64);
+    if (s->shp_tex) cudaDestroyTextureObject(s->shp_tex);
+    if (s->geo_tex) cudaDestroyTextureObject(s->geo_tex);
     cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
     for (auto& fs : s->scratch) {
         cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.fallback_tiles2); cudaFree(fs.ready);
@@ -133,7 +135,37 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->parent, 2 * n - 1));
     TRY(dev_alloc(&s->aabb, (2 * n - 1) * 6));
     TRY(dev_alloc(&s->geo, n * 4));
-    if (has_sh) TRY(dev_alloc(&s->shp, n * 12));
+#if SHADE_GEO_TEX
+    {
+        cudaResourceDesc rd = {};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = s->geo;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = (size_t)n * 4 * sizeof(float4);
+        cudaTextureDesc td = {};
+        td.readMode = cudaReadModeElementType;
+        CUDA_TRY(cudaCreateTextureObject(&s->geo_tex, &rd, &td, nullptr));
+    }
+#endif
+    if (has_sh) {
+        // the SH records and a linear float4 texture over them (eval_colour fetches part of a record through the
+        // texture path: the LSU pipe bounds the shading, the TEX pipe has throughput to spare)
+        TRY(dev_alloc(&s->shp, n * 12));
+        if (n <= rtgs_dev::SH_TEX_MAX_RECORDS || !SHADE_SH_TEX_RUNTIME) {
+            if (n > rtgs_dev::SH_TEX_MAX_RECORDS) {
+                rtgs_set_error("too many Gaussians with SH for the record texture (%lld)", (long long)n);
+                return RTGS_ERR_INVALID;
+            }
+            cudaResourceDesc rd = {};
+            rd.resType = cudaResourceTypeLinear;
+            rd.res.linear.devPtr = s->shp;
+            rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+            rd.res.linear.sizeInBytes = (size_t)n * 12 * sizeof(float4);
+            cudaTextureDesc td = {};
+            td.readMode = cudaReadModeElementType;
+            CUDA_TRY(cudaCreateTextureObject(&s->shp_tex, &rd, &td, nullptr));
+        }
+    }
     TRY(dev_alloc(&s->raw, n * 3));
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->leafbox, n * 2));

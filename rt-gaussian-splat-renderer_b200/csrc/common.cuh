@@ -83,6 +83,8 @@ struct rtgs_scene {
     // packed render records
     float4* geo = nullptr;
     float4* shp = nullptr;
+    cudaTextureObject_t geo_tex = 0;   // (experiment) geo as a linear float4 texture
+    cudaTextureObject_t shp_tex = 0;   // shp as a linear float4 texture (eval_colour); 0 when the scene exceeds one texture
     float4* raw = nullptr;
     float4* nodes = nullptr;
     float4* leafbox = nullptr;   // n*2: leaf box (centre, half extent) by sorted position

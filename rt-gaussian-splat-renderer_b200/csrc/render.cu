@@ -633,6 +633,8 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
     P.nodes4 = s->nodes4;
     P.geo = s->geo;
     P.shp = s->shp;
+    P.shp_tex = s->shp_tex;
+    P.geo_tex = s->geo_tex;
     P.raw = s->raw;
     P.leafbox = s->leafbox;
     P.cam = make_camd(cam);

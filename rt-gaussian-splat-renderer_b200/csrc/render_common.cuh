@@ -55,6 +55,9 @@ struct RenderParams {
     const float4* nodes4;     // two-level nodes (k_tile_lists)
     const float4* geo;
     const float4* shp;
+    cudaTextureObject_t geo_tex;   // (experiment SHADE_GEO_TEX) the geometry records as a linear float4 texture
+    cudaTextureObject_t shp_tex;   // the same records as a linear float4 texture, or 0 (too many for one texture): eval_colour
+                                   // fetches part of a record through the texture path, the rest with 256-bit loads
     const float4* raw;
     const float4* leafbox;
     CamD cam;
@@ -432,8 +435,16 @@ __device__ __forceinline__ void stage_candidate(const RenderParams& P, const Til
                                                 float (&poly)[6]) {
     const CamD& cam = P.cam;
     float4 g0, g1, g2, g3;
+#if SHADE_GEO_TEX
+    {   // experiment: the 64-byte geometry record through the texture path as well
+        const int t0 = s * 4;
+        g0 = tex1Dfetch<float4>(P.geo_tex, t0); g1 = tex1Dfetch<float4>(P.geo_tex, t0 + 1);
+        g2 = tex1Dfetch<float4>(P.geo_tex, t0 + 2); g3 = tex1Dfetch<float4>(P.geo_tex, t0 + 3);
+    }
+#else
     ldg256(P.geo + (int64_t)s * 4 + 0, g0, g1);
     ldg256(P.geo + (int64_t)s * 4 + 2, g2, g3);
+#endif
     const double W00 = g1.x, W01 = g1.y, W02 = g1.z, W10 = g1.w, W11 = g2.x, W12 = g2.y, W20 = g2.z, W21 = g2.w,
                  W22 = g3.x;
     auto Wmul = [&](const d3& v) {
@@ -532,6 +543,17 @@ __device__ __forceinline__ PreciseHit precise_test(const RenderParams& P, const 
     return h;
 }
 
+#ifndef SHADE_SH_TEX
+#define SHADE_SH_TEX 8     // quads (of 12) of an SH record fetched through the texture path; even.  Measured on the
+#endif                     // bench scene (k_shade_tiles): 0 -> 0.585 ms, 4 -> 0.554, 6 -> 0.544, 8 -> 0.536, 10 -> 0.537, 12 -> 0.551
+#ifndef SHADE_GEO_TEX
+#define SHADE_GEO_TEX 0
+#endif
+#ifndef SHADE_SH_TEX_RUNTIME
+#define SHADE_SH_TEX_RUNTIME 1   // 1: scenes too large for one linear texture fall back to loads at run time (P.shp_tex == 0)
+#endif
+constexpr long long SH_TEX_MAX_RECORDS = (1ll << 27) / 12;   // one linear texture holds 2^27 texels
+static_assert(SHADE_SH_TEX >= 0 && SHADE_SH_TEX <= 12 && SHADE_SH_TEX % 2 == 0, "SHADE_SH_TEX: even, 0..12");
 // rgb = color + eval_sh(normalize(dir))  (gaussian.py:199-200) of the Gaussian at sorted position s.
 // With SH the 192-byte record holds the 45 coefficients followed by the DC colour.
 __device__ __forceinline__ void eval_colour(const RenderParams& P, int s, const float (&Y)[15], float& r, float& g,
@@ -539,8 +561,32 @@ __device__ __forceinline__ void eval_colour(const RenderParams& P, int s, const 
     if (P.has_sh) {
         const float4* sp = P.shp + (int64_t)s * 12;
         float v[48];
+        // The record comes in through BOTH L1 front ends: the first SHADE_SH_TEX quads as 16-byte texture fetches (TEX
+        // pipe, a linear float4 texture over the same memory; tex1Dfetch is cheaper than a 2-D fetch: 0.536 vs 0.560 ms),
+        // the rest as 256-bit loads (LSU pipe).  The LSU pipe is what bounds the shading (shared-memory gathers + these
+        // loads: 85 % busy before); the texture path has wavefront throughput of its own.  The handle must be
+        // warp-uniform (a per-lane choice among several textures made the fetches 35 % slower than no texture at
+        // all), so scenes beyond one linear texture (2^27 texels = 11 M records) take the all-LSU path.
+#if SHADE_SH_TEX_RUNTIME
+        if (P.shp_tex == 0) {
 #pragma unroll
-        for (int f = 0; f < 6; ++f) {
+            for (int f = 0; f < SHADE_SH_TEX / 2; ++f) {
+                float4 x, y;
+                ldg256(sp + 2 * f, x, y);
+                v[8 * f] = x.x; v[8 * f + 1] = x.y; v[8 * f + 2] = x.z; v[8 * f + 3] = x.w;
+                v[8 * f + 4] = y.x; v[8 * f + 5] = y.y; v[8 * f + 6] = y.z; v[8 * f + 7] = y.w;
+            }
+        } else
+#endif
+        {
+#pragma unroll
+            for (int f = 0; f < SHADE_SH_TEX; ++f) {
+                const float4 x = tex1Dfetch<float4>(P.shp_tex, s * 12 + f);
+                v[4 * f] = x.x; v[4 * f + 1] = x.y; v[4 * f + 2] = x.z; v[4 * f + 3] = x.w;
+            }
+        }
+#pragma unroll
+        for (int f = SHADE_SH_TEX / 2; f < 6; ++f) {
             float4 x, y;
             ldg256(sp + 2 * f, x, y);
             v[8 * f] = x.x; v[8 * f + 1] = x.y; v[8 * f + 2] = x.z; v[8 * f + 3] = x.w;

@@ -184,6 +184,13 @@ class PeerFrame:
         """The tensor of the frame begun last (on rank 0: complete after ``wait()``)."""
         return self._images[self.frames % self.buffers][slot]
 
+    @staticmethod
+    def uses_of_buffer(frame: int, buffers: int) -> int:
+        """How many of the frames 1 .. `frame` (this one included) went into the buffer frame `frame` uses
+        (frame f uses buffer f % buffers): what every rank's arrive counter of that buffer must have reached."""
+        b = frame % buffers
+        return len(range(b if b else buffers, frame + 1, buffers))
+
     def wait(self, stream=None):
         """Rank 0: make `stream` (default: torch's current stream) wait until every rank's part of the frame begun
         last has landed."""
@@ -191,7 +198,7 @@ class PeerFrame:
         assert self.rank == 0
         f = self.frames
         b = f % self.buffers
-        uses = len(range(b if b else self.buffers, f + 1, self.buffers))   # frames that have used buffer b, this one included
+        uses = self.uses_of_buffer(f, self.buffers)
         st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
         from . import _native
         _native.check(self._lib.rtgs_stream_wait_counter(self.device, self._arrive(b), self.world * uses, st))

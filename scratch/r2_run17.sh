@@ -1,0 +1,12 @@
+#!/bin/bash
+L=$PWD/rt-gaussian-splat-renderer_b200/lib
+fmt='
+import sys,json
+for x in sys.stdin:
+    if x.startswith("{"):
+        d=json.loads(x); print(sys.argv[1], "value", round(d["value"],1), "serial", round(d["serial_value"],1), "e2e", round(d["e2e"]["value"],1), [(k["kernel"], round(k["ms"],4)) for k in d["kernels"]])
+'
+for n in 4 6 8 10 12; do
+RTGS_SH_TEX=1 RTGS_B200_LIB=$L/lib_tex$n.so timeout 600 python bench.py --steps 64 --warmup 5 --no-cpu-baseline --no-tiles 2> gpurun_out/r2_b17_$n.err | python -c "$fmt" sh_tex_$n >> gpurun_out/r2_ab17.log
+done
+cat gpurun_out/r2_ab17.log
