@@ -134,10 +134,8 @@ __device__ __forceinline__ void grant_wait(const RenderParams& P, PeerGrant& g) 
 // The frame is complete (call from ONE thread, after every CTA of the frame's last kernel has finished its stores):
 // hand-over signal for whoever gathers the frame, then the work counters are zeroed for the next frame.
 __device__ __forceinline__ void frame_complete(const RenderParams& P) {
-    if (P.arrive) {
-        __threadfence_system();
+    if (P.arrive)   // (the release covers everything cta_is_last has ordered before this thread)
         asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(P.arrive) : "memory");
-    }
     if (P.self_clean) {
 #pragma unroll
         for (int k = 0; k < CTR_COUNT; ++k) P.counters[k] = 0u;
