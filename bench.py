@@ -309,33 +309,49 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
     peer = PeerFrame(W, H, rank, world, local_rank, dist, slots=1, buffers=4)
     scene.set_stripe(world, rank)
 
+    local = [torch.empty((W, H, 3), dtype=torch.float32, device="cuda") for _ in range(2)]
+
     def tile_step(s, _):
+        # gather by STORES: the render kernels write their stripes into rank 0's frame over NVLink as they go
         rt.render_device(DEPTH, out=peer.begin(scene))
         if rank == 0:
             peer.wait()
             peer.release()
 
+    def tile_step_copy(s, _):
+        # gather by COPY: render into local memory, then one strided copy of the rank's stripes over NVLink
+        peer.begin_copy()
+        rt.render_device(DEPTH, out=local[s % 2])
+        peer.deliver_stripes(local[s % 2])
+        if rank == 0:
+            peer.wait()
+            peer.release()
+
     per_mode = {}
-    for mode in modes:
+    variants = [(m, "stores") for m in modes] + ([(modes[0], "copy")] if world > 1 else [])
+    for mode, gather in variants:
+        step = tile_step if gather == "stores" else tile_step_copy
         scene.set_option("render_mode", mode)
-        lat = timed(tile_step, False, warmup, steps)
-        pipe = timed(tile_step, True, warmup, steps)
+        lat = timed(step, False, warmup, steps)
+        pipe = timed(step, True, warmup, steps)
         scene.set_option("kernel_timing", min(steps, 256))
-        timed(tile_step, False, 0, min(steps, 256))
+        timed(step, False, 0, min(steps, 256))
         kt = scene.read_kernel_times(min(steps, 256)).astype(np.float64).mean(axis=0)
         scene.set_option("kernel_timing", 0)
         lat, pipe = allmax(dist, torch, [lat, pipe])
         per_rank = allgather(dist, torch, kt.tolist(), world)
-        per_mode[mode] = {"ms_per_frame": lat, "ms_per_frame_two_streams": pipe, "kernel_names": list(scene.kernel_names),
-                          "kernels_ms_per_rank": [[round(v, 5) for v in r] for r in per_rank]}
+        per_mode[(mode, gather)] = {"ms_per_frame": lat, "ms_per_frame_two_streams": pipe,
+                                    "kernel_names": list(scene.kernel_names),
+                                    "kernels_ms_per_rank": [[round(v, 5) for v in r] for r in per_rank]}
     best = min(per_mode, key=lambda m: min(per_mode[m]["ms_per_frame_two_streams"], per_mode[m]["ms_per_frame"]))
-    scene.set_option("render_mode", best)
+    scene.set_option("render_mode", best[0])
+    best_step = tile_step if best[1] == "stores" else tile_step_copy
 
     # ---- untimed check: the assembled frame == rank 0's own full-frame render, bit for bit
     set_view(0)
     torch.cuda.synchronize()
     barrier()
-    tile_step(0, None)
+    best_step(0, None)
     torch.cuda.synchronize()
     barrier()
     verified = None
@@ -407,7 +423,10 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
     kmax = [max(r[i] for r in k) for i in range(3)]
     dom = int(np.argmax(kmax))
     tput = min(b["ms_per_frame_two_streams"], b["ms_per_frame"])     # frames per second of a sweep: the better schedule
-    res = {"resolution": [W, H], "frames": steps, "render_mode": best,
+    res = {"resolution": [W, H], "frames": steps, "render_mode": best[0],
+           "gather": ("peer stores from the render kernels" if best[1] == "stores" else
+                      "render into local memory + one strided peer copy of the rank's stripes") +
+                     " + device-side arrive/grant counters (no collective)",
            "ms_per_frame": tput, "mrays": W * H / tput / 1e3,
            "schedule": "two streams (two frames in flight per GPU)" if b["ms_per_frame_two_streams"] <= b["ms_per_frame"]
                        else "one stream (one frame in flight per GPU)",
@@ -419,16 +438,16 @@ def measure_tiles(torch, dist, rank, world, local_rank, scene, rt, cam, views, W
            "limiting_kernel": {"name": b["kernel_names"][dom], "slowest_rank_ms": kmax[dom],
                                "per_rank_ms": [r[dom] for r in k],
                                "frame_minus_kernels_ms": b["ms_per_frame"] - sum(kmax)},
-           "by_mode": {str(m): {"ms_per_frame_latency": v["ms_per_frame"], "ms_per_frame_two_streams": v["ms_per_frame_two_streams"],
-                                "kernels": v["kernel_names"], "kernels_ms_per_rank": v["kernels_ms_per_rank"]}
+           "by_mode": {f"{m[0]}" + ("" if m[1] == "stores" else "_copy"):
+                       {"ms_per_frame_latency": v["ms_per_frame"], "ms_per_frame_two_streams": v["ms_per_frame_two_streams"],
+                        "kernels": v["kernel_names"], "kernels_ms_per_rank": v["kernels_ms_per_rank"]}
                        for m, v in per_mode.items()},
            "single_gpu_by_mode": {str(m): {"ms_per_frame_latency": v[0], "ms_per_frame_two_streams": v[1]}
                                   for m, v in single.items()},
            "e2e": {"ms_per_frame": e2e_ms, "mrays": W * H / e2e_ms / 1e3, "d2h_bytes_per_frame": W * H * 12,
                    "verified_bit_identical": host_verified,
                    "api": "rtgs.sharding.HostFrame: every rank DMAs its own stripes into one shared page-locked host "
-                          "image over its own PCIe link, flags in the same shared memory; rank 0 collects every frame"},
-           "gather": "peer stores + device-side arrive/grant counters (no collective)"}
+                          "image over its own PCIe link, flags in the same shared memory; rank 0 collects every frame"}}
     return res
 
 

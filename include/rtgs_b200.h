@@ -244,6 +244,13 @@ int rtgs_stream_store_u32(int device, uint32_t* counter, uint32_t value, void* s
  * into one shared, registered host image the frame crosses PCIe on all the GPUs' links in parallel. */
 int rtgs_copy_stripes_d2h(int device, float* host_rgb, const float* dev_rgb, int32_t W, int32_t H,
                           int32_t world, int32_t rank, void* stream);
+/* The same stripes into a (W,H,3) DEVICE image, typically the gathering rank's peer-mapped frame: the bulk-copy form
+ * of the gather (render into local memory, then one strided copy over NVLink) next to the default one (the render
+ * kernels store into the peer frame directly).  rtgs_stream_add_counter queues a one-thread kernel that
+ * release-increments *counter at system scope: the `arrive` signal of a frame gathered this way. */
+int rtgs_copy_stripes_d2d(int device, float* dst_rgb, const float* dev_rgb, int32_t W, int32_t H,
+                          int32_t world, int32_t rank, void* stream);
+int rtgs_stream_add_counter(int device, uint32_t* counter, void* stream);
 
 /* Same as rtgs_render but with HOST output buffers (the end-to-end call a user of
  * RayTracer makes: camera in, image out): `host_rgb` ((w,h,3) float32) and optionally

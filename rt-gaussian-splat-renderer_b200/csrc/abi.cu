@@ -151,7 +151,9 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
         // the SH records and a linear float4 texture over them (eval_colour fetches part of a record through the
         // texture path: the LSU pipe bounds the shading, the TEX pipe has throughput to spare)
         TRY(dev_alloc(&s->shp, n * 12));
-        if (n <= rtgs_dev::SH_TEX_MAX_RECORDS || !SHADE_SH_TEX_RUNTIME) {
+        const char* tex_env = getenv("RTGS_SH_TEX");     // "0": no texture, loads only (what huge scenes get; tests)
+        const bool tex_off = SHADE_SH_TEX_RUNTIME && tex_env != nullptr && atoi(tex_env) == 0;
+        if (!tex_off && (n <= rtgs_dev::SH_TEX_MAX_RECORDS || !SHADE_SH_TEX_RUNTIME)) {
             if (n > rtgs_dev::SH_TEX_MAX_RECORDS) {
                 rtgs_set_error("too many Gaussians with SH for the record texture (%lld)", (long long)n);
                 return RTGS_ERR_INVALID;
@@ -602,8 +604,31 @@ int rtgs_stream_store_u32(int device, uint32_t* counter, uint32_t value, void* s
     return rtgs_launch_store_u32(counter, value, (cudaStream_t)stream);
 }
 
+static int copy_stripes(int device, float* dst_rgb, const float* dev_rgb, int32_t W, int32_t H, int32_t world,
+                        int32_t rank, void* stream, cudaMemcpyKind kind);
+
 int rtgs_copy_stripes_d2h(int device, float* host_rgb, const float* dev_rgb, int32_t W, int32_t H, int32_t world,
                           int32_t rank, void* stream) {
+    return copy_stripes(device, host_rgb, dev_rgb, W, H, world, rank, stream, cudaMemcpyDeviceToHost);
+}
+
+int rtgs_copy_stripes_d2d(int device, float* dst_rgb, const float* dev_rgb, int32_t W, int32_t H, int32_t world,
+                          int32_t rank, void* stream) {
+    return copy_stripes(device, dst_rgb, dev_rgb, W, H, world, rank, stream, cudaMemcpyDefault);
+}
+
+int rtgs_stream_add_counter(int device, uint32_t* counter, void* stream) {
+    RTGS_CHECK_ARG(counter != nullptr);
+    DeviceGuard g(device);
+    if (!g.ok) {
+        rtgs_set_error("cudaSetDevice(%d) failed", device);
+        return RTGS_ERR_CUDA;
+    }
+    return rtgs_launch_add_counter(counter, (cudaStream_t)stream);
+}
+
+static int copy_stripes(int device, float* host_rgb, const float* dev_rgb, int32_t W, int32_t H, int32_t world,
+                        int32_t rank, void* stream, cudaMemcpyKind kind) {
     RTGS_CHECK_ARG(host_rgb != nullptr && dev_rgb != nullptr);
     RTGS_CHECK_ARG(W > 0 && H > 0 && world >= 1 && rank >= 0 && rank < world);
     DeviceGuard g(device);
@@ -621,13 +646,12 @@ int rtgs_copy_stripes_d2h(int device, float* host_rgb, const float* dev_rgb, int
     const char* src = reinterpret_cast<const char*>(dev_rgb) + (size_t)rank * stripe;
     char* dst = reinterpret_cast<char*>(host_rgb) + (size_t)rank * stripe;
     if (mine_full > 0)
-        CUDA_TRY(cudaMemcpy2DAsync(dst, stripe * world, src, stripe * world, stripe, (size_t)mine_full,
-                                   cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaMemcpy2DAsync(dst, stripe * world, src, stripe * world, stripe, (size_t)mine_full, kind, st));
     if (nstripes > full && (nstripes - 1) % world == rank) {   // the ragged last stripe
         const size_t off = (size_t)(nstripes - 1) * stripe;
         const size_t bytes = (size_t)(W - 32 * full) * H * 3 * sizeof(float);
         CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(host_rgb) + off, reinterpret_cast<const char*>(dev_rgb) + off,
-                                 bytes, cudaMemcpyDeviceToHost, st));
+                                 bytes, kind, st));
     }
     return RTGS_OK;
 }

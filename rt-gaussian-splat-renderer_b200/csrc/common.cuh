@@ -175,6 +175,7 @@ int rtgs_launch_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays, i
 int rtgs_launch_wait_counter(const unsigned int* counter, unsigned int value, cudaStream_t stream);
 int rtgs_launch_set_counter(unsigned int* counter, unsigned int value, cudaStream_t stream);
 int rtgs_launch_store_u32(unsigned int* counter, unsigned int value, cudaStream_t stream);
+int rtgs_launch_add_counter(unsigned int* counter, cudaStream_t stream);
 int rtgs_launch_pack_pixels(const float* rgb, void* out, int64_t npix, int format, cudaStream_t stream);
 int rtgs_launch_activate_ply(int64_t n, const float* rows_dev, int stride, const int32_t* col,
                              float scale, int sh_layout, float* pos, float* rot, float* sca,

@@ -33,6 +33,12 @@ using rtgs_dev::fused::k_render;
 
 namespace {
 
+// Release-increment at system scope: "everything before me on this stream has arrived" (bulk-copy gather).
+__global__ void k_add_counter(unsigned int* counter) {
+    __threadfence_system();
+    asm volatile("red.release.sys.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+}
+
 // Plain release-store at system scope (flags in mapped HOST memory, one writer each: PCIe atomics are not assumed).
 __global__ void k_store_u32(unsigned int* counter, unsigned int value) {
     __threadfence_system();
@@ -823,6 +829,12 @@ int rtgs_launch_wait_counter(const unsigned int* counter, unsigned int value, cu
 int rtgs_launch_pack_pixels(const float* rgb, void* out, int64_t npix, int format, cudaStream_t stream) {
     const int64_t work = format == RTGS_PIXELS_F16 ? (npix * 3 + 1) / 2 : npix;
     k_pack_pixels<<<(int)((work + 255) / 256), 256, 0, stream>>>(rgb, out, npix, format);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
+int rtgs_launch_add_counter(unsigned int* counter, cudaStream_t stream) {
+    k_add_counter<<<1, 1, 0, stream>>>(counter);
     CUDA_TRY(cudaGetLastError());
     return RTGS_OK;
 }

@@ -66,6 +66,8 @@ SIGNATURES = {
     "rtgs_host_device_pointer": (C.c_int, [_vp, C.POINTER(_vp)]),
     "rtgs_stream_store_u32": (C.c_int, [C.c_int, _vp, C.c_uint32, _vp]),
     "rtgs_copy_stripes_d2h": (C.c_int, [C.c_int, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "rtgs_copy_stripes_d2d": (C.c_int, [C.c_int, _vp, _vp, C.c_int32, C.c_int32, C.c_int32, C.c_int32, _vp]),
+    "rtgs_stream_add_counter": (C.c_int, [C.c_int, _vp, _vp]),
     "rtgs_scene_read_kernel_times": (C.c_int, [_vp, C.c_int32, _vp]),
     "rtgs_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_vp)]),
     "rtgs_host_free": (C.c_int, [_vp]),

@@ -180,6 +180,26 @@ class PeerFrame:
                              grant_value=f - self.buffers)
         return self._images[b][slot]
 
+    def begin_copy(self):
+        """Bulk-copy form of the tile gather: start this rank's next frame WITHOUT arming the render kernels' hand-over
+        (the frame is rendered into local memory); returns nothing.  Follow the render with ``deliver_stripes``."""
+        self.frames += 1
+
+    def deliver_stripes(self, local_image, stream=None):
+        """Copy this rank's stripes of ``local_image`` (a (W,H,3) CUDA tensor) into the shared frame with one strided
+        copy over NVLink, then signal the arrival - both stream-ordered."""
+        import torch
+
+        from . import _native
+        f = self.frames
+        b = f % self.buffers
+        st = torch.cuda.current_stream(self.device).cuda_stream if stream is None else stream
+        if f > self.buffers:      # the buffer is being reused: wait (on the stream) until its previous frame is consumed
+            _native.check(self._lib.rtgs_stream_wait_counter(self.device, self._consumed, f - self.buffers, st))
+        _native.check(self._lib.rtgs_copy_stripes_d2d(self.device, self._images[b][0].data_ptr(), local_image.data_ptr(),
+                                                      self.W, self.H, self.world, self.rank, st))
+        _native.check(self._lib.rtgs_stream_add_counter(self.device, self._arrive(b), st))
+
     def frame(self, slot: int = 0):
         """The tensor of the frame begun last (on rank 0: complete after ``wait()``)."""
         return self._images[self.frames % self.buffers][slot]

@@ -514,3 +514,24 @@ def test_compact_host_delivery_matches_the_float32_frame():
             else:
                 assert np.array_equal(got[..., :3], (np.clip(ref0, 0, 1) * np.float32(255) + np.float32(0.5)).astype(np.uint8))
     pend[0][2].result()
+
+
+def test_sh_records_through_texture_and_through_loads_are_bit_identical(monkeypatch):
+    """eval_colour fetches two thirds of an SH record through the texture path (a linear texture over the same memory)
+    and the rest with 256-bit loads; scenes too large for one texture (> 11 M Gaussians) get loads only.  Both routes
+    read the same bits: RTGS_SH_TEX=0 forces the second one, and the images are identical in every render mode."""
+    from rtgs.ray_tracer import RayTracer
+    gs = random_set(5000, seed=16, mean_scale=0.04)
+    cam, ocam = make_camera(0.6, 1.2, 2.4, 160, 104)
+    images = {}
+    for tex in ("1", "0"):
+        monkeypatch.setenv("RTGS_SH_TEX", tex)
+        scene = make_scene(gs)
+        rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+        for mode in (0, 2, 1):
+            scene.set_option("render_mode", mode)
+            images[(tex, mode)] = rt.render(16).copy()
+    for mode in (0, 2, 1):
+        assert np.array_equal(images[("1", mode)], images[("0", mode)]), mode
+    ref = O.render(gs, ocam, depth=16)["rgb"]
+    assert np.abs(images[("1", 0)] - ref).max() <= TOL
