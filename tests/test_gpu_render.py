@@ -462,6 +462,17 @@ def test_stripe_delivery_to_host_assembles_the_frame():
             rest = np.setdiff1d(np.arange(W), done)
             assert np.array_equal(img[done], want[done]) and (img[rest] == -7.0).all(), (world, r)
         assert np.array_equal(img, want)
+    # the same stripes into a DEVICE image (the bulk-copy form of the peer gather) + the stream-ordered arrive signal
+    dst = torch.full((W, H, 3), -7.0, dtype=torch.float32, device="cuda")
+    counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+    for r in range(3):
+        scene.set_stripe(3, r)
+        part = torch.full((W, H, 3), -9.0, dtype=torch.float32, device="cuda")
+        rt.render_device(16, out=part)
+        _native.check(lib.rtgs_copy_stripes_d2d(dev, dst.data_ptr(), part.data_ptr(), W, H, 3, r, stream))
+        _native.check(lib.rtgs_stream_add_counter(dev, counter.data_ptr(), stream))
+    torch.cuda.synchronize()
+    assert np.array_equal(dst.cpu().numpy(), want) and int(counter.item()) == 3
     scene.set_stripe()
     # HostFrame with one rank: deliver / wait / release over more frames than buffers
     hf = HostFrame(W, H, 0, 1, dev, None, buffers=2)
