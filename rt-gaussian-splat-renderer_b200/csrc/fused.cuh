@@ -80,6 +80,7 @@ struct __align__(16) WarpShared {
     float kb_t[K][32];     // per-lane hit buffer (unsorted): entry distance, sorted position, alpha
     int kb_i[K][32];
     float kb_a[K][32];
+    int band_state[4];     // lane 0's band-completion counts (render_common.cuh: BandCount)
 };
 
 // STATS = true compiles the per-render counters in (rtgs_render with a stats pointer); the timed path
@@ -106,7 +107,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
     }
 
     PeerGrant grant;
+    BandCount band_count;
     grant_begin(P, grant);
+    band_begin(P, band_count, ws.band_state, lane);
     unsigned long long st_nodes = 0, st_cands = 0, st_pairs = 0, st_f64 = 0, st_layers = 0, st_hit = 0,
                        st_rays = 0, st_tiles = 0, st_steps = 0, st_ins = 0;
     unsigned st_max_stack = 0;
@@ -122,9 +125,10 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         }
         tile = __shfl_sync(FULL, tile, 0);
         if (tile >= P.ntiles) break;
+        band_claim(P, band_count, tile, lane);
         int i0, j0;
         if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
-            tile_done(P, tile, lane);
+            tile_done(P, band_count, tile, lane);
             continue;
         }
         const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
@@ -498,7 +502,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         }
         grant_wait(P, grant);
         store_tile(P, reinterpret_cast<float*>(&ws.kb_t[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
-        tile_done(P, tile, lane);
+        tile_done(P, band_count, tile, lane);
         if (active) {
             ST(st_rays += 1);
             ST(st_hit += nl > 0);
@@ -507,6 +511,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
         ST(if (lane == 0) st_tiles += 1);
     }
 
+    band_flush(P, band_count, lane);
     if (STATS && P.stats) {
         unsigned long long v[ST_COUNT] = {0};
         v[ST_RAYS] = st_rays; v[ST_RAYS_HIT] = st_hit; v[ST_LAYERS] = st_layers; v[ST_F64] = st_f64;

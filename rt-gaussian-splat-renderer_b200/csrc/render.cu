@@ -146,20 +146,24 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_shade_tiles(const
     const int xe = P.x0 + P.w, ye = P.y0 + P.h;
     ShadeStats S;
     PeerGrant G;
+    BandCount BC;
     grant_begin(P, G);
+    band_begin(P, BC, ws.band_state, lane);
 #pragma unroll 1
     for (;;) {
         int tile = 0;
         if (lane == 0) tile = (int)atomicAdd(P.counters + CTR_WORK2, 1u);
         tile = work_to_id(P, __shfl_sync(FULL, tile, 0), P.macro_cols * TILES_PER_MACRO, P.ntiles);
         if (tile >= P.ntiles) break;
+        band_claim(P, BC, tile, lane);
         int i0, j0;
         if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
-            tile_done(P, tile, lane);
+            tile_done(P, BC, tile, lane);
             continue;
         }
-        shade_tile<STATS>(P, ws, S, G, tile, lane);
+        shade_tile<STATS>(P, ws, S, G, BC, tile, lane);
     }
+    band_flush(P, BC, lane);
     flush_shade_stats<STATS>(P, S, lane);
 }
 
@@ -180,7 +184,9 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_frame(const __gri
     ListsState LS;
     ShadeStats SS;
     PeerGrant G;
+    BandCount BC;
     grant_begin(P, G);
+    band_begin(P, BC, ws.shade.band_state, lane);   // (beyond the traversal's part of the union)
     // Every warp claims ONE group, then up to FOUR tiles, and repeats.  Tile claims therefore never run ahead of
     // four times the group claims: the group of a claimed tile has been claimed by a warp that is resident and
     // does not wait for anybody, so the acquire below always terminates.  Groups and tiles run out together.
@@ -205,9 +211,10 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_frame(const __gri
                 tiles_left = false;
                 break;
             }
+            band_claim(P, BC, tile, lane);
             int i0, j0;
             if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) {
-                tile_done(P, tile, lane);
+                tile_done(P, BC, tile, lane);
                 continue;
             }
             if (lane == 0) {   // acquire the publication of the tile's group (tile_lists.cuh)
@@ -220,10 +227,11 @@ __global__ void __launch_bounds__(SHADE_WARPS * 32, K2_CTAS) k_frame(const __gri
                 }
             }
             __syncwarp();
-            shade_tile<STATS>(P, ws.shade, SS, G, tile, lane);
+            shade_tile<STATS>(P, ws.shade, SS, G, BC, tile, lane);
             __syncwarp();
         }
     }
+    band_flush(P, BC, lane);
     flush_lists_stats<STATS>(P, LS, lane);
     flush_shade_stats<STATS>(P, SS, lane);
 

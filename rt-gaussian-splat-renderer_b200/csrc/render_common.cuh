@@ -170,29 +170,63 @@ __device__ __forceinline__ TileDesc load_desc(const RenderParams& P, int tile) {
 }
 
 
-// A tile id has been rendered (its framebuffer stores are issued) or skipped: count it for its band and, when
-// the band is complete, raise the host-visible flag.  Call with the whole warp converged, after store_tile.
-__device__ __forceinline__ void tile_done(const RenderParams& P, int tile, int lane) {
-    if (P.nbands == 0) return;
-    if (lane == 0) {
-        const int mi = tile / TILES_PER_MACRO / P.macro_cols;
-        const int band = mi / P.band_macro_cols;
+// Band completion (host-pipelined framebuffer copy, rtgs_render_host).  A tile id has been rendered (its framebuffer
+// stores are issued) or skipped: it counts for its band, and the warp that completes a band raises the host-visible
+// flag.  A warp's tiles come in order, so consecutive tiles nearly always belong to the same band: the counts are
+// accumulated per warp (BandCount) and released in ONE atomic when the warp claims a tile of another band or ends -
+// the release-add per tile (MEMBAR + ATOMG) cost k_shade_tiles 8 %.  The flush happens at CLAIM time, before the
+// new tile is processed, so a band is never held back by the duration of a tile of the next band.
+// The per-warp state {band, pending} lives in two ints of the warp's SHARED memory (only lane 0 touches them, and only
+// in banded launches): in registers it cost the un-banded kernels 0.8 %.
+struct BandCount {
+    int* st;   // st[0] = band of the pending counts (-1: none), st[1] = pending count
+};
+__device__ __forceinline__ void band_begin(const RenderParams& P, BandCount& bc, int* smem2, int lane) {
+    bc.st = smem2;
+    if (P.nbands != 0 && lane == 0) {
+        smem2[0] = -1;
+        smem2[1] = 0;
+    }
+}
+__device__ __forceinline__ int band_of(const RenderParams& P, int tile) {
+    return (tile / TILES_PER_MACRO / P.macro_cols) / P.band_macro_cols;
+}
+// (lane 0 only)
+__device__ __forceinline__ void band_flush_lane0(const RenderParams& P, BandCount& bc) {
+    const unsigned pending = (unsigned)bc.st[1];
+    if (pending != 0) {
+        const int band = bc.st[0];
         const int cols = min(P.macro_rows, (band + 1) * P.band_macro_cols) - band * P.band_macro_cols;
         const unsigned total = (unsigned)(cols * P.macro_cols * TILES_PER_MACRO);
-        // Release-add: the warp's framebuffer stores (ordered before it by __syncwarp; release is cumulative) are
-        // visible before the count (MEMBAR.ALL.GPU + ATOMG; __threadfence() would add an L1 invalidation per tile).
-        // Only the warp that completes the band pays for the acquire side.  Measured: the per-tile barrier + count
-        // cost k_shade_tiles 8 % (0.584 -> 0.631 ms) whichever form is used and also when it is issued one tile
-        // late, which is why the pipelined delivery (rtgs_render_host_submit) renders without bands.
+        // Release-add: the warp's framebuffer stores of all the counted tiles (ordered before it by the __syncwarp
+        // that ends store_tile; release is cumulative) are visible before the count.  Only the warp that completes
+        // the band pays for the acquire side.
         unsigned int before;
-        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;"
-                     : "=r"(before) : "l"(P.band_done + band) : "memory");
-        if (before + 1u == total) {
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], %2;"
+                     : "=r"(before) : "l"(P.band_done + band), "r"(pending) : "memory");
+        if (before + pending == total) {
             __threadfence();
             __threadfence_system();
             *reinterpret_cast<volatile int*>(P.band_flags + band) = 1;
         }
+        bc.st[1] = 0;
     }
+}
+__device__ __forceinline__ void band_flush(const RenderParams& P, BandCount& bc, int lane) {
+    if (P.nbands != 0 && lane == 0) band_flush_lane0(P, bc);
+}
+// call when a tile id has been claimed (before it is processed)
+__device__ __forceinline__ void band_claim(const RenderParams& P, BandCount& bc, int tile, int lane) {
+    if (P.nbands == 0 || lane != 0) return;
+    const int band = band_of(P, tile);
+    if (band != bc.st[0]) {
+        band_flush_lane0(P, bc);
+        bc.st[0] = band;
+    }
+}
+// call with the whole warp converged, after store_tile (or when the tile is skipped)
+__device__ __forceinline__ void tile_done(const RenderParams& P, BandCount& bc, int tile, int lane) {
+    if (P.nbands != 0 && lane == 0) bc.st[1] += 1;
 }
 
 // 256-bit read-only global load (sm_100 LDG.E.256): the L1 data pipe is charged per 128-byte line and

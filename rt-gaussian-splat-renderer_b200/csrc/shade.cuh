@@ -54,6 +54,7 @@ struct __align__(16) ShadeShared {
     int kb_i[SHADE_K][32];
     float kb_a[SHADE_K][32];
     float amb[2][32];                      // per lane: id and alpha of the nearest hit that is NOT in the buffer
+    int band_state[4];                     // lane 0's band-completion counts (render_common.cuh: BandCount)
 };
 
 struct ShadeStats {
@@ -63,8 +64,8 @@ struct ShadeStats {
 
 // Shade tile `tile` (a valid id < P.ntiles whose descriptor has been published).
 template <bool STATS>
-__device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& ws, ShadeStats& S, PeerGrant& G, int tile,
-                                           int lane) {
+__device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& ws, ShadeStats& S, PeerGrant& G,
+                                           BandCount& BC, int tile, int lane) {
     constexpr int K = SHADE_K;
     constexpr int BATCH = SHADE_BATCH;
     const CamD& cam = P.cam;
@@ -294,7 +295,7 @@ __device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& w
     }
     grant_wait(P, G);
     store_tile(P, reinterpret_cast<float*>(&ws.rec[0][0]), lane, i0, j0, pi, pj, active, cr, cg, cb, T);
-    tile_done(P, tile, lane);
+    tile_done(P, BC, tile, lane);
     if (active) {
         ST(S.st_rays += 1);
         ST(S.st_hit += nl > 0);

@@ -546,3 +546,36 @@ def test_sh_records_through_texture_and_through_loads_are_bit_identical(monkeypa
         assert np.array_equal(images[("1", mode)], images[("0", mode)]), mode
     ref = O.render(gs, ocam, depth=16)["rgb"]
     assert np.abs(images[("1", 0)] - ref).max() <= TOL
+
+
+def test_transmittance_exhaustion_pruning_changes_nothing():
+    """With t_cut > 0 the fused kernel closes a ray as soon as the hits it holds bring its transmittance below t_cut
+    and prunes everything behind the hit that does so (fused.cuh: d_T).  Nothing that is pruned would have been
+    composited: on a wall of opaque splats with a generous t_cut (rays exhausted after ~8 of 16 layers) the fused
+    kernel equals the list path at the same t_cut, which prunes nothing; with t_cut = 0 all three modes agree with
+    the oracle as everywhere else."""
+    from rtgs.ray_tracer import RayTracer
+    rng = np.random.default_rng(91)
+    n = 5000
+    gs = random_set(n, seed=92, mean_scale=0.2)
+    gs.pos[:, 0] = rng.uniform(-0.9, 0.9, n)
+    gs.opacity[:] = rng.uniform(0.85, 0.999, n)
+    scene = make_scene(gs)
+    cam, ocam = make_camera(0.0, np.pi / 2, 2.6, 96, 64)
+    for t_cut in (0.05, 1e-4):
+        rt = RayTracer(cam.buf_size, scene, cam, t_cut=t_cut)
+        imgs, layers = {}, {}
+        for mode in (0, 1, 2):
+            scene.set_option("render_mode", mode)
+            imgs[mode] = rt.render(16).copy()
+            rt.render_device(16, collect_stats=True)
+            layers[mode] = rt.last_stats["layers"] / rt.last_stats["rays"]
+        scene.set_option("render_mode", 0)
+        print("t_cut", t_cut, "layers per ray", layers)
+        if t_cut == 0.05:
+            assert layers[1] < 12.0                              # the early-out does bite
+        assert abs(layers[1] - layers[0]) < 1e-3                 # the same layers are composited either way
+        assert np.abs(imgs[1] - imgs[0]).max() <= 2e-6
+        assert np.array_equal(imgs[2], imgs[0])
+    ref = O.render(gs, ocam, depth=16)
+    assert np.abs(imgs[0] - ref["rgb"]).max() <= TOL + 4e-4       # (t_cut = 1e-4 changes a pixel by < 4e-4)
