@@ -55,6 +55,7 @@ void free_scene(rtgs_scene* s) {
     cudaFree(s->aabb); cudaFree(s->geo); cudaFree(s->shp); cudaFree(s->raw); cudaFree(s->nodes); cudaFree(s->leafbox); cudaFree(s->nodes4);
     for (auto& fs : s->scratch) {
         cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.fallback_tiles2); cudaFree(fs.ready);
+        cudaFree(fs.heavy_groups); cudaFree(fs.tile_cap); cudaFree(fs.heavy_scratch);
         cudaFree(fs.counters);
         if (fs.free_event) cudaEventDestroy(fs.free_event);
     }
@@ -100,12 +101,11 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     CUDA_TRY(cudaStreamCreateWithFlags(&s->own_stream2, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream, cudaStreamNonBlocking));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->copy_stream2, cudaStreamNonBlocking));
-    // [0, MAX) band flags of host slot 0, [MAX] [MAX+1] the mirrors of frame scratch 0, [MAX+2, 2 MAX+2) band flags
-    // of host slot 1, [2 MAX+2] [2 MAX+3] the mirrors of frame scratch 1
-    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (2 * RTGS_MAX_BANDS + 4) * sizeof(int), cudaHostAllocMapped));
+    // [0, MAX) band flags of host slot 0, [MAX, 2 MAX) those of host slot 1, then four mirror words per frame scratch
+    CUDA_TRY(cudaHostAlloc((void**)&s->band_flags, (2 * RTGS_MAX_BANDS + 8) * sizeof(int), cudaHostAllocMapped));
     CUDA_TRY(cudaHostGetDevicePointer((void**)&s->band_flags_dev, s->band_flags, 0));
     for (int k = 0; k < 2; ++k) {
-        const int off = k == 0 ? 0 : RTGS_MAX_BANDS + 2;
+        const int off = k * RTGS_MAX_BANDS;
         s->host_slot[k].flags = s->band_flags + off;
         s->host_slot[k].flags_dev = s->band_flags_dev + off;
         CUDA_TRY(cudaEventCreateWithFlags(&s->host_slot[k].done, cudaEventDisableTiming));
@@ -114,11 +114,13 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->band_done, RTGS_MAX_BANDS));
     for (int k = 0; k < 2; ++k) {
         rtgs_scene::FrameScratch& fs = s->scratch[k];
-        const int off = k == 0 ? RTGS_MAX_BANDS : 2 * RTGS_MAX_BANDS + 2;
+        const int off = 2 * RTGS_MAX_BANDS + 4 * k;
         fs.mirror = s->band_flags + off;
         fs.mirror_dev = s->band_flags_dev + off;
         fs.mirror[0] = 0;   // pool demand of the last finished frame (render.cu: ensure_lists)
         fs.mirror[1] = 0;   // some finished frame had fallback tiles (render.cu: launch_render_k)
+        fs.mirror[2] = 0;   // some frame had groups whose candidate list overflows shared memory (render.cu: k_heavy_lists)
+        fs.mirror[3] = 0;
         TRY(dev_alloc(&fs.counters, 16));      // CTR_COUNT (render_common.cuh)
         CUDA_TRY(cudaMemset(fs.counters, 0, 16 * sizeof(unsigned int)));   // k_frame leaves them zeroed frame after frame
         CUDA_TRY(cudaEventCreateWithFlags(&fs.free_event, cudaEventDisableTiming));
@@ -172,7 +174,7 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->leafbox, n * 2));
     TRY(dev_alloc(&s->nodes4, s->num_nodes * 8));
-    TRY(dev_alloc(&s->stats_dev, 16));
+    TRY(dev_alloc(&s->stats_dev, 24));   // ST_TOTAL (render_common.cuh)
     return RTGS_OK;
 }
 
@@ -451,13 +453,16 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
     TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_image_pitch, out_rgb, out_T, st,
                            stats != nullptr));
     if (stats) {
-        unsigned long long hs[16];
+        unsigned long long hs[24];
         CUDA_TRY(cudaMemcpyAsync(hs, s->stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
         stats->candidates = hs[4]; stats->pair_tests = hs[5]; stats->f64_refinements = hs[6]; stats->tiles = hs[7];
         stats->traversal_steps = hs[8]; stats->insert_rounds = hs[9]; stats->fallback_tiles = hs[10]; stats->useful_candidates = hs[11];
         stats->max_lists_stack = hs[12]; stats->max_fused_stack = hs[13]; stats->max_group_list = hs[14];
+        stats->heavy_groups = hs[15]; stats->heavy_failed = hs[16]; stats->heavy_passes = hs[17];
+        stats->heavy_sample_tests = hs[18]; stats->max_deferred = hs[19]; stats->heavy_retries = hs[20];
+        stats->heavy_failed_list = hs[21]; stats->heavy_failed_deferred = hs[22]; stats->heavy_failed_passes = hs[23];
     }
     return RTGS_OK;
 }
@@ -476,6 +481,8 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             // dropped here, re-created with the new capacity by the next render
             for (auto& fs : s->scratch) {
                 cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.fallback_tiles2); cudaFree(fs.ready);
+                cudaFree(fs.heavy_groups); cudaFree(fs.tile_cap);
+                fs.heavy_groups = nullptr; fs.tile_cap = nullptr;
                 fs.tile_desc = nullptr; fs.list_pool = nullptr; fs.fallback_tiles = nullptr; fs.fallback_tiles2 = nullptr; fs.ready = nullptr;
                 fs.list_tiles = 0;
                 fs.pool_chunks = 0;
@@ -508,6 +515,14 @@ int rtgs_scene_set_option(rtgs_scene* s, int32_t option, int64_t value) {
             }
             return RTGS_OK;
         }
+        case RTGS_OPT_HEAVY_LISTS:
+            RTGS_CHECK_ARG(value >= -1 && value <= 2);
+            s->opt_heavy_lists = (int)value;
+            return RTGS_OK;
+        case RTGS_OPT_HEAVY_LIMIT:
+            RTGS_CHECK_ARG(value >= -1 && value <= (1ll << 30));
+            s->opt_heavy_limit = (int)value;
+            return RTGS_OK;
         case RTGS_OPT_TREE_DEPTH:
             rtgs_set_error("RTGS_OPT_TREE_DEPTH is read-only");
             return RTGS_ERR_INVALID;
@@ -535,6 +550,8 @@ int rtgs_scene_get_option(const rtgs_scene* s, int32_t option, int64_t* value) {
         case RTGS_OPT_KERNEL_TIMING: *value = (int64_t)s->timing_ran.size(); return RTGS_OK;
         case RTGS_OPT_STRIPE: *value = ((int64_t)s->opt_stripe_mod << 32) | (int64_t)s->opt_stripe_rem; return RTGS_OK;
         case RTGS_OPT_MORTON_BITS: *value = s->built ? s->morton_bits_used : s->opt_morton_bits; return RTGS_OK;
+        case RTGS_OPT_HEAVY_LISTS: *value = rtgs_heavy_lists_mode(s); return RTGS_OK;
+        case RTGS_OPT_HEAVY_LIMIT: *value = s->opt_heavy_limit; return RTGS_OK;
         case RTGS_OPT_TREE_DEPTH:
             if (!s->built) {
                 rtgs_set_error("rtgs_scene_get_option(RTGS_OPT_TREE_DEPTH): call rtgs_scene_build_bvh first");

@@ -108,7 +108,12 @@ struct rtgs_scene {
         int list_tiles = 0;
         int pool_chunks = 0;
         int* mirror = nullptr;                // mapped pinned host memory: [0] pool demand of the last finished frame,
-        int* mirror_dev = nullptr;            //                            [1] some finished frame had fallback tiles
+        int* mirror_dev = nullptr;            //                            [1] some finished frame had fallback tiles,
+                                              //                            [2] some frame had heavy groups (k_heavy_lists)
+        int* heavy_groups = nullptr;          // depth-capped lists (heavy_lists.cuh): queue of heavy groups, per-tile caps,
+        float* tile_cap = nullptr;            // per-warp lists of deferred nodes; sized with the candidate lists / on first use
+        int2* heavy_scratch = nullptr;
+        int heavy_scratch_warps = 0;
         cudaEvent_t free_event = nullptr;     // behind the last frame that used this scratch
         cudaStream_t stream = nullptr;        // the stream that frame was launched on
         bool used = false;
@@ -125,6 +130,8 @@ struct rtgs_scene {
     int64_t opt_pool_chunks = -1;             // RTGS_OPT_LIST_POOL_CHUNKS (-1 = default sizing)
     int opt_stripe_mod = 1, opt_stripe_rem = 0;   // RTGS_OPT_STRIPE
     int opt_render_mode = -1;                 // RTGS_OPT_RENDER_MODE (-1 = RTGS_RENDER_MODE env or 0)
+    int opt_heavy_lists = -1;                 // RTGS_OPT_HEAVY_LISTS (-1 = RTGS_HEAVY_SLAB env or 1)
+    int opt_heavy_limit = -1;                 // RTGS_OPT_HEAVY_LIMIT (-1 = RTGS_HEAVY_LIMIT env or the shared-memory capacity)
     // rtgs_render_host: device staging + band flags, double-buffered so that two frames can be in flight
     // (rtgs_render_host_submit / _collect: frame f+1 renders while the last bands of frame f are copied out)
     struct HostSlot {
@@ -169,6 +176,7 @@ int rtgs_lbvh_build(rtgs_scene* s);   // lbvh.cu
 int rtgs_launch_render(rtgs_scene* s, const rtgs_camera* cam, int x0, int y0, int w, int h,
                        int depth, float t_cut, int accumulate, int full_pitch, float* out_rgb,
                        float* out_T, cudaStream_t stream, bool want_stats);  // render.cu
+int rtgs_heavy_lists_mode(const rtgs_scene* s);
 int rtgs_launch_generate_rays(const rtgs_camera* cam, float* rays, cudaStream_t stream);
 int rtgs_launch_trace_closest(rtgs_scene* s, int64_t nrays, const float* rays, int32_t* idx,
                               float* t12, cudaStream_t stream);

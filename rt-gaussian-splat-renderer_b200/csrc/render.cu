@@ -16,11 +16,14 @@
 //                  fused kernel from the device if (and only if) some tile went to the fallback list, signals the
 //                  `arrive` counter of a multi-GPU gather and zeroes the work counters for the next frame.
 //   k_tile_lists + k_shade_tiles (+ k_render)   the same device code as separate launches (mode 0; A/B and ncu)
+//   k_heavy_lists  (mode 0, scenes that have them) depth-capped lists for the groups whose frustum overflows the
+//                  traversal's shared-memory list (heavy_lists.cuh), between k_tile_lists and k_shade_tiles
 //   k_render       fused.cuh (mode 1, depth > 16, fallback tiles)
 //   k_generate_rays, k_trace_closest, k_activate_ply   API companions (Camera.generate_ray_field, Scene.hit, PLY ingest)
 #include <stdlib.h>
 
 #include "fused.cuh"
+#include "heavy_lists.cuh"
 #include "shade.cuh"
 #include "tile_lists.cuh"
 
@@ -127,6 +130,48 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
         lists_group<STATS>(P, ws, S, group, gi0, gj0, lane);
     }
     flush_lists_stats<STATS>(P, S, lane);
+}
+
+// ---- depth-capped lists for the heavy groups k_tile_lists queued (heavy_lists.cuh) -------------------------------
+constexpr int HEAVY_CTAS = 2;
+template <bool STATS>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, HEAVY_CTAS) k_heavy_lists(const __grid_constant__ RenderParams P) {
+#if LISTS_STATIC_SMEM
+    __shared__ ListsShared smem[WARPS_PER_CTA];
+    ListsShared& ws = smem[threadIdx.x >> 5];
+#else
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ListsShared& ws = reinterpret_cast<ListsShared*>(smem_raw)[threadIdx.x >> 5];
+#endif
+    const int lane = threadIdx.x & 31;
+    ListsState S;
+    HeavyStats HS;
+    const int n = (int)min(P.counters[CTR_HEAVY], (unsigned)(P.ntiles / TILES_PER_GROUP));
+    int2* def = P.heavy_scratch + ((int64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 * P.heavy_defer_cap;
+#pragma unroll 1
+    for (;;) {
+        int k = 0;
+        if (lane == 0) k = (int)atomicAdd(P.counters + CTR_WORK5, 1u);
+        k = __shfl_sync(FULL, k, 0);
+        if (k >= n) break;
+        const int group = P.heavy_groups[k];
+        int gi0, gj0;
+        group_origin(P, group, gi0, gj0);
+        heavy_group<STATS>(P, ws, S, HS, def, group, gi0, gj0, lane);
+        __syncwarp();
+    }
+    flush_lists_stats<STATS>(P, S, lane);
+    if (STATS && P.stats && lane == 0) {
+        if (HS.groups) atomicAdd(P.stats + ST_HEAVY_GROUPS, HS.groups);
+        if (HS.failed) atomicAdd(P.stats + ST_HEAVY_FAILED, HS.failed);
+        if (HS.iters) atomicAdd(P.stats + ST_HEAVY_PASSES, HS.iters);
+        if (HS.tested) atomicAdd(P.stats + ST_HEAVY_TESTS, HS.tested);
+        if (HS.retries) atomicAdd(P.stats + ST_HEAVY_RETRIES, HS.retries);
+        if (HS.fail_list) atomicAdd(P.stats + ST_HEAVY_FAIL_LIST, HS.fail_list);
+        if (HS.fail_defer) atomicAdd(P.stats + ST_HEAVY_FAIL_DEFER, HS.fail_defer);
+        if (HS.fail_passes) atomicAdd(P.stats + ST_HEAVY_FAIL_PASSES, HS.fail_passes);
+        atomicMax(P.stats + ST_MAX_DEFERRED, (unsigned long long)HS.max_deferred);
+    }
 }
 
 #ifndef K2_WARPS
@@ -480,6 +525,35 @@ int launch_tile_lists(rtgs_scene* s, const RenderParams& P, cudaStream_t stream)
     return RTGS_OK;
 }
 
+// Deferred-node lists of k_heavy_lists: two of HEAVY_DEFER_CAP entries per warp of its grid (allocated on first use).
+constexpr int HEAVY_DEFER_CAP = 2048;
+template <bool STATS>
+int launch_heavy_lists(rtgs_scene* s, rtgs_scene::FrameScratch& fs, RenderParams& P, cudaStream_t stream) {
+    static int cache[16] = {0};
+    const size_t smem = LISTS_STATIC_SMEM ? 0 : sizeof(ListsShared) * WARPS_PER_CTA;
+    int nb = 0;
+    int r = persistent_blocks(s, k_heavy_lists<STATS>, WARPS_PER_CTA * 32, smem, cache, "k_heavy_lists", &nb);
+    if (r != RTGS_OK) return r;
+    if (nb > HEAVY_CTAS) nb = HEAVY_CTAS;
+    int grid = s->sm_count * nb;
+    const int need = (P.ntiles / TILES_PER_GROUP + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    if (grid > need) grid = need;
+    if (grid < 1) grid = 1;
+    const int warps = grid * WARPS_PER_CTA;
+    if (fs.heavy_scratch_warps < warps) {
+        cudaFree(fs.heavy_scratch);
+        fs.heavy_scratch = nullptr;
+        fs.heavy_scratch_warps = 0;
+        CUDA_TRY(cudaMalloc((void**)&fs.heavy_scratch, (size_t)warps * 2 * HEAVY_DEFER_CAP * sizeof(int2)));
+        fs.heavy_scratch_warps = warps;
+    }
+    P.heavy_scratch = fs.heavy_scratch;
+    P.heavy_defer_cap = HEAVY_DEFER_CAP;
+    k_heavy_lists<STATS><<<grid, WARPS_PER_CTA * 32, smem, stream>>>(P);
+    CUDA_TRY(cudaGetLastError());
+    return RTGS_OK;
+}
+
 template <bool STATS>
 int launch_shade_tiles(rtgs_scene* s, const RenderParams& P, cudaStream_t stream, bool dependent) {
     static int cache[16] = {0};
@@ -548,6 +622,22 @@ int render_mode(const rtgs_scene* s) {
     return mode;
 }
 
+}  // namespace
+
+// Heavy groups (heavy_lists.cuh): 1 (default) = depth-capped lists once the scene has shown heavy groups, 2 = from the
+// first frame on, 0 = the fused kernel renders their tiles.
+int rtgs_heavy_lists_mode(const rtgs_scene* s) {
+    if (s->opt_heavy_lists >= 0) return s->opt_heavy_lists;
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("RTGS_HEAVY_SLAB");
+        mode = e ? atoi(e) : 1;
+        if (mode < 0 || mode > 2) mode = 1;
+    }
+    return mode;
+}
+
+namespace {
 // k_frame's fallback tiles: 1 (default) = its last CTA tail-launches the fused kernel from the device when there
 // are any; 0 = the host queues the fused kernel behind every frame (it returns at once when the list is empty).
 int tail_launch_mode() {
@@ -577,7 +667,9 @@ int ensure_lists(rtgs_scene* s, rtgs_scene::FrameScratch& fs, int ntiles) {
     const bool grow_only = fs.list_tiles >= ntiles;
     const int tiles = grow_only ? fs.list_tiles : ntiles;
     cudaFree(fs.tile_desc); cudaFree(fs.list_pool); cudaFree(fs.fallback_tiles); cudaFree(fs.fallback_tiles2); cudaFree(fs.ready);
+    cudaFree(fs.heavy_groups); cudaFree(fs.tile_cap);
     fs.tile_desc = nullptr; fs.list_pool = nullptr; fs.fallback_tiles = nullptr; fs.fallback_tiles2 = nullptr; fs.ready = nullptr;
+    fs.heavy_groups = nullptr; fs.tile_cap = nullptr;
     fs.list_tiles = 0;
     int64_t chunks = s->opt_pool_chunks >= 0 ? s->opt_pool_chunks : (int64_t)tiles * 16;
     if (grow_only && want > chunks) chunks = want;
@@ -586,6 +678,8 @@ int ensure_lists(rtgs_scene* s, rtgs_scene::FrameScratch& fs, int ntiles) {
     CUDA_TRY(cudaMalloc((void**)&fs.list_pool, (size_t)(chunks > 0 ? chunks : 1) * CHUNK_INTS * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&fs.fallback_tiles, (size_t)tiles * sizeof(int)));
     CUDA_TRY(cudaMalloc((void**)&fs.fallback_tiles2, (size_t)tiles * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&fs.heavy_groups, ((size_t)tiles / TILES_PER_GROUP + 1) * sizeof(int)));
+    CUDA_TRY(cudaMalloc((void**)&fs.tile_cap, (size_t)tiles * sizeof(float)));
     // group publication flags: compared with the frame sequence number, which starts at 1 and never repeats
     const size_t groups = (size_t)tiles / TILES_PER_GROUP + 1;
     CUDA_TRY(cudaMalloc((void**)&fs.ready, groups * sizeof(unsigned int)));
@@ -678,7 +772,16 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
     static const int heavy_fused = getenv("RTGS_HEAVY_FUSED") ? atoi(getenv("RTGS_HEAVY_FUSED")) : 1;
     P.heavy_fused = heavy_fused;
     static const int heavy_limit = getenv("RTGS_HEAVY_LIMIT") ? atoi(getenv("RTGS_HEAVY_LIMIT")) : 1 << 30;
-    P.heavy_limit = heavy_limit;
+    P.heavy_limit = s->opt_heavy_limit >= 0 ? s->opt_heavy_limit : heavy_limit;
+    P.heavy_slab = 0;
+    P.heavy_groups = nullptr;
+    P.tile_cap = nullptr;
+    P.heavy_scratch = nullptr;
+    P.heavy_defer_cap = 0;
+    static const float slab_margin = getenv("RTGS_SLAB_MARGIN") ? (float)atof(getenv("RTGS_SLAB_MARGIN")) : 1.015f;
+    P.slab_margin = slab_margin >= 1.0f ? slab_margin : 1.0f;
+    static const float slab_step = getenv("RTGS_SLAB_STEP_MAX") ? (float)atof(getenv("RTGS_SLAB_STEP_MAX")) : 0.08f;
+    P.slab_step_max = slab_step;
     {
         // batch threshold of the traversal stack: the tuned value, capped by what this tree's depth allows
         static const int tuned = getenv("RTGS_LISTS_SINGLE") ? atoi(getenv("RTGS_LISTS_SINGLE")) : 112;
@@ -770,8 +873,21 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
         }
         return mark(3);
     }
+    // Groups whose frustum overflows the traversal's shared-memory list ("heavy"): once a frame of this scene has
+    // reported some (mirror[2]), the traversal queues them and k_heavy_lists lists them in depth slabs
+    // (heavy_lists.cuh); until then - and with RTGS_OPT_HEAVY_LISTS = 0 - they go to the fused kernel.  Scenes
+    // without heavy groups never launch the extra kernel.  (Its time is counted with k_tile_lists.)
+    P.tile_cap = fs.tile_cap;
+    P.heavy_groups = fs.heavy_groups;
+    const int heavy_mode = rtgs_heavy_lists_mode(s);
+    const bool heavy_seen = *reinterpret_cast<volatile int*>(s->scratch[0].mirror + 2) != 0 ||
+                            *reinterpret_cast<volatile int*>(s->scratch[1].mirror + 2) != 0;
+    P.heavy_slab = (heavy_mode == 2 || (heavy_mode == 1 && heavy_seen)) ? 1 : 0;
     if ((r = mark(0)) != RTGS_OK) return r;
     if ((r = want_stats ? launch_tile_lists<true>(s, P, stream) : launch_tile_lists<false>(s, P, stream)) != RTGS_OK) return r;
+    if (P.heavy_slab &&
+        (r = want_stats ? launch_heavy_lists<true>(s, fs, P, stream) : launch_heavy_lists<false>(s, fs, P, stream)) != RTGS_OK)
+        return r;
     if ((r = mark(1)) != RTGS_OK) return r;
     // Tiles the traversal handed to the fused kernel (groups whose frustum holds ~1000 Gaussians or more, or a list
     // pool that ran out) are known before the shading starts.  RTGS_HEAVY_OVERLAP=1 renders them FIRST and launches the

@@ -34,21 +34,31 @@ constexpr int SLAB_CHUNKS = 16;   // chunks a warp takes from the pool per atomi
 
 struct TileDesc {
     int head;    // first chunk, -1 if the list is empty
-    int count;   // candidates; -1: the list did not fit the pool, the tile is in the fallback list
+    int count;   // candidates; -1: the list did not fit the pool, the tile is in the fallback list;
+                 // | TILE_CAPPED: the list is depth-capped (heavy_lists.cuh), tile_cap[tile] holds the cap
 };
+constexpr int TILE_CAPPED = 1 << 30;
 
 // CTR_FALLBACK / CTR_WORK3: tiles the traversal hands to k_render (list pool exhausted, or a group whose frustum holds
 // too many candidates) and the cursor of the launch that renders them; CTR_FALLBACK2 / CTR_WORK4: tiles the shading
 // hands over (three hits within rounding at the K-th place) and their cursor.  Two lists, because the first one is
 // complete BEFORE the shading starts and its tiles are rendered concurrently with it (render.cu).
 enum { CTR_WORK = 0, CTR_POOL = 1, CTR_FALLBACK = 2, CTR_WORK2 = 3, CTR_WORK3 = 4, CTR_DONE = 5, CTR_DONE2 = 6,
-       CTR_FALLBACK2 = 7, CTR_WORK4 = 8, CTR_DONE3 = 9, CTR_COUNT = 16 };
+       CTR_FALLBACK2 = 7, CTR_WORK4 = 8, CTR_DONE3 = 9,
+       CTR_HEAVY = 10, CTR_WORK5 = 11,   // heavy groups queued by the traversal / the cursor of k_heavy_lists
+       CTR_HEAVY_FAILED = 12,            // ... of them handed on to k_render (statistics)
+       CTR_COUNT = 16 };
 enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64, ST_TILES, ST_STEPS, ST_INSERTS,
        ST_FALLBACK, ST_USEFUL, ST_COUNT = 12,
        // high-water marks (maxima, not sums; statistics builds only): deepest traversal stacks and the fullest group
        // list seen - the stack bounds of tile_lists.cuh / fused.cuh checked on the device (compute-sanitizer is not
        // available on the GPU pool, so the deep-tree tests assert these instead)
-       ST_MAX_LISTS_STACK = 12, ST_MAX_FUSED_STACK = 13, ST_MAX_GROUP_LIST = 14, ST_TOTAL = 16 };
+       ST_MAX_LISTS_STACK = 12, ST_MAX_FUSED_STACK = 13, ST_MAX_GROUP_LIST = 14,
+       // depth-capped lists (heavy_lists.cuh): groups listed that way, of them handed on to the fused kernel, cap raises,
+       // candidates tested against the sample rays; ST_MAX_DEFERRED: longest deferred list (a maximum)
+       ST_HEAVY_GROUPS = 15, ST_HEAVY_FAILED = 16, ST_HEAVY_PASSES = 17, ST_HEAVY_TESTS = 18, ST_MAX_DEFERRED = 19,
+       ST_HEAVY_RETRIES = 20, ST_HEAVY_FAIL_LIST = 21, ST_HEAVY_FAIL_DEFER = 22, ST_HEAVY_FAIL_PASSES = 23,
+       ST_TOTAL = 24 };
 
 struct RenderParams {
     const float4* nodes;
@@ -84,6 +94,14 @@ struct RenderParams {
                               // launch): the shading that follows does not depend on this launch
     int heavy_fused;          // k_tile_lists: a group whose list overflows shared memory goes to k_render (distance pruning)
     int heavy_limit;          // ... "overflows" = more candidates than this (<= the capacity of the shared-memory list)
+    // depth-capped lists of heavy groups (heavy_lists.cuh; all unused while heavy_slab == 0)
+    int heavy_slab;           // lists_group queues a group whose list overflows in heavy_groups instead (k_heavy_lists follows)
+    int* heavy_groups;        // ngroups
+    float* tile_cap;          // ntiles: every Gaussian that can enter a ray of the tile nearer than this is in its list
+    int2* heavy_scratch;      // per warp of k_heavy_lists: 2 x heavy_defer_cap deferred (node, depth bits) entries
+    int heavy_defer_cap;
+    float slab_margin;        // the cap is (farthest 16th hit of the sample rays) x this
+    float slab_step_max;      // largest relative raise of the cap per pass while the sample rays are not full
     int lists_single;         // lists_group pops one node per step while its stack holds more entries than this (tile_lists.cuh)
     // band completion (host-pipelined framebuffer copy, rtgs_render_host): the frame is cut into nbands bands of
     // band_macro_cols 32-pixel columns; a band is finished when all its tile ids have been rendered or skipped

@@ -75,6 +75,8 @@ __device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& w
     tile_origin(P, tile, i0, j0);
     const TileDesc desc = load_desc(P, tile);
     if (desc.count < 0) return;   // list did not fit the pool: the fused kernel renders this tile
+    const bool capped = (desc.count & TILE_CAPPED) != 0;   // depth-capped list of a heavy group (heavy_lists.cuh)
+    const int desc_count = desc.count & ~TILE_CAPPED;
     const int pi = i0 + lane / TILE_J, pj = j0 + lane % TILE_J;
     const bool active = pi < xe && pj < ye;
 
@@ -89,9 +91,9 @@ __device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& w
     float e1_t = INFINITY, kmax_t = INFINITY;
     int kmax_slot = 0;
     TileRays tr;
-    if (desc.count > 0) {
+    if (desc_count > 0) {
         make_tile_rays(cam, i0, j0, pi, pj, active, tr);
-        int left = desc.count;
+        int left = desc_count;
         // one coalesced 128-byte read per chunk: lanes 0..30 candidates, lane 31 the next chunk
         int cur = POOL_LOAD(P.pool + (int64_t)desc.head * CHUNK_INTS + lane);
 #pragma unroll 1
@@ -188,6 +190,20 @@ __device__ __forceinline__ void shade_tile(const RenderParams& P, ShadeShared& w
                 ST(S.st_ins += 1);
             }
             __syncwarp();
+        }
+    }
+
+    // ---- a depth-capped list holds every Gaussian that can enter a ray of the tile nearer than tile_cap[tile]: the
+    // tile is decided iff every ray has its K hits nearer than that (the cap is a guess from sample rays); if not,
+    // k_render renders the tile from scratch, as for the near-ties below
+    if (capped) {
+        const float cap = __ldcg(P.tile_cap + tile);
+        if (__any_sync(FULL, active && !(cnt == K && kmax_t < cap))) {
+            if (lane == 0) {
+                P.fallback_tiles2[atomicAdd(P.counters + CTR_FALLBACK2, 1u)] = tile;
+                *reinterpret_cast<volatile int*>(P.mirror + 1) = 1;
+            }
+            return;
         }
     }
 

@@ -65,6 +65,7 @@ struct ListsState {
     int slab_next = 0, slab_end = 0;
     unsigned long long st_nodes = 0, st_steps = 0, st_cands = 0;
     unsigned st_max_stack = 0, st_max_list = 0;     // high-water marks (statistics builds)
+    bool heavy_flagged = false;                     // this warp has reported a heavy group to the host (mirror[2])
 };
 
 // `group` is a group of this launch whose pixel origin (gi0, gj0) lies inside the rendered region (the caller has
@@ -277,6 +278,10 @@ __device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& 
             if (ok[t] && ncq[t] > 0) ok[t] = write_chunk(ws.cq + t * CQ_TILE, ncq[t], ncq[t], head[t], count[t]);
             finish_tile(group * TILES_PER_GROUP + t, head[t], count[t], ok[t]);
         }
+    } else if (P.heavy_slab) {
+        // ---- the group's list did not fit shared memory: k_heavy_lists (next on the stream) lists it in depth slabs
+        // and writes the four descriptors (heavy_lists.cuh)
+        if (lane == 0) P.heavy_groups[atomicAdd(P.counters + CTR_HEAVY, 1u)] = group;
     } else if (P.heavy_fused) {
         // ---- the group's list did not fit shared memory: its frustum holds ~1000 Gaussians or more, typically
         // because it looks along a surface.  Listing them all is the wrong plan - the rays will have their K
@@ -287,6 +292,11 @@ __device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& 
             const int i0 = gi0 + (sub / GROUP_TJ) * TILE_I, j0 = gj0 + (sub % GROUP_TJ) * TILE_J;
             if (i0 >= xe || j0 >= ye) continue;
             finish_tile(group * TILES_PER_GROUP + sub, -1, 0, false);
+        }
+        // tell the host that this scene has heavy groups: later frames run k_heavy_lists for them (render.cu)
+        if (lane == 0 && !S.heavy_flagged) {
+            *reinterpret_cast<volatile int*>(P.mirror + 2) = 1;
+            S.heavy_flagged = true;
         }
     } else {
         // ---- (RTGS_HEAVY_FUSED=0) one traversal per tile, leaves stream out -------

@@ -28,7 +28,10 @@ class rtgs_render_stats(C.Structure):
     _fields_ = [(n, C.c_uint64) for n in ("rays", "rays_hit", "layers", "nodes_tested", "candidates",
                                           "pair_tests", "f64_refinements", "tiles", "traversal_steps",
                                           "insert_rounds", "fallback_tiles", "useful_candidates",
-                                          "max_lists_stack", "max_fused_stack", "max_group_list")]
+                                          "max_lists_stack", "max_fused_stack", "max_group_list",
+                                          "heavy_groups", "heavy_failed", "heavy_passes", "heavy_sample_tests",
+                                          "max_deferred", "heavy_retries", "heavy_failed_list",
+                                          "heavy_failed_deferred", "heavy_failed_passes")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}
@@ -89,6 +92,7 @@ SIGNATURES = {
 }
 
 OPT_RENDER_MODE, OPT_LIST_POOL_CHUNKS, OPT_KERNEL_TIMING, OPT_STRIPE, OPT_MORTON_BITS, OPT_TREE_DEPTH = 0, 1, 2, 3, 4, 5
+OPT_HEAVY_LISTS, OPT_HEAVY_LIMIT = 6, 7
 #: the (up to) three launches of a frame, by render mode (rtgs_scene_read_kernel_times); None = no launch
 KERNEL_NAMES_BY_MODE = {0: ("k_tile_lists", "k_shade_tiles", "k_render"),
                         1: (None, None, "k_render"),

@@ -222,7 +222,8 @@ class Scene:
 
     _OPTIONS = {"render_mode": _native.OPT_RENDER_MODE, "list_pool_chunks": _native.OPT_LIST_POOL_CHUNKS,
                 "kernel_timing": _native.OPT_KERNEL_TIMING, "stripe": _native.OPT_STRIPE,
-                "morton_bits": _native.OPT_MORTON_BITS, "tree_depth": _native.OPT_TREE_DEPTH}
+                "morton_bits": _native.OPT_MORTON_BITS, "tree_depth": _native.OPT_TREE_DEPTH,
+                "heavy_lists": _native.OPT_HEAVY_LISTS, "heavy_limit": _native.OPT_HEAVY_LIMIT}
 
     def set_option(self, name: str, value: int) -> "Scene":
         """Render-path tuning (rtgs_scene_set_option): ``render_mode`` 0 = tile lists + shading kernels (default),

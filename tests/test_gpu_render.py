@@ -329,6 +329,7 @@ def test_overflowing_groups_take_the_pruning_kernel():
     cam, ocam = make_camera(0.0, np.pi / 2, 2.6, 96, 64)
     from rtgs.ray_tracer import RayTracer
     rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    scene.set_option("heavy_lists", 0)                 # (the default lists such groups in depth slabs: next test)
     for depth in (16, 32):
         ref = O.render(gs, ocam, depth=depth)
         assert np.minimum(ref["nhit"], depth).mean() > 0.9 * depth      # the buffers do fill
@@ -342,6 +343,65 @@ def test_overflowing_groups_take_the_pruning_kernel():
             if mode != 1 and depth == 16:
                 assert st["fallback_tiles"] > 0.5 * (96 // 4) * (64 // 8)      # the groups overflowed
     scene.set_option("render_mode", 0)
+
+
+def _wall_scene():
+    rng = np.random.default_rng(77)
+    n = 6000
+    gs = random_set(n, seed=78, mean_scale=0.25)
+    gs.pos[:, 0] = rng.uniform(-0.9, 0.9, n)
+    gs.opacity[:] = rng.uniform(0.2, 0.95, n)
+    return gs
+
+
+@pytest.mark.parametrize("case", ["wall", "cloud_forced", "surface_forced"])
+def test_heavy_groups_are_listed_in_depth_slabs(case):
+    """Groups whose frustum overflows the traversal's shared list are listed by k_heavy_lists in depth slabs
+    (csrc/heavy_lists.cuh): the cap comes from 32 sample rays, the shading verifies it for every ray and hands the tile
+    to k_render when it does not hold.  Whatever the guess, the frame must equal the one rendered with the pruning
+    kernel (heavy_lists = 0) bit for bit, and the oracle within tolerance.  `wall`: every group is heavy and every
+    ray fills its buffer; `cloud_forced` / `surface_forced`: a low heavy_limit sends ordinary groups down the path,
+    including groups whose rays never fill (complete, uncapped lists) and image borders."""
+    from rtgs.ray_tracer import RayTracer
+    from rtgs.synthetic import make_surface_scene
+    if case == "wall":
+        gs, limit = _wall_scene(), -1
+        cam, ocam = make_camera(0.0, np.pi / 2, 2.6, 96, 64)
+    elif case == "cloud_forced":
+        gs, limit = random_set(6000, seed=41, mean_scale=0.03), 24
+        cam, ocam = make_camera(0.7, 1.2, 2.4, 203, 131)         # not a multiple of the group size
+    else:
+        sc = make_surface_scene(12000, seed=5)
+        gs = O.GaussianSet(sc["pos"], sc["rot"], sc["scale"], sc["color"], sc["opacity"], sc["sh"])
+        limit = 64
+        cam, ocam = make_camera(0.4, np.pi / 2 - 0.3, 2.2, 192, 128)
+    scene = make_scene(gs)
+    scene.set_option("heavy_limit", limit)
+    ref = O.render(gs, ocam, depth=16)["rgb"]
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    scene.set_option("heavy_lists", 0)
+    base = rt.render(16).copy()
+    rt.render_device(16, collect_stats=True)
+    st0 = dict(rt.last_stats)
+    assert st0["heavy_groups"] == 0 and st0["fallback_tiles"] > 0
+    scene.set_option("heavy_lists", 2)
+    img = rt.render(16).copy()
+    rt.render_device(16, collect_stats=True)
+    st = dict(rt.last_stats)
+    print(case, {k: st[k] for k in ("heavy_groups", "heavy_failed", "heavy_passes", "heavy_sample_tests",
+                                     "max_deferred", "fallback_tiles", "max_group_list")}, "before:", st0["fallback_tiles"])
+    assert st["heavy_groups"] > 0
+    assert st["max_deferred"] <= 2048 and st["max_group_list"] <= 960
+    assert st["fallback_tiles"] < st0["fallback_tiles"]           # most heavy tiles are decided by their slab
+    assert np.array_equal(img, base)
+    mx, ps, _ = compare(img, ref, TOL)
+    assert mx <= TOL and ps >= 60.0, (mx, ps)
+    # the default (1) switches over by itself once a frame has reported heavy groups
+    scene.set_option("heavy_lists", 1)
+    rt.render(16)
+    rt.render_device(16, collect_stats=True)
+    assert rt.last_stats["heavy_groups"] > 0
+    assert np.array_equal(rt.render(16), base)
 
 
 def test_pipelined_sweep_is_bit_identical_to_synchronous_renders():
