@@ -71,15 +71,18 @@ typedef struct rtgs_render_stats {
     uint64_t max_fused_stack;    /* deepest stack of the fused kernel (entries) */
     uint64_t max_group_list;     /* longest shared-memory candidate list of an 8x16-pixel group (<= 960) */
     /* depth-capped lists of heavy groups (RTGS_OPT_HEAVY_LISTS, csrc/heavy_lists.cuh) */
-    uint64_t heavy_groups;       /* 8x16-pixel groups listed in depth slabs (their frustum overflows the shared list) */
+    uint64_t heavy_groups;       /* 4x8-pixel tiles listed in depth slabs (their group's frustum overflows the shared list) */
     uint64_t heavy_failed;       /* ... of them handed on to the fused kernel (slab or deferred list overflowed) */
     uint64_t heavy_passes;       /* cap raises, summed over the heavy groups */
-    uint64_t heavy_sample_tests; /* candidates intersected with the 32 sample rays of their group */
+    uint64_t heavy_sample_tests; /* candidates run through the hit test by k_heavy_lists */
     uint64_t max_deferred;       /* longest list of deferred nodes (<= 2048) */
     uint64_t heavy_retries;      /* passes repeated with a smaller step because the slab overflowed the shared list */
     uint64_t heavy_failed_list;      /* heavy_failed by cause: the slab the sample rays ask for overflows the shared list, */
     uint64_t heavy_failed_deferred;  /* the list of deferred nodes overflowed, */
-    uint64_t heavy_failed_passes;    /* more than 96 passes */
+    uint64_t heavy_failed_passes;    /* more than 128 passes */
+    uint64_t heavy_cycles_walk;      /* SM clock cycles, summed over the warps of k_heavy_lists: the slab walk (of which */
+    uint64_t heavy_cycles_test;      /* ... the hit tests) and */
+    uint64_t heavy_cycles_publish;   /* writing the lists */
 } rtgs_render_stats;
 
 const char* rtgs_last_error(void);
@@ -185,10 +188,10 @@ typedef enum rtgs_option {
     RTGS_OPT_KERNEL_TIMING = 2,
     RTGS_OPT_STRIPE = 3,
     RTGS_OPT_MORTON_BITS = 4,
-    RTGS_OPT_HEAVY_LISTS = 6,    /* groups whose frustum holds more candidates than the traversal's shared-memory list:
-                                  * 1 (default; env RTGS_HEAVY_SLAB) = listed in depth slabs by k_heavy_lists once a frame of
-                                  * the scene has had such groups, 2 = from the first frame on, 0 = their tiles are rendered
-                                  * by the fused kernel k_render (round 1's path).  Mode 0 renders only. */
+    RTGS_OPT_HEAVY_LISTS = 6,    /* tiles of groups whose frustum holds more candidates than the traversal's shared-memory
+                                  * list: 0 (default; env RTGS_HEAVY_SLAB) = rendered by the fused kernel k_render; 1 = listed
+                                  * in depth slabs by k_heavy_lists once a frame of the scene has had such groups, 2 = from
+                                  * the first frame on (csrc/heavy_lists.cuh; same pixels, bit for bit).  Mode 0 renders only. */
     RTGS_OPT_HEAVY_LIMIT = 7,    /* a group is heavy above this many candidates (default -1: the capacity of the shared
                                   * list, 896; smaller values are for tests) */
     RTGS_OPT_TREE_DEPTH = 5      /* read-only: depth of the deepest LBVH leaf (root = 0); the traversal stacks are

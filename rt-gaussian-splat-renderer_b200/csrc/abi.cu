@@ -174,7 +174,7 @@ int alloc_scene(int device, int64_t n, bool has_sh, rtgs_scene** out) {
     TRY(dev_alloc(&s->nodes, s->num_nodes * 4));
     TRY(dev_alloc(&s->leafbox, n * 2));
     TRY(dev_alloc(&s->nodes4, s->num_nodes * 8));
-    TRY(dev_alloc(&s->stats_dev, 24));   // ST_TOTAL (render_common.cuh)
+    TRY(dev_alloc(&s->stats_dev, 32));   // ST_TOTAL (render_common.cuh)
     return RTGS_OK;
 }
 
@@ -453,7 +453,7 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
     TRY(rtgs_launch_render(s, cam, x0, y0, w, h, depth, t_cut, accumulate, full_image_pitch, out_rgb, out_T, st,
                            stats != nullptr));
     if (stats) {
-        unsigned long long hs[24];
+        unsigned long long hs[32];
         CUDA_TRY(cudaMemcpyAsync(hs, s->stats_dev, sizeof(hs), cudaMemcpyDeviceToHost, st));
         CUDA_TRY(cudaStreamSynchronize(st));
         stats->rays = hs[0]; stats->rays_hit = hs[1]; stats->layers = hs[2]; stats->nodes_tested = hs[3];
@@ -462,6 +462,7 @@ int rtgs_render(rtgs_scene* s, const rtgs_camera* cam, int32_t x0, int32_t y0, i
         stats->max_lists_stack = hs[12]; stats->max_fused_stack = hs[13]; stats->max_group_list = hs[14];
         stats->heavy_groups = hs[15]; stats->heavy_failed = hs[16]; stats->heavy_passes = hs[17];
         stats->heavy_sample_tests = hs[18]; stats->max_deferred = hs[19]; stats->heavy_retries = hs[20];
+        stats->heavy_cycles_walk = hs[24]; stats->heavy_cycles_test = hs[25]; stats->heavy_cycles_publish = hs[26];
         stats->heavy_failed_list = hs[21]; stats->heavy_failed_deferred = hs[22]; stats->heavy_failed_passes = hs[23];
     }
     return RTGS_OK;

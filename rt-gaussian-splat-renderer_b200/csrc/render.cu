@@ -132,21 +132,17 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, K1_CTAS) k_tile_lists(cons
     flush_lists_stats<STATS>(P, S, lane);
 }
 
-// ---- depth-capped lists for the heavy groups k_tile_lists queued (heavy_lists.cuh) -------------------------------
+// ---- depth-capped lists for the tiles of the heavy groups k_tile_lists queued (heavy_lists.cuh) --------------------
 constexpr int HEAVY_CTAS = 2;
 template <bool STATS>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, HEAVY_CTAS) k_heavy_lists(const __grid_constant__ RenderParams P) {
-#if LISTS_STATIC_SMEM
-    __shared__ ListsShared smem[WARPS_PER_CTA];
-    ListsShared& ws = smem[threadIdx.x >> 5];
-#else
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    ListsShared& ws = reinterpret_cast<ListsShared*>(smem_raw)[threadIdx.x >> 5];
-#endif
+    HeavyShared& hs = reinterpret_cast<HeavyShared*>(smem_raw)[threadIdx.x >> 5];
     const int lane = threadIdx.x & 31;
+    const int xe = P.x0 + P.w, ye = P.y0 + P.h;
     ListsState S;
     HeavyStats HS;
-    const int n = (int)min(P.counters[CTR_HEAVY], (unsigned)(P.ntiles / TILES_PER_GROUP));
+    const int n = (int)min(P.counters[CTR_HEAVY], (unsigned)(P.ntiles / TILES_PER_GROUP)) * TILES_PER_GROUP;
     int2* def = P.heavy_scratch + ((int64_t)blockIdx.x * WARPS_PER_CTA + (threadIdx.x >> 5)) * 2 * P.heavy_defer_cap;
 #pragma unroll 1
     for (;;) {
@@ -154,15 +150,15 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, HEAVY_CTAS) k_heavy_lists(
         if (lane == 0) k = (int)atomicAdd(P.counters + CTR_WORK5, 1u);
         k = __shfl_sync(FULL, k, 0);
         if (k >= n) break;
-        const int group = P.heavy_groups[k];
-        int gi0, gj0;
-        group_origin(P, group, gi0, gj0);
-        heavy_group<STATS>(P, ws, S, HS, def, group, gi0, gj0, lane);
+        const int tile = P.heavy_groups[k / TILES_PER_GROUP] * TILES_PER_GROUP + k % TILES_PER_GROUP;
+        int i0, j0;
+        if (!tile_origin(P, tile, i0, j0) || i0 >= xe || j0 >= ye) continue;
+        heavy_tile<STATS>(P, hs, S, HS, def, tile, i0, j0, 0.0f, lane);
         __syncwarp();
     }
     flush_lists_stats<STATS>(P, S, lane);
     if (STATS && P.stats && lane == 0) {
-        if (HS.groups) atomicAdd(P.stats + ST_HEAVY_GROUPS, HS.groups);
+        if (HS.tiles) atomicAdd(P.stats + ST_HEAVY_GROUPS, HS.tiles);
         if (HS.failed) atomicAdd(P.stats + ST_HEAVY_FAILED, HS.failed);
         if (HS.iters) atomicAdd(P.stats + ST_HEAVY_PASSES, HS.iters);
         if (HS.tested) atomicAdd(P.stats + ST_HEAVY_TESTS, HS.tested);
@@ -171,6 +167,9 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, HEAVY_CTAS) k_heavy_lists(
         if (HS.fail_defer) atomicAdd(P.stats + ST_HEAVY_FAIL_DEFER, HS.fail_defer);
         if (HS.fail_passes) atomicAdd(P.stats + ST_HEAVY_FAIL_PASSES, HS.fail_passes);
         atomicMax(P.stats + ST_MAX_DEFERRED, (unsigned long long)HS.max_deferred);
+        atomicAdd(P.stats + ST_HEAVY_CYC_WALK, HS.cyc_walk);
+        atomicAdd(P.stats + ST_HEAVY_CYC_TEST, HS.cyc_test);
+        atomicAdd(P.stats + ST_HEAVY_CYC_PUBLISH, HS.cyc_publish);
     }
 }
 
@@ -530,13 +529,13 @@ constexpr int HEAVY_DEFER_CAP = 2048;
 template <bool STATS>
 int launch_heavy_lists(rtgs_scene* s, rtgs_scene::FrameScratch& fs, RenderParams& P, cudaStream_t stream) {
     static int cache[16] = {0};
-    const size_t smem = LISTS_STATIC_SMEM ? 0 : sizeof(ListsShared) * WARPS_PER_CTA;
+    const size_t smem = sizeof(HeavyShared) * WARPS_PER_CTA;
     int nb = 0;
     int r = persistent_blocks(s, k_heavy_lists<STATS>, WARPS_PER_CTA * 32, smem, cache, "k_heavy_lists", &nb);
     if (r != RTGS_OK) return r;
     if (nb > HEAVY_CTAS) nb = HEAVY_CTAS;
     int grid = s->sm_count * nb;
-    const int need = (P.ntiles / TILES_PER_GROUP + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
+    const int need = (P.ntiles + WARPS_PER_CTA - 1) / WARPS_PER_CTA;
     if (grid > need) grid = need;
     if (grid < 1) grid = 1;
     const int warps = grid * WARPS_PER_CTA;
@@ -624,15 +623,16 @@ int render_mode(const rtgs_scene* s) {
 
 }  // namespace
 
-// Heavy groups (heavy_lists.cuh): 1 (default) = depth-capped lists once the scene has shown heavy groups, 2 = from the
-// first frame on, 0 = the fused kernel renders their tiles.
+// Heavy groups (heavy_lists.cuh): 0 (default) = the fused kernel renders their tiles, 1 = depth-capped lists once the
+// scene has shown heavy groups, 2 = from the first frame on.  Off by default: on the surface-like scene the two routes
+// cost the same, and the fused kernel is the simpler one.
 int rtgs_heavy_lists_mode(const rtgs_scene* s) {
     if (s->opt_heavy_lists >= 0) return s->opt_heavy_lists;
     static int mode = -1;
     if (mode < 0) {
         const char* e = getenv("RTGS_HEAVY_SLAB");
-        mode = e ? atoi(e) : 1;
-        if (mode < 0 || mode > 2) mode = 1;
+        mode = e ? atoi(e) : 0;
+        if (mode < 0 || mode > 2) mode = 0;
     }
     return mode;
 }
@@ -778,10 +778,8 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
     P.tile_cap = nullptr;
     P.heavy_scratch = nullptr;
     P.heavy_defer_cap = 0;
-    static const float slab_margin = getenv("RTGS_SLAB_MARGIN") ? (float)atof(getenv("RTGS_SLAB_MARGIN")) : 1.015f;
-    P.slab_margin = slab_margin >= 1.0f ? slab_margin : 1.0f;
-    static const float slab_step = getenv("RTGS_SLAB_STEP_MAX") ? (float)atof(getenv("RTGS_SLAB_STEP_MAX")) : 0.08f;
-    P.slab_step_max = slab_step;
+    static const int slab_rank = getenv("RTGS_SLAB_RANK") ? atoi(getenv("RTGS_SLAB_RANK")) : 24;
+    P.slab_rank = slab_rank < 0 ? 0 : (slab_rank > 31 ? 31 : slab_rank);
     {
         // batch threshold of the traversal stack: the tuned value, capped by what this tree's depth allows
         static const int tuned = getenv("RTGS_LISTS_SINGLE") ? atoi(getenv("RTGS_LISTS_SINGLE")) : 112;
@@ -873,10 +871,10 @@ static int launch_render_on(rtgs_scene* s, rtgs_scene::FrameScratch& fs, const r
         }
         return mark(3);
     }
-    // Groups whose frustum overflows the traversal's shared-memory list ("heavy"): once a frame of this scene has
-    // reported some (mirror[2]), the traversal queues them and k_heavy_lists lists them in depth slabs
-    // (heavy_lists.cuh); until then - and with RTGS_OPT_HEAVY_LISTS = 0 - they go to the fused kernel.  Scenes
-    // without heavy groups never launch the extra kernel.  (Its time is counted with k_tile_lists.)
+    // Groups whose frustum overflows the traversal's shared-memory list ("heavy") go to the fused kernel.  With
+    // RTGS_OPT_HEAVY_LISTS = 1 (2) the traversal queues them instead, once a frame of this scene has reported some
+    // (from the first frame on), and k_heavy_lists lists their tiles in depth slabs (heavy_lists.cuh); scenes without
+    // heavy groups never launch the extra kernel.  (Its time is counted with k_tile_lists.)
     P.tile_cap = fs.tile_cap;
     P.heavy_groups = fs.heavy_groups;
     const int heavy_mode = rtgs_heavy_lists_mode(s);

@@ -58,7 +58,8 @@ enum { ST_RAYS = 0, ST_RAYS_HIT, ST_LAYERS, ST_NODES, ST_CANDS, ST_PAIRS, ST_F64
        // candidates tested against the sample rays; ST_MAX_DEFERRED: longest deferred list (a maximum)
        ST_HEAVY_GROUPS = 15, ST_HEAVY_FAILED = 16, ST_HEAVY_PASSES = 17, ST_HEAVY_TESTS = 18, ST_MAX_DEFERRED = 19,
        ST_HEAVY_RETRIES = 20, ST_HEAVY_FAIL_LIST = 21, ST_HEAVY_FAIL_DEFER = 22, ST_HEAVY_FAIL_PASSES = 23,
-       ST_TOTAL = 24 };
+       ST_HEAVY_CYC_WALK = 24, ST_HEAVY_CYC_TEST = 25, ST_HEAVY_CYC_PUBLISH = 26,   // warp clock cycles per phase
+       ST_TOTAL = 32 };
 
 struct RenderParams {
     const float4* nodes;
@@ -100,8 +101,7 @@ struct RenderParams {
     float* tile_cap;          // ntiles: every Gaussian that can enter a ray of the tile nearer than this is in its list
     int2* heavy_scratch;      // per warp of k_heavy_lists: 2 x heavy_defer_cap deferred (node, depth bits) entries
     int heavy_defer_cap;
-    float slab_margin;        // the cap is (farthest 16th hit of the sample rays) x this
-    float slab_step_max;      // largest relative raise of the cap per pass while the sample rays are not full
+    int slab_rank;            // the cap of a pass = the slab_rank-th smallest of the 32 per-lane nearest deferred depths
     int lists_single;         // lists_group pops one node per step while its stack holds more entries than this (tile_lists.cuh)
     // band completion (host-pipelined framebuffer copy, rtgs_render_host): the frame is cut into nbands bands of
     // band_macro_cols 32-pixel columns; a band is finished when all its tile ids have been rendered or skipped

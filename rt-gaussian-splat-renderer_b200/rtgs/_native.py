@@ -31,7 +31,8 @@ class rtgs_render_stats(C.Structure):
                                           "max_lists_stack", "max_fused_stack", "max_group_list",
                                           "heavy_groups", "heavy_failed", "heavy_passes", "heavy_sample_tests",
                                           "max_deferred", "heavy_retries", "heavy_failed_list",
-                                          "heavy_failed_deferred", "heavy_failed_passes")]
+                                          "heavy_failed_deferred", "heavy_failed_passes",
+                                          "heavy_cycles_walk", "heavy_cycles_test", "heavy_cycles_publish")]
 
     def as_dict(self):
         return {n: int(getattr(self, n)) for n, _ in self._fields_}

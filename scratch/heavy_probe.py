@@ -22,9 +22,9 @@ for mode in (0, 2):
         img = out.cpu().numpy().copy()
         if mode == 0: ref[v] = img
         same = "" if mode == 0 else f" identical={np.array_equal(img, ref[v])} maxdiff={np.abs(img - ref[v]).max():.2e}"
-        print(f"heavy_lists {mode} view {v}: heavy groups {st['heavy_groups']} failed {st['heavy_failed']} passes/group "
+        print(f"heavy_lists {mode} view {v}: heavy tiles {st['heavy_groups']} failed {st['heavy_failed']} passes/group "
               f"{st['heavy_passes']/max(st['heavy_groups'],1):.1f} sample tests/group {st['heavy_sample_tests']/max(st['heavy_groups'],1):.0f} "
-              f"max deferred {st['max_deferred']} retries {st['heavy_retries']} fail list/defer/passes {st['heavy_failed_list']}/{st['heavy_failed_deferred']}/{st['heavy_failed_passes']} steps {st['traversal_steps']} nodes {st['nodes_tested']} fallback tiles {st['fallback_tiles']} cands/tile {st['candidates']/max(st['tiles'],1):.0f}{same}", flush=True)
+              f"kcyc/tile walk {st['heavy_cycles_walk']/max(st['heavy_groups'],1)/1e3:.1f} test {st['heavy_cycles_test']/max(st['heavy_groups'],1)/1e3:.1f} pub {st['heavy_cycles_publish']/max(st['heavy_groups'],1)/1e3:.1f} max deferred {st['max_deferred']} retries {st['heavy_retries']} fail list/defer/passes {st['heavy_failed_list']}/{st['heavy_failed_deferred']}/{st['heavy_failed_passes']} steps {st['traversal_steps']} nodes {st['nodes_tested']} fallback tiles {st['fallback_tiles']} cands/tile {st['candidates']/max(st['tiles'],1):.0f}{same}", flush=True)
     # timing: 16-view orbit, 3 rounds, per-kernel events
     scene.set_option("kernel_timing", 64)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
