@@ -48,11 +48,21 @@ namespace fused {
 #define RTGS_STACK_CAP 512
 #endif
 constexpr int STACK_CAP = RTGS_STACK_CAP;
-// Above STACK_SINGLE the traversal pops one node at a time (depth first): a batch step grows the stack by <= 32
-// (two children per popped node), a single pop by <= 1 per level descended, i.e. by <= RTGS_MAX_TREE_DEPTH in all.
+#ifndef FUSED_TWO_LEVEL
+#define FUSED_TWO_LEVEL 0     // 1: a step pops two-level nodes (four grandchild boxes per lane; measured on the surface-like
+                              // scene: 1.368 -> 1.396 ms, fewer steps but as many instructions), 0: binary nodes
+#endif
+// Above STACK_SINGLE the traversal pops one node at a time (depth first).  Binary nodes: a batch step grows the stack
+// by <= 32 (two children per popped node), a single pop by <= 1 per level descended, i.e. by <= RTGS_MAX_TREE_DEPTH in
+// all.  Two-level nodes: <= 3 x 32 per batch step, <= 3 per single pop, which descends two levels.
+#if FUSED_TWO_LEVEL
+constexpr int STACK_SINGLE = STACK_CAP - 96 - 3 * ((RTGS_MAX_TREE_DEPTH + 1) / 2);
+constexpr int CQ_CAP = 160;   // < 32 waiting + <= 128 leaves of one step
+#else
 constexpr int STACK_SINGLE = STACK_CAP - 32 - RTGS_MAX_TREE_DEPTH;
-static_assert(STACK_SINGLE >= 64, "k_render: stack too small for batched traversal");
 constexpr int CQ_CAP = 96;
+#endif
+static_assert(STACK_SINGLE >= 64, "k_render: stack too small for batched traversal");
 constexpr int BATCH = 32;
 constexpr int REC_Q = 5;                 // quads per staged record (80-byte stride: conflict-free gathers)
 
@@ -195,6 +205,68 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 }
                 top -= take;
                 __syncwarp();
+#if FUSED_TWO_LEVEL
+                // every lane takes a whole two-level node (lbvh.cu: k_pack_nodes4: the records of both children side
+                // by side): four grandchild boxes per lane, one step descends two tree levels - half as many
+                // dependent steps per tile, which is what a tile that looks along a surface is made of
+                bool hb[4];
+                int cb[4];
+                float db[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { hb[k] = false; cb[k] = 0; db[k] = 0.0f; }
+                if (node >= 0) {
+                    const float4* rec = P.nodes4 + (int64_t)node * 8;
+                    float4 q[8];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) ldg256(rec + 2 * k, q[2 * k], q[2 * k + 1]);   // all four loads in flight
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const float4 a = q[4 * h], b = q[4 * h + 1], c = q[4 * h + 2], d = q[4 * h + 3];
+                        cb[2 * h] = __float_as_int(d.x);
+                        cb[2 * h + 1] = __float_as_int(d.y);
+                        hb[2 * h] = box_in_frustum(fr, a.x, a.y, a.z, a.w, b.x, b.y);
+                        hb[2 * h + 1] = box_in_frustum(fr, b.z, b.w, c.x, c.y, c.z, c.w);
+                        db[2 * h] = box_dist2(a.x, a.y, a.z, a.w, b.x, b.y);
+                        db[2 * h + 1] = box_dist2(b.z, b.w, c.x, c.y, c.z, c.w);
+                        if (cut2 >= 0.0f) {
+                            if (hb[2 * h] && db[2 * h] > cut2)
+                                hb[2 * h] = open_mask != 0 && (open_all || box_in_frustum(tr.open, a.x, a.y, a.z, a.w, b.x, b.y));
+                            if (hb[2 * h + 1] && db[2 * h + 1] > cut2)
+                                hb[2 * h + 1] = open_mask != 0 && (open_all || box_in_frustum(tr.open, b.z, b.w, c.x, c.y, c.z, c.w));
+                        }
+                    }
+                    // farthest first (pushed first, popped last): sorting network on four
+                    auto cswap = [&](int i, int j) {
+                        if (db[i] < db[j]) {
+                            const float td = db[i]; db[i] = db[j]; db[j] = td;
+                            const int tc = cb[i]; cb[i] = cb[j]; cb[j] = tc;
+                            const bool th = hb[i]; hb[i] = hb[j]; hb[j] = th;
+                        }
+                    };
+                    cswap(0, 1); cswap(2, 3); cswap(0, 2); cswap(1, 3); cswap(1, 2);
+                }
+                ST(st_nodes += 4ull * (unsigned)take);
+                ST(st_steps += 1);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool in = hb[k] && cb[k] >= 0;
+                    const unsigned m = __ballot_sync(FULL, in);
+                    if (in) {
+                        tr.stack[top + __popc(m & lt_mask)] = cb[k];
+#if FUSED_POP_PRUNE
+                        tr.sdist[top + __popc(m & lt_mask)] = db[k];
+#endif
+                    }
+                    top += __popc(m);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const bool lf = hb[k] && cb[k] < 0;
+                    const unsigned m = __ballot_sync(FULL, lf);
+                    if (lf) tr.cq[ncq + __popc(m & lt_mask)] = ~cb[k];
+                    ncq += __popc(m);
+                }
+#else
                 bool h0 = false, h1 = false;
                 int c0 = 0, c1 = 0;
                 float dd0 = 0.0f, dd1 = 0.0f;
@@ -243,6 +315,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
                 const int ncqa = ncq + __popc(mL0);
                 if (h1 && c1 < 0) tr.cq[ncqa + __popc(mL1 & lt_mask)] = ~c1;
                 ncq = ncqa + __popc(mL1);
+#endif
                 ST(st_max_stack = max(st_max_stack, (unsigned)top));
                 __syncwarp();
             }
