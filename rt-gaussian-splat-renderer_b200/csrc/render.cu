@@ -4,20 +4,21 @@
 // BVH traversal (scene.py:406-450), ray-Gaussian intersection (gaussian.py:203-230), response + SH colour
 // (gaussian.py:140-201) and front-to-back compositing of the `depth` nearest entries (ray_tracer.py:79-104).
 //
-//   k_frame        (default, RTGS_OPT_RENDER_MODE 2) ONE launch per frame.  Persistent warps alternate between the
-//                  two halves of the path: one 8x16-pixel group of the traversal (tile_lists.cuh: lists_group,
-//                  which publishes the group's four candidate lists), then four 4x8-pixel tiles of shading
-//                  (shade.cuh: shade_tile, which acquires the publication of its tile's group).  Claims are
-//                  ordered - a tile is only ever claimed after its group - so a waiting warp always waits for a
-//                  warp that is running.  Traversal (issue- and latency-bound) and shading (L1-pipe-bound) overlap
-//                  on every SM, there is no kernel boundary inside the frame, and a frame that is spread over many
-//                  GPUs is no longer floored by a traversal kernel that runs before any shading can start.
+//   k_tile_lists + k_shade_tiles (+ k_render)   (default, RTGS_OPT_RENDER_MODE 0) the two halves of the path as separate
+//                  launches: the traversal writes one candidate list per 4x8-pixel tile (tile_lists.cuh), the shading
+//                  consumes them (shade.cuh), the fused kernel renders the tiles either of them handed over.  The fastest
+//                  route for whole frames on one GPU (0.68 vs 0.83 ms) and for sweeps (frames on two streams overlap).
+//   k_frame        (RTGS_OPT_RENDER_MODE 2) ONE launch per frame.  Persistent warps alternate between the
+//                  two halves of the path: one 8x16-pixel group of the traversal (lists_group, which publishes the
+//                  group's four candidate lists), then four 4x8-pixel tiles of shading (shade_tile, which acquires the
+//                  publication of its tile's group).  Claims are ordered - a tile is only ever claimed after its
+//                  group - so a waiting warp always waits for a warp that is running.  No kernel boundary inside the
+//                  frame: the lowest LATENCY of a single frame that is spread over >= 4 GPUs (few groups per SM).
 //                  The last CTA completes the frame: it mirrors the list-pool demand to the host, tail-launches the
-//                  fused kernel from the device if (and only if) some tile went to the fallback list, signals the
+//                  fused kernel from the device (RTGS_CDP builds) if some tile went to a hand-over list, signals the
 //                  `arrive` counter of a multi-GPU gather and zeroes the work counters for the next frame.
-//   k_tile_lists + k_shade_tiles (+ k_render)   the same device code as separate launches (mode 0; A/B and ncu)
-//   k_heavy_lists  (mode 0, scenes that have them) depth-capped lists for the groups whose frustum overflows the
-//                  traversal's shared-memory list (heavy_lists.cuh), between k_tile_lists and k_shade_tiles
+//   k_heavy_lists  (mode 0, opt-in RTGS_OPT_HEAVY_LISTS) depth-capped lists for the tiles of groups whose frustum overflows
+//                  the traversal's shared-memory list (heavy_lists.cuh), between k_tile_lists and k_shade_tiles
 //   k_render       fused.cuh (mode 1, depth > 16, fallback tiles)
 //   k_generate_rays, k_trace_closest, k_activate_ply   API companions (Camera.generate_ray_field, Scene.hit, PLY ingest)
 #include <stdlib.h>
