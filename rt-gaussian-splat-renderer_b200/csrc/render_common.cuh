@@ -581,7 +581,12 @@ __device__ __forceinline__ PreciseHit precise_test(const RenderParams& P, const 
     h.hit = (q < 3.0f) && (h.t1 > 0.0f);
     h.refined = false;
     const bool near_q = fabsf(q - 3.0f) < ax.z;
-    const bool near_t = (q < 3.0f + ax.z) && fabsf(h.t1) <= 2e-6f * (fabsf(tc) + fabsf(tau));
+    // t1 = tc + tau loses its float32 accuracy where the two terms cancel (a camera just outside a large ellipsoid:
+    // tc = 0.5, tau = -0.4992 - two such hits 5e-8 apart were composited in the wrong order).  Where the entry
+    // distance is smaller than |tau| it is taken from the float64 evaluation, so that every kept distance is accurate
+    // relative to ITSELF and the relative tie bands of the k-buffer hold (elsewhere its error is <= 6e-7 t1).
+    // Distances that are negative beyond rounding - the camera inside the ellipsoid - are misses either way.
+    const bool near_t = (q < 3.0f + ax.z) && h.t1 > -2e-6f * (fabsf(tc) + fabsf(tau)) && h.t1 < fabsf(tau);
     if (near_q || near_t) {
         const ExactHit e = exact_eval(P.raw, P.cam, h.s, pi, pj);
         h.hit = e.hit && (e.t1 > 0.0);

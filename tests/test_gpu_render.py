@@ -92,6 +92,27 @@ def test_camera_inside_the_cloud():
     assert mx <= TOL and ps >= 60.0
 
 
+def test_camera_just_outside_large_ellipsoids():
+    """A camera in the middle of a cloud of LARGE Gaussians (it is inside 350 of the 2400 ellipsoids, and the nearest
+    surfaces are 1e-3 away): entry distances t1 = t_c + tau are differences of terms 1000x larger, so two hits 5e-8
+    apart (6e-5 relative) are beyond float32 - the tie bands of the k-buffer must scale with the cancelling terms,
+    not with t1 (found by a fuzz sweep in round 2: two pixels off by 0.01, the first two layers swapped)."""
+    from rtgs.ray_tracer import RayTracer
+    gs = random_set(2427, seed=11020, mean_scale=0.24913786492941115, sh=False)
+    gs.pos[:, 2] *= 0.02                                   # a sheet of large splats, the camera 0.1 above it
+    scene = make_scene(gs)
+    cam, ocam = make_camera(2.52281928787616, 2.007240515427329, 0.25061865417331775, 188, 133, fov=31.52202888953712)
+    rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+    for depth in (5, 16):
+        ref = O.render(gs, ocam, depth=depth)
+        assert ref["nhit"].max() > 400
+        for mode in (0, 1, 2):
+            scene.set_option("render_mode", mode)
+            mx, ps, bad = compare(rt.render(depth), ref["rgb"], TOL)
+            assert mx <= TOL and ps >= 60.0, (depth, mode, mx, ps, bad)
+    scene.set_option("render_mode", 0)
+
+
 def test_attenuation_and_stats():
     import torch
     from rtgs.ray_tracer import RayTracer
