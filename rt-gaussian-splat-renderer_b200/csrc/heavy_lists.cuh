@@ -443,7 +443,7 @@ __device__ __noinline__ float heavy_tile(const RenderParams& P, HeavyShared& hs,
         if (keep) ws.cq[ncq + __popc(mk & lt_mask)] = s;
         ncq += __popc(mk);
         __syncwarp();
-        if (ncq >= CHUNK_IDS) write_chunk(CHUNK_IDS);
+        while (ok && ncq >= CHUNK_IDS) write_chunk(CHUNK_IDS);
     }
     if (ok && ncq > 0) write_chunk(ncq);
     if (lane == 0) {

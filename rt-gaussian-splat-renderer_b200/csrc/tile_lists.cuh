@@ -268,9 +268,12 @@ __device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& 
                 ncq[t] += __popc(mh);
             }
             __syncwarp();
+            // (a batch may add 32 entries to a queue that holds up to 30: two chunks then, or the queue would creep
+            // past its 64 slots into its neighbour's - a dense cluster of Gaussians that all touch one tile)
 #pragma unroll
             for (int t = 0; t < TILES_PER_GROUP; ++t)
-                if (ncq[t] >= CHUNK_IDS) ok[t] = write_chunk(ws.cq + t * CQ_TILE, CHUNK_IDS, ncq[t], head[t], count[t]);
+                while (ok[t] && ncq[t] >= CHUNK_IDS)
+                    ok[t] = write_chunk(ws.cq + t * CQ_TILE, CHUNK_IDS, ncq[t], head[t], count[t]);
         }
 #pragma unroll
         for (int t = 0; t < TILES_PER_GROUP; ++t) {

@@ -113,6 +113,37 @@ def test_camera_just_outside_large_ellipsoids():
     scene.set_option("render_mode", 0)
 
 
+def test_dense_cluster_fills_one_tile_queue():
+    """A dense core of 2000 small Gaussians seen from close by: almost every candidate of an 8x16-pixel group touches
+    the SAME 4x8-pixel tile, so that tile's output queue of the fused four-tile filter takes 32 entries per batch.
+    (Round 2 fuzz sweep: the queue was flushed one chunk per batch, crept past its 64 slots into its neighbour's
+    and beyond - wrong pixels, garbage candidate ids, an illegal memory access.)  All routes against the oracle, and
+    against each other with a transmittance cut."""
+    from rtgs.ray_tracer import RayTracer
+    rng = np.random.default_rng(31025)
+    n = 2000
+    gs = random_set(n, seed=31026, mean_scale=0.006)
+    gs.pos[:] = (gs.pos * rng.uniform(0.0, 1.0, (n, 1)) ** 3).astype(np.float32)
+    scene = make_scene(gs)
+    for (theta, phi, r, W, H, fov) in ((0.9, 1.1, 0.37, 32, 51, 50.0), (2.0, 1.8, 0.11, 101, 71, 35.0)):
+        cam, ocam = make_camera(theta, phi, r, W, H, fov=fov)
+        ref = O.render(gs, ocam, depth=16)
+        rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+        cut = RayTracer(cam.buf_size, scene, cam, t_cut=0.01)
+        imgs = []
+        for mode in (0, 2, 1):
+            scene.set_option("render_mode", mode)
+            mx, ps, bad = compare(rt.render(16), ref["rgb"], TOL)
+            assert mx <= TOL and ps >= 60.0, (mode, mx, ps, bad)
+            imgs.append(cut.render(16).copy())
+        rt.render_device(16, collect_stats=True)          # (mode 1 statistics are not needed; back to the lists)
+        scene.set_option("render_mode", 0)
+        rt.render_device(16, collect_stats=True)
+        print("max group list", rt.last_stats["max_group_list"], "candidates per tile", rt.last_stats["candidates"] / max(rt.last_stats["tiles"], 1))
+        assert np.abs(imgs[0] - imgs[2]).max() <= 1e-5 and np.abs(imgs[1] - imgs[2]).max() <= 1e-5
+    scene.set_option("render_mode", 0)
+
+
 def test_attenuation_and_stats():
     import torch
     from rtgs.ray_tracer import RayTracer
