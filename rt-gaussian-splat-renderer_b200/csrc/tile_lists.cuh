@@ -51,6 +51,7 @@ __host__ __device__ constexpr int lists_single_bound(int tree_depth) {
 constexpr int GLIST_CAP = 960;
 constexpr int CQ_TILE = 64;                          // per-tile output queue of the fused four-tile filter (< 31 + 32)
 constexpr int CQ_CAP = TILES_PER_GROUP * CQ_TILE;    // the per-tile traversal uses it as one queue
+static_assert(TILES_PER_GROUP == 4, "lists_group: the second-chunk test is written for four tiles");
 static_assert(GLIST_CAP >= LISTS_STACK_CAP, "per-tile traversal keeps its stack in the group list");
 static_assert(CQ_CAP >= CHUNK_IDS + 4 * LISTS_TAKE, "per-tile traversal: a step may add 4 leaves per node");
 
@@ -272,8 +273,13 @@ __device__ __forceinline__ void lists_group(const RenderParams& P, ListsShared& 
             // past its 64 slots into its neighbour's - a dense cluster of Gaussians that all touch one tile)
 #pragma unroll
             for (int t = 0; t < TILES_PER_GROUP; ++t)
-                while (ok[t] && ncq[t] >= CHUNK_IDS)
-                    ok[t] = write_chunk(ws.cq + t * CQ_TILE, CHUNK_IDS, ncq[t], head[t], count[t]);
+                if (ncq[t] >= CHUNK_IDS) ok[t] = write_chunk(ws.cq + t * CQ_TILE, CHUNK_IDS, ncq[t], head[t], count[t]);
+            if (max(max(ncq[0], ncq[1]), max(ncq[2], ncq[3])) >= CHUNK_IDS) {   // rare: a second chunk
+#pragma unroll
+                for (int t = 0; t < TILES_PER_GROUP; ++t)
+                    if (ok[t] && ncq[t] >= CHUNK_IDS)
+                        ok[t] = write_chunk(ws.cq + t * CQ_TILE, CHUNK_IDS, ncq[t], head[t], count[t]);
+            }
         }
 #pragma unroll
         for (int t = 0; t < TILES_PER_GROUP; ++t) {
