@@ -46,13 +46,14 @@ for view, (th, ph, r, tgt) in enumerate(((0.3, 1.4, 2.2, None), (2.0, 1.0, 0.25,
     scene.set_option("render_mode", 0)
     import torch
     out = torch.empty((W, H, 3), dtype=torch.float32, device="cuda")
-    for hl in (0, 2):
-        scene.set_option("heavy_lists", hl)
+    for hl in (0, 2, -1):
+        scene.set_option("heavy_lists", max(hl, 0))
+        if hl < 0: rt = RayTracer((W, H), scene, cam, t_cut=1e-4)     # the default transmittance cut of bench.py / the CLI
         for _ in range(3): rt.render_device(16, out=out)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize(); e0.record()
         for _ in range(10): rt.render_device(16, out=out)
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 10
-        print(f"   heavy_lists {hl}: {ms:.3f} ms per frame = {W*H/ms/1e3:.0f} Mrays/s", flush=True)
+        print(f"   heavy_lists {max(hl, 0)} t_cut {rt.t_cut}: {ms:.3f} ms per frame = {W*H/ms/1e3:.0f} Mrays/s", flush=True)
     scene.set_option("heavy_lists", 0)
