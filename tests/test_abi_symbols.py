@@ -30,6 +30,22 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.rtgs_abi_version() == 3
 
 
+def test_struct_and_enum_mirrors_match_the_header():
+    """The ctypes mirrors in rtgs/_native.py are written by hand: field names and order of rtgs_render_stats (every
+    field uint64_t), and the option numbers, must be those of the header - a drifted mirror corrupts memory silently."""
+    from rtgs import _native
+    text = (ROOT / "include" / "rtgs_b200.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    body = re.search(r"typedef struct rtgs_render_stats \{(.*?)\} rtgs_render_stats;", text, flags=re.S).group(1)
+    decls = [d.strip() for d in body.split(";") if d.strip()]
+    assert all(d.startswith("uint64_t ") for d in decls)
+    assert [d.split()[1] for d in decls] == [n for n, _ in _native.rtgs_render_stats._fields_]
+    assert ctypes.sizeof(_native.rtgs_render_stats) == 8 * len(decls)
+    enum = dict(re.findall(r"\b(RTGS_OPT_[A-Z_]+)\s*=\s*(\d+)", text))
+    for name, value in enum.items():
+        assert getattr(_native, name[len("RTGS_"):]) == int(value), name
+
+
 def test_errors_are_reported_not_thrown(lib):
     # argument validation happens before any CUDA call, so this is safe without a GPU
     out = ctypes.c_void_p()
