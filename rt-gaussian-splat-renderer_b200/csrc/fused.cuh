@@ -146,6 +146,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
 
         TileRays ry;
         make_tile_rays(cam, i0, j0, pi, pj, active, ry);
+        // Distance pruning compares Euclidean box distances with ray parameters: distance = t |d|, and |d| is 1 only
+        // for a unit camera quaternion (the reference uses the rotation as given, camera.py:52).  len_max = the longest
+        // direction among the tile's rays (corners and centre, with a margin for the rays in between).
+        float len_max;
+        {
+            double l2 = d3dot(ry.d0, ry.d0);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const d3 e = cam_dir(cam, (double)(i0 + (k & 1) * TILE_I), (double)(j0 + (k >> 1) * TILE_J));
+                l2 = fmax(l2, d3dot(e, e));
+            }
+            len_max = (float)(sqrt(l2) * 1.0001);
+        }
         Frustum fr;
         make_frustum(cam, i0, i0 + TILE_I, j0, j0 + TILE_J, fr);
 
@@ -448,7 +461,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (K <= 16 ? 2 : 1)) k_rende
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) cm = fmaxf(cm, __shfl_xor_sync(FULL, cm, o));
                     if (cm >= 0.0f) {
-                        cm *= 1.0001f;
+                        cm *= 1.0001f * len_max;     // ray parameter -> distance
                         cut2 = cm * cm;
                     }
                     const bool open = active && !closed;

@@ -144,6 +144,37 @@ def test_dense_cluster_fills_one_tile_queue():
     scene.set_option("render_mode", 0)
 
 
+def test_camera_quaternion_is_used_as_given():
+    """The reference rotates the pinhole directions by the camera quaternion AS GIVEN (camera.py:52): a quaternion of
+    norm 1.67 stretches every direction, so ray parameters are not distances.  The fused kernel's distance pruning
+    compared the two (round 2 fuzz sweep: k_render alone, full hit buffers, error 0.45)."""
+    from rtgs.camera import Camera
+    from rtgs.orbit import focal_from_fov, orbit_pose
+    from rtgs.ray_tracer import RayTracer
+    gs = random_set(3000, seed=61059, mean_scale=0.12)
+    scene = make_scene(gs)
+    pos, rot = orbit_pose(1.3, 1.2, 2.5)
+    W, H = 230, 120
+    f = focal_from_fov(H, 25.0)
+    for norm in (1.67, 0.6):
+        rq = np.asarray(rot, np.float64) * norm
+        cam = Camera(pos, rq, (W, H), (f, f))
+        ocam = O.CameraParams(np.asarray(pos), rq, W, H, (f, f))
+        ref = O.render(gs, ocam, depth=16)
+        assert np.minimum(ref["nhit"], 16).mean() > 8          # the buffers fill: pruning is active
+        rt = RayTracer(cam.buf_size, scene, cam, t_cut=0.0)
+        for mode in (1, 0, 2):
+            scene.set_option("render_mode", mode)
+            mx, ps, bad = compare(rt.render(16), ref["rgb"], TOL)
+            assert mx <= TOL and ps >= 60.0, (norm, mode, mx, ps, bad)
+        scene.set_option("heavy_limit", 16)                    # the same through the hand-over route and the slab lists
+        for hl in (0, 2):
+            scene.set_option("render_mode", 0); scene.set_option("heavy_lists", hl)
+            mx, ps, bad = compare(rt.render(16), ref["rgb"], TOL)
+            assert mx <= TOL and ps >= 60.0, (norm, "heavy", hl, mx, ps, bad)
+        scene.set_option("heavy_limit", -1); scene.set_option("heavy_lists", 0)
+
+
 def test_attenuation_and_stats():
     import torch
     from rtgs.ray_tracer import RayTracer
